@@ -1,0 +1,145 @@
+/*
+ * nraps_mc.h -- C ABI of the B200 Monte Carlo k-eigenvalue transport path.
+ *
+ * Drop-in boundary for the reference's
+ *
+ *     pub fn monte_carlo(variables: &Variables, xsdata: &XSData, delta_x: &DeltaX,
+ *                        meshid: &Vec<Mesh>, fuel_indices: &Vec<usize>, k_new: f32)
+ *                        -> SolutionResults                (src/mc_code.rs:276-283)
+ *
+ * The reference has no FFI of its own; this header is what a Rust `extern "C"`
+ * block (rust/) binds.  Plain pointers and sizes only, no
+ * allocation crosses the boundary, every entry point returns an int status
+ * (the reference panics instead: src/mc_code.rs:302,332).
+ *
+ * All entry points require a CUDA device (sm_100a).  There is NO CPU fallback:
+ * without a usable device they return NRAPS_ERR_CUDA.
+ */
+#ifndef NRAPS_MC_H
+#define NRAPS_MC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRAPS_ABI_VERSION 1
+#define NRAPS_TALLY_FRAC_BITS 28 /* tallies are exact integers in 2^-28 cm */
+
+enum {
+    NRAPS_OK = 0,
+    NRAPS_ERR_NULL = 1,        /* a required pointer is NULL                   */
+    NRAPS_ERR_SHAPE = 2,       /* M/G/N/NF/numass/generations/skip out of range */
+    NRAPS_ERR_MESH = 3,        /* right[i] != left[i+1], matid >= M, fuel index >= N */
+    NRAPS_ERR_XS = 4,          /* inv_sigtr not finite-positive for a used material */
+    NRAPS_ERR_TOO_LARGE = 5,   /* tables do not fit the 227 KB shared-memory budget */
+    NRAPS_ERR_CUDA = 6,        /* CUDA runtime error (nraps_last_cuda_error())  */
+    NRAPS_ERR_OPTION = 7,      /* unknown mode in nraps_options                 */
+    NRAPS_ERR_STATE = 8,       /* call order violated                           */
+    NRAPS_ERR_IO = 9           /* host-side file error (nraps_host.h)           */
+};
+
+/*
+ * Flat views of the reference's in-memory contract.
+ *   Variables ......... src/main.rs:22-39      XSData .. src/main.rs:46-56
+ *   Mesh (AoS there) .. src/main.rs:68-75      DeltaX .. src/main.rs:41-44
+ * XS tables are indexed [mat + M*g]; scat is [G*G*mat + G*g_from + g_to]
+ * (src/mc_code.rs:89-98).  Inputs are borrowed for the duration of the call.
+ */
+typedef struct nraps_problem {
+    uint32_t M, G, N, NF, numass;
+    uint64_t generations, histories, skip;
+    float boundl, boundr, dx_fuel, dx_water, k0;
+    const float *sigt, *sigs, *mu, *siga, *sigf, *nut, *chit, *inv_sigtr; /* [M*G]   */
+    const float *scat;                                                     /* [M*G*G] */
+    const uint8_t *matid;                                                  /* [N]     */
+    const float *dx, *left, *right;                                        /* [N]     */
+    const uint64_t *fuel_indices;                                          /* [NF]    */
+} nraps_problem;
+
+enum { NRAPS_SCATTER_SINGLE_XI = 0, NRAPS_SCATTER_RUST_PRE182 = 1, NRAPS_SCATTER_RUST_182 = 2 };
+enum { NRAPS_SOURCE_UNIFORM_FUEL = 0, NRAPS_SOURCE_FISSION_BANK = 1 };
+enum { NRAPS_TRACK_SURFACE = 0, NRAPS_TRACK_WOODCOCK = 1 };
+enum { NRAPS_KERNEL_FUSED = 0, NRAPS_KERNEL_EVENT = 1 };
+
+typedef struct nraps_options {
+    uint64_t seed, stream, stride; /* PCG32 master (seed, sequence) and per-history jump; 0,0,0 => 42,54,152917 */
+    int32_t device;                /* CUDA ordinal                                    */
+    int32_t scatter_mode;          /* SURVEY 9-Q3; default single_xi                  */
+    int32_t stale_xs;              /* SURVEY 9-Q1; 1 = faithful to src/mc_code.rs:147 */
+    int32_t source_mode;
+    int32_t tracking_mode;
+    int32_t kernel_variant;
+    int32_t threads_per_block;     /* 0 = auto */
+    int32_t blocks_per_sm;         /* 0 = auto */
+    int32_t chunk;                 /* histories a warp claims per global atomic; 0 = auto */
+    int32_t quiet;                 /* 0 = print "running MC code" (src/mc_code.rs:292) */
+    uint64_t max_flights;          /* per-history safety cap; 0 = 1<<24               */
+} nraps_options;
+
+enum {
+    NRAPS_CT_HISTORIES = 0, NRAPS_CT_COLLISIONS, NRAPS_CT_CROSSINGS, NRAPS_CT_FLIGHTS,
+    NRAPS_CT_REFLECTIONS, NRAPS_CT_LEAKS, NRAPS_CT_TRUNCATED, NRAPS_CT_BANKED,
+    NRAPS_CT_WORDS
+};
+
+/* per-history replay record written by nraps_mc_trace (10 x u32) */
+enum {
+    NRAPS_TR_COLLISIONS = 0, NRAPS_TR_CROSSINGS, NRAPS_TR_FLIGHTS, NRAPS_TR_REFLECTIONS,
+    NRAPS_TR_RNG_LO, NRAPS_TR_RNG_HI, NRAPS_TR_CELL, NRAPS_TR_XBITS, NRAPS_TR_FATE, NRAPS_TR_GROUP,
+    NRAPS_TR_WORDS
+};
+enum { NRAPS_FATE_ABSORBED = 1, NRAPS_FATE_LEAKED = 2, NRAPS_FATE_TRUNCATED = 3 };
+
+/* SolutionResults, src/main.rs:77-83; row-major [g][cell]; caller-allocated. */
+typedef struct nraps_results {
+    float *flux, *assembly_average; /* [G*N]  */
+    float *fission_source;          /* [N]    */
+    float *k, *k_fund;              /* [generations] */
+    uint64_t *tally_fixed;          /* optional [generations][G][N], 2^-28 units (forces a sync per generation) */
+    uint64_t counters[NRAPS_CT_WORDS]; /* summed over generations; crossings/flights/reflections only in trace runs */
+    double seconds_device;          /* CUDA-event time of the generation loop */
+} nraps_results;
+
+typedef struct nraps_mc_ctx nraps_mc_ctx;
+
+/* Whole job on one GPU: the monte_carlo() replacement. */
+int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nraps_results *r);
+
+/*
+ * Generation-level API (one context per GPU / process).  A multi-GPU host
+ * shards [0, histories) across ranks, calls transport on its shard, sums the
+ * integer tally buffer across ranks (NCCL all-reduce on int64), then finalizes;
+ * every rank then holds identical k / flux.  `stream` is a cudaStream_t (NULL
+ * = default stream); calls are asynchronous unless stated.
+ */
+int nraps_mc_create(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **out);
+int nraps_mc_destroy(nraps_mc_ctx *ctx);
+int nraps_mc_reset(nraps_mc_ctx *ctx, float k0, void *stream);
+int nraps_mc_transport(nraps_mc_ctx *ctx, uint64_t gen, uint64_t hist_begin, uint64_t hist_count, void *stream);
+int nraps_mc_finalize_generation(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
+/* device buffer of G*N tally words followed by NRAPS_CT_WORDS counter words (uint64) */
+int nraps_mc_tally_buffer(nraps_mc_ctx *ctx, void **device_ptr, uint64_t *n_words);
+int nraps_mc_set_tally_buffer(nraps_mc_ctx *ctx, void *device_ptr); /* caller-owned, same size */
+int nraps_mc_read_tally(nraps_mc_ctx *ctx, uint64_t *host_words, void *stream);      /* synchronous */
+int nraps_mc_fetch(nraps_mc_ctx *ctx, nraps_results *r, void *stream);               /* synchronous */
+/* replay: run [hist_begin, hist_begin+hist_count) of `gen` and return one record per history (synchronous) */
+int nraps_mc_trace(nraps_mc_ctx *ctx, uint64_t gen, uint64_t hist_begin, uint64_t hist_count,
+                   uint32_t *host_records, void *stream);
+/* launch geometry chosen for this context: {grid, block, dynamic smem bytes, blocks/SM, SM count, chunk} */
+int nraps_mc_launch_info(nraps_mc_ctx *ctx, uint32_t out[6]);
+
+/* device-side unit probes for the golden-vector tests (each runs a 1-block kernel) */
+int nraps_dev_logf(const float *x, float *out, uint32_t n, int32_t device);
+int nraps_dev_pcg32(uint64_t seed, uint64_t stream, uint64_t stride, uint64_t hid, uint32_t n,
+                    uint32_t *out_u32, float *out_unit, int32_t device);
+
+const char *nraps_strerror(int code);
+const char *nraps_last_cuda_error(void);
+int nraps_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,523 @@
+// C-ABI layer: validation, derived tables, device residency, launch order.
+//
+// What is precomputed on the host (once per context) and why it is bit-safe:
+// every derived table is a pure function of the input tables evaluated with the
+// reference's own binary32 operations in the reference's order, so looking it
+// up on the device equals recomputing it per collision as the reference does.
+//   p_abs[xs]   = siga[xs] / sigt[xs] ...................... src/mc_code.rs:121
+//   scat_cdf[mat][g][xs_g][j] = cumsum_j(scat row (mat,g)) * (1/sigs[mat+M*xs_g])
+//                                                            src/mc_code.rs:89-100,190
+//   chi_cdf[mat][j] = cumsum_j chit[mat + M*j] .............. src/mc_code.rs:19-30
+//   run bounds per cell: first/last+1 cell of its material run (replaces the
+//   per-crossing matid compare of src/mc_code.rs:175-181)
+//   PCG32 jump table (A_b, C_b): the affine map of stride*2^b LCG steps
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mc_internal.h"
+
+using namespace nraps;
+
+namespace {
+
+thread_local std::string g_cuda_error;
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return NRAPS_ERR_CUDA;
+}
+
+#define CU(call)                                             \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+    } while (0)
+
+constexpr uint64_t kPcgMult = 6364136223846793005ULL;
+constexpr uint32_t kMaxSmem = 232448; // 227 KB opt-in limit per block on sm_100
+
+struct Pcg { uint64_t state, inc; };
+
+uint32_t pcg_step(Pcg &r)
+{
+    const uint64_t old = r.state;
+    r.state = old * kPcgMult + r.inc;
+    const uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
+    const uint32_t rot = (uint32_t)(old >> 59);
+    return (xs >> rot) | (xs << ((32u - rot) & 31u));
+}
+
+Pcg pcg_seed(uint64_t seed, uint64_t seq) // src/rand.rs:49-71 with an explicit seed
+{
+    Pcg r{0u, (seq << 1) | 1u};
+    pcg_step(r);
+    r.state += seed;
+    pcg_step(r);
+    return r;
+}
+
+// affine map of `delta` LCG steps: state' = mult*state + plus
+void pcg_jump_coeffs(uint64_t inc, uint64_t delta, uint64_t *mult, uint64_t *plus)
+{
+    uint64_t cm = kPcgMult, cp = inc, am = 1u, ap = 0u;
+    while (delta) {
+        if (delta & 1u) { am *= cm; ap = ap * cm + cp; }
+        cp = (cm + 1u) * cp;
+        cm *= cm;
+        delta >>= 1;
+    }
+    *mult = am;
+    *plus = ap;
+}
+
+template <typename T> cudaError_t upload(T **dst, const std::vector<T> &src)
+{
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), std::max<size_t>(1, src.size()) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (src.empty()) return cudaSuccess;
+    return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+} // namespace
+
+struct nraps_mc_ctx {
+    nraps_options opt{};
+    uint32_t M = 0, G = 0, N = 0, NF = 0, numass = 0;
+    uint64_t generations = 0, histories = 0, skip = 0;
+    float boundl = 0, boundr = 0, dx_fuel = 0, length = 0, nut_m1 = 0, k0 = 1.0f;
+    int device = 0, sm_count = 0;
+    Pcg master{};
+    uint64_t stride = 0;
+    SmemLayout layout{};
+    uint32_t grid = 0, block = 0, blocks_per_sm = 0, chunk = 0, max_flights = 0;
+
+    float *d_edges = nullptr, *d_xs = nullptr, *d_dx = nullptr, *d_nut = nullptr, *d_sigf = nullptr;
+    uint32_t *d_runb = nullptr;
+    uint8_t *d_matid = nullptr;
+    uint16_t *d_fuel = nullptr;
+    ulonglong2 *d_jump = nullptr;
+    unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
+    float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
+    uint32_t *d_trace = nullptr;
+    uint64_t trace_cap = 0;
+};
+
+namespace {
+
+int validate(const nraps_problem *p, const nraps_options *o)
+{
+    if (!p || !o) return NRAPS_ERR_NULL;
+    if (!p->sigt || !p->sigs || !p->mu || !p->siga || !p->sigf || !p->nut || !p->chit || !p->inv_sigtr || !p->scat ||
+        !p->matid || !p->dx || !p->left || !p->right || !p->fuel_indices)
+        return NRAPS_ERR_NULL;
+    // G >= 2: the flux conversion reads nut[M*1] (src/mc_code.rs:356); skip < generations: k_fund[skip] (:368)
+    if (p->M == 0 || p->M > 64 || p->G < 2 || p->G > 8 || p->N == 0 || p->N > 65535 || p->NF == 0 || p->numass == 0 ||
+        p->numass > p->N || p->generations == 0 || p->skip >= p->generations || p->histories == 0)
+        return NRAPS_ERR_SHAPE;
+    if ((uint64_t)p->M * p->G * p->G * p->G > 8192) return NRAPS_ERR_TOO_LARGE;
+    if (o->scatter_mode < 0 || o->scatter_mode > NRAPS_SCATTER_RUST_182) return NRAPS_ERR_OPTION;
+    if (o->source_mode != NRAPS_SOURCE_UNIFORM_FUEL || o->tracking_mode != NRAPS_TRACK_SURFACE ||
+        o->kernel_variant != NRAPS_KERNEL_FUSED)
+        return NRAPS_ERR_OPTION;
+    for (uint32_t i = 0; i < p->N; ++i) {
+        if (p->matid[i] >= p->M) return NRAPS_ERR_MESH;
+        if (i + 1 < p->N && std::memcmp(&p->right[i], &p->left[i + 1], sizeof(float)) != 0) return NRAPS_ERR_MESH;
+        if (!(p->right[i] > p->left[i])) return NRAPS_ERR_MESH;
+        for (uint32_t g = 0; g < p->G; ++g) {
+            const float v = p->inv_sigtr[p->matid[i] + p->M * g];
+            if (!(v > 0.0f) || !std::isfinite(v)) return NRAPS_ERR_XS;
+        }
+    }
+    for (uint32_t j = 0; j < p->NF; ++j)
+        if (p->fuel_indices[j] >= p->N) return NRAPS_ERR_MESH;
+    if (!(p->k0 > 0.0f) || !std::isfinite(p->k0)) return NRAPS_ERR_SHAPE;
+    return NRAPS_OK;
+}
+
+void free_ctx(nraps_mc_ctx *c)
+{
+    if (!c) return;
+    cudaFree(c->d_edges); cudaFree(c->d_xs); cudaFree(c->d_dx); cudaFree(c->d_nut); cudaFree(c->d_sigf);
+    cudaFree(c->d_runb); cudaFree(c->d_matid); cudaFree(c->d_fuel); cudaFree(c->d_jump);
+    cudaFree(c->d_tally_own); cudaFree(c->d_work); cudaFree(c->d_counters_total);
+    cudaFree(c->d_terms); cudaFree(c->d_res_flux); cudaFree(c->d_res_fission); cudaFree(c->d_k_hist); cudaFree(c->d_k_cur);
+    cudaFree(c->d_trace);
+    delete c;
+}
+
+int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count, bool trace, cudaStream_t s)
+{
+    if (begin > c->histories || count > c->histories - begin) return NRAPS_ERR_SHAPE;
+    const uint64_t words = (uint64_t)c->G * c->N + NRAPS_CT_WORDS;
+    CU(cudaMemsetAsync(c->d_tally, 0, words * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
+    if (count == 0) return NRAPS_OK;
+
+    TransportParams P{};
+    P.edges = c->d_edges; P.runb = c->d_runb; P.matid = c->d_matid; P.fuel = c->d_fuel; P.xs = c->d_xs; P.jump = c->d_jump;
+    P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF;
+    P.boundl = c->boundl; P.boundr = c->boundr; P.dx_fuel = c->dx_fuel;
+    // history (gen, y) owns the stream position (gen*H + y)*stride; the kernel adds the y part
+    uint64_t jm, jp;
+    pcg_jump_coeffs(c->master.inc, gen * c->histories * c->stride, &jm, &jp);
+    P.rng_state = jm * c->master.state + jp;
+    P.rng_inc = c->master.inc;
+    P.hist_begin = begin; P.hist_end = begin + count;
+    P.work = c->d_work; P.tally = c->d_tally;
+    P.trace = trace ? c->d_trace : nullptr;
+    P.chunk = c->chunk; P.max_flights = c->max_flights;
+    P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
+    CU(launch_transport(P, trace, dim3(c->grid), dim3(c->block), c->layout.total, s));
+    return NRAPS_OK;
+}
+
+} // namespace
+
+extern "C" int nraps_abi_version(void) { return NRAPS_ABI_VERSION; }
+extern "C" const char *nraps_last_cuda_error(void) { return g_cuda_error.c_str(); }
+
+extern "C" const char *nraps_strerror(int code)
+{
+    switch (code) {
+    case NRAPS_OK: return "ok";
+    case NRAPS_ERR_NULL: return "required pointer is NULL";
+    case NRAPS_ERR_SHAPE: return "problem dimensions out of range (need M in 1..64, G in 2..8, N in 1..65535, skip < generations)";
+    case NRAPS_ERR_MESH: return "mesh inconsistent (right[i] != left[i+1], matid >= M or fuel index >= N)";
+    case NRAPS_ERR_XS: return "inv_sigtr must be finite and positive for every material present in the mesh";
+    case NRAPS_ERR_TOO_LARGE: return "tables exceed the 227 KB shared-memory budget of one SM";
+    case NRAPS_ERR_CUDA: return "CUDA error (see nraps_last_cuda_error)";
+    case NRAPS_ERR_OPTION: return "unsupported value in nraps_options";
+    case NRAPS_ERR_STATE: return "call order violated";
+    case NRAPS_ERR_IO: return "file error";
+    default: return "unknown error";
+    }
+}
+
+extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **out)
+{
+    if (!out) return NRAPS_ERR_NULL;
+    *out = nullptr;
+    int rc = validate(p, o);
+    if (rc != NRAPS_OK) return rc;
+
+    const uint32_t M = p->M, G = p->G, N = p->N, NF = p->NF, MG = M * G;
+    const SmemLayout L = make_layout(M, G, N, NF);
+    if (L.total > kMaxSmem) return NRAPS_ERR_TOO_LARGE;
+
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (o->device < 0 || o->device >= ndev) return cuda_fail(cudaErrorInvalidDevice, "nraps_options.device");
+    CU(cudaSetDevice(o->device));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, o->device));
+    if (prop.major != 10) return cuda_fail(cudaErrorNoKernelImageForDevice, "this library is built for sm_100a only");
+
+    nraps_mc_ctx *c = new nraps_mc_ctx();
+    c->opt = *o;
+    c->M = M; c->G = G; c->N = N; c->NF = NF; c->numass = p->numass;
+    c->generations = p->generations; c->histories = p->histories; c->skip = p->skip;
+    c->boundl = p->boundl; c->boundr = p->boundr; c->dx_fuel = p->dx_fuel;
+    c->length = p->right[N - 1]; c->nut_m1 = p->nut[0 + M * 1]; c->k0 = p->k0;
+    c->device = o->device; c->sm_count = prop.multiProcessorCount;
+    const bool dflt = (o->seed == 0 && o->stream == 0 && o->stride == 0);
+    c->master = pcg_seed(dflt ? 42u : o->seed, dflt ? 54u : o->stream);
+    c->stride = dflt ? 152917u : o->stride;
+    c->layout = L;
+    c->max_flights = (uint32_t)std::min<uint64_t>(o->max_flights ? o->max_flights : (1ull << 24), 0xffffffffull);
+    c->chunk = o->chunk > 0 ? (uint32_t)o->chunk : 64u;
+
+    // launch geometry: persistent grid, a multiple of the SM count
+    uint32_t bps = o->blocks_per_sm > 0 ? (uint32_t)o->blocks_per_sm : 2u;
+    while (bps > 1 && (uint64_t)bps * (L.total + 1024) > 233472ull) --bps;
+    uint32_t threads = o->threads_per_block > 0 ? (uint32_t)o->threads_per_block : 1024u / bps;
+    threads = std::max(32u, std::min(1024u, threads / 32u * 32u));
+    c->blocks_per_sm = bps; c->block = threads; c->grid = (uint32_t)c->sm_count * bps;
+
+    // ---- derived tables
+    std::vector<float> edges(N + 1);
+    std::vector<uint32_t> runb(N);
+    std::vector<uint8_t> matid(p->matid, p->matid + N);
+    std::vector<uint16_t> fuel(NF);
+    for (uint32_t i = 0; i < N; ++i) edges[i] = p->left[i];
+    edges[N] = p->right[N - 1];
+    for (uint32_t i = 0; i < N;) {
+        uint32_t j = i;
+        while (j < N && p->matid[j] == p->matid[i]) ++j;
+        for (uint32_t q = i; q < j; ++q) runb[q] = i | (j << 16);
+        i = j;
+    }
+    for (uint32_t j = 0; j < NF; ++j) fuel[j] = (uint16_t)p->fuel_indices[j];
+
+    std::vector<float> xs(3 * MG + MG * G * G);
+    float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *scat_cdf = chi_cdf + MG;
+    for (uint32_t i = 0; i < MG; ++i) {
+        inv_sigtr[i] = p->inv_sigtr[i];
+        p_abs[i] = p->siga[i] / p->sigt[i];
+    }
+    for (uint32_t m = 0; m < M; ++m) {
+        float cum = 0.0f;
+        for (uint32_t g = 0; g < G; ++g) { cum = cum + p->chit[m + M * g]; chi_cdf[m * G + g] = cum; }
+        for (uint32_t g = 0; g < G; ++g)
+            for (uint32_t xg = 0; xg < G; ++xg) {
+                const float inv_sigs = 1.0f / p->sigs[m + M * xg];
+                float c2 = 0.0f;
+                for (uint32_t j = 0; j < G; ++j) {
+                    c2 = c2 + p->scat[G * G * m + G * g + j];
+                    scat_cdf[((m * G + g) * G + xg) * G + j] = c2 * inv_sigs;
+                }
+            }
+    }
+    std::vector<ulonglong2> jump(64);
+    {
+        uint64_t a, cc;
+        pcg_jump_coeffs(c->master.inc, c->stride, &a, &cc);
+        for (int b = 0; b < 64; ++b) {
+            jump[b].x = a; jump[b].y = cc;
+            cc = (a + 1u) * cc;
+            a = a * a;
+        }
+    }
+    std::vector<float> dx(p->dx, p->dx + N), nut(p->nut, p->nut + MG), sigf(p->sigf, p->sigf + MG);
+
+    const uint64_t GN = (uint64_t)G * N;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return r == cudaSuccess; };
+    ok(upload(&c->d_edges, edges)); ok(upload(&c->d_runb, runb)); ok(upload(&c->d_matid, matid));
+    ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump));
+    ok(upload(&c->d_dx, dx)); ok(upload(&c->d_nut, nut)); ok(upload(&c->d_sigf, sigf));
+    ok(cudaMalloc((void **)&c->d_tally_own, (GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
+    ok(cudaMalloc((void **)&c->d_work, sizeof(unsigned long long)));
+    ok(cudaMalloc((void **)&c->d_counters_total, NRAPS_CT_WORDS * sizeof(unsigned long long)));
+    ok(cudaMalloc((void **)&c->d_terms, GN * sizeof(float)));
+    ok(cudaMalloc((void **)&c->d_res_flux, GN * sizeof(float)));
+    ok(cudaMalloc((void **)&c->d_res_fission, N * sizeof(float)));
+    ok(cudaMalloc((void **)&c->d_k_hist, c->generations * sizeof(float)));
+    ok(cudaMalloc((void **)&c->d_k_cur, sizeof(float)));
+    ok(prepare_transport(L.total));
+    if (e != cudaSuccess) {
+        free_ctx(c);
+        return cuda_fail(e, "nraps_mc_create");
+    }
+    c->d_tally = c->d_tally_own;
+    rc = nraps_mc_reset(c, c->k0, nullptr);
+    if (rc != NRAPS_OK) { free_ctx(c); return rc; }
+    CU(cudaDeviceSynchronize());
+    *out = c;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_destroy(nraps_mc_ctx *ctx)
+{
+    if (!ctx) return NRAPS_ERR_NULL;
+    cudaSetDevice(ctx->device);
+    free_ctx(ctx);
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_reset(nraps_mc_ctx *c, float k0, void *stream)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU(cudaSetDevice(c->device));
+    const uint64_t GN = (uint64_t)c->G * c->N;
+    CU(cudaMemsetAsync(c->d_res_flux, 0, GN * sizeof(float), s));
+    CU(cudaMemsetAsync(c->d_res_fission, 0, c->N * sizeof(float), s));
+    CU(cudaMemsetAsync(c->d_k_hist, 0, c->generations * sizeof(float), s));
+    CU(cudaMemsetAsync(c->d_counters_total, 0, NRAPS_CT_WORDS * sizeof(unsigned long long), s));
+    CU(cudaMemcpyAsync(c->d_k_cur, &k0, sizeof(float), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s)); // k0 lives on the caller's stack
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t hist_begin, uint64_t hist_count, void *stream)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    CU(cudaSetDevice(c->device));
+    return run_transport(c, gen, hist_begin, hist_count, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nraps_mc_finalize_generation(nraps_mc_ctx *c, uint64_t gen, void *stream)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    if (gen >= c->generations) return NRAPS_ERR_SHAPE;
+    CU(cudaSetDevice(c->device));
+    FinalizeParams F{};
+    F.tally = c->d_tally; F.dx = c->d_dx; F.matid = c->d_matid; F.nusigf_nut = c->d_nut; F.sigf = c->d_sigf;
+    F.terms = c->d_terms; F.res_flux = c->d_res_flux; F.res_fission = c->d_res_fission;
+    F.k_hist = c->d_k_hist; F.k_cur = c->d_k_cur; F.counters_total = c->d_counters_total;
+    F.M = c->M; F.G = c->G; F.N = c->N;
+    F.histories_f32 = (float)c->histories;
+    F.length = c->length; F.nut_m1 = c->nut_m1;
+    // 1 / (generations - (skip - 1)) in wrapping usize arithmetic, src/mc_code.rs:340
+    F.fund = 1.0f / (float)(uint64_t)(c->generations - (c->skip - 1));
+    F.gen = gen; F.skip = c->skip;
+    CU(launch_finalize(F, static_cast<cudaStream_t>(stream)));
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_tally_buffer(nraps_mc_ctx *c, void **device_ptr, uint64_t *n_words)
+{
+    if (!c || !device_ptr || !n_words) return NRAPS_ERR_NULL;
+    *device_ptr = c->d_tally;
+    *n_words = (uint64_t)c->G * c->N + NRAPS_CT_WORDS;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_set_tally_buffer(nraps_mc_ctx *c, void *device_ptr)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    c->d_tally = device_ptr ? static_cast<unsigned long long *>(device_ptr) : c->d_tally_own;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_read_tally(nraps_mc_ctx *c, uint64_t *host_words, void *stream)
+{
+    if (!c || !host_words) return NRAPS_ERR_NULL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU(cudaSetDevice(c->device));
+    const uint64_t words = (uint64_t)c->G * c->N + NRAPS_CT_WORDS;
+    CU(cudaMemcpyAsync(host_words, c->d_tally, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_fetch(nraps_mc_ctx *c, nraps_results *r, void *stream)
+{
+    if (!c || !r || !r->flux || !r->assembly_average || !r->fission_source || !r->k || !r->k_fund) return NRAPS_ERR_NULL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU(cudaSetDevice(c->device));
+    const uint64_t GN = (uint64_t)c->G * c->N;
+    CU(cudaMemcpyAsync(r->flux, c->d_res_flux, GN * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(r->fission_source, c->d_res_fission, c->N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(r->k, c->d_k_hist, c->generations * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(r->counters, c->d_counters_total, NRAPS_CT_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // average_assembly (src/mc_code.rs:259-274) and k_fund (:368-376): O(G*N), O(gens^2) host work
+    const uint32_t span = c->N / c->numass;
+    for (uint32_t g = 0; g < c->G; ++g) {
+        const float *row = r->flux + (size_t)g * c->N;
+        float *dst = r->assembly_average + (size_t)g * c->N;
+        for (uint32_t i = 0; i < c->N; ++i) dst[i] = 0.0f;
+        for (uint32_t a = 0; a < c->numass; ++a) {
+            float acc = 0.0f;
+            for (uint32_t i = a * span; i < (a + 1) * span; ++i) acc = acc + row[i];
+            const float mean = acc / (float)span;
+            for (uint32_t i = a * span; i < (a + 1) * span; ++i) dst[i] = mean;
+        }
+    }
+    for (uint64_t n = 0; n < c->generations; ++n) r->k_fund[n] = 0.0f;
+    r->k_fund[c->skip] = r->k[c->skip];
+    for (uint64_t n = c->skip + 1; n < c->generations; ++n) {
+        float acc = 0.0f;
+        for (uint64_t j = c->skip; j <= n; ++j) acc = acc + r->k[j];
+        r->k_fund[n] = acc / (float)(uint64_t)(n - (c->skip - 1));
+    }
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_trace(nraps_mc_ctx *c, uint64_t gen, uint64_t hist_begin, uint64_t hist_count,
+                              uint32_t *host_records, void *stream)
+{
+    if (!c || !host_records) return NRAPS_ERR_NULL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU(cudaSetDevice(c->device));
+    if (hist_count > c->trace_cap) {
+        CU(cudaFree(c->d_trace));
+        c->d_trace = nullptr; c->trace_cap = 0;
+        CU(cudaMalloc((void **)&c->d_trace, hist_count * NRAPS_TR_WORDS * sizeof(uint32_t)));
+        c->trace_cap = hist_count;
+    }
+    if (hist_count) CU(cudaMemsetAsync(c->d_trace, 0, hist_count * NRAPS_TR_WORDS * sizeof(uint32_t), s));
+    int rc = run_transport(c, gen, hist_begin, hist_count, true, s);
+    if (rc != NRAPS_OK) return rc;
+    if (hist_count)
+        CU(cudaMemcpyAsync(host_records, c->d_trace, hist_count * NRAPS_TR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_launch_info(nraps_mc_ctx *c, uint32_t out[6])
+{
+    if (!c || !out) return NRAPS_ERR_NULL;
+    out[0] = c->grid; out[1] = c->block; out[2] = c->layout.total; out[3] = c->blocks_per_sm;
+    out[4] = (uint32_t)c->sm_count; out[5] = c->chunk;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nraps_results *r)
+{
+    if (!p || !o || !r) return NRAPS_ERR_NULL;
+    if (!r->flux || !r->assembly_average || !r->fission_source || !r->k || !r->k_fund) return NRAPS_ERR_NULL;
+    nraps_mc_ctx *c = nullptr;
+    int rc = nraps_mc_create(p, o, &c);
+    if (rc != NRAPS_OK) return rc;
+    if (!o->quiet) { std::printf("running MC code\n"); std::fflush(stdout); } // src/mc_code.rs:292
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t s = nullptr;
+    auto bail = [&](int code) {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (s) cudaStreamDestroy(s);
+        nraps_mc_destroy(c);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess ||
+        cudaEventCreate(&e1) != cudaSuccess)
+        return bail(cuda_fail(cudaGetLastError(), "stream/event create"));
+    cudaEventRecord(e0, s);
+    const uint64_t GN = (uint64_t)p->G * p->N;
+    std::vector<uint64_t> words(r->tally_fixed ? GN + NRAPS_CT_WORDS : 0);
+    for (uint64_t gen = 0; gen < p->generations; ++gen) {
+        if ((rc = nraps_mc_transport(c, gen, 0, p->histories, s)) != NRAPS_OK) return bail(rc);
+        if (r->tally_fixed) {
+            if ((rc = nraps_mc_read_tally(c, words.data(), s)) != NRAPS_OK) return bail(rc);
+            std::memcpy(r->tally_fixed + gen * GN, words.data(), GN * sizeof(uint64_t));
+        }
+        if ((rc = nraps_mc_finalize_generation(c, gen, s)) != NRAPS_OK) return bail(rc);
+    }
+    cudaEventRecord(e1, s);
+    if ((rc = nraps_mc_fetch(c, r, s)) != NRAPS_OK) return bail(rc);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    r->seconds_device = 1e-3 * (double)ms;
+    return bail(NRAPS_OK);
+}
+
+extern "C" int nraps_dev_logf(const float *x, float *out, uint32_t n, int32_t device)
+{
+    if (!x || !out) return NRAPS_ERR_NULL;
+    CU(cudaSetDevice(device));
+    float *dx = nullptr, *dout = nullptr;
+    CU(cudaMalloc((void **)&dx, std::max<size_t>(1, n) * sizeof(float)));
+    CU(cudaMalloc((void **)&dout, std::max<size_t>(1, n) * sizeof(float)));
+    CU(cudaMemcpy(dx, x, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_probe_logf(dx, dout, n, nullptr));
+    CU(cudaMemcpy(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dout);
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_dev_pcg32(uint64_t seed, uint64_t stream, uint64_t stride, uint64_t hid, uint32_t n,
+                               uint32_t *out_u32, float *out_unit, int32_t device)
+{
+    if (!out_u32 || !out_unit) return NRAPS_ERR_NULL;
+    CU(cudaSetDevice(device));
+    Pcg m = pcg_seed(seed, stream);
+    uint64_t jm, jp;
+    pcg_jump_coeffs(m.inc, hid * stride, &jm, &jp);
+    uint32_t *du = nullptr;
+    float *df = nullptr;
+    CU(cudaMalloc((void **)&du, std::max<size_t>(1, n) * sizeof(uint32_t)));
+    CU(cudaMalloc((void **)&df, std::max<size_t>(1, n) * sizeof(float)));
+    CU(launch_probe_pcg(jm * m.state + jp, m.inc, n, du, df, nullptr));
+    CU(cudaMemcpy(out_u32, du, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_unit, df, n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(du); cudaFree(df);
+    return NRAPS_OK;
+}

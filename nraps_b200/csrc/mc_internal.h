@@ -1,0 +1,89 @@
+// Internal contract between the C-ABI layer (mc_api.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/nraps_mc.h"
+
+namespace nraps {
+
+constexpr float kTallyScale = 268435456.0f; // 2^NRAPS_TALLY_FRAC_BITS
+constexpr double kTallyInvScale = 1.0 / 268435456.0;
+
+// Byte offsets of the per-block shared-memory image.  Everything a history
+// touches between birth and death lives here; HBM is only read at block start
+// (tables, ~N*11 bytes) and written at block end (tally flush).
+struct SmemLayout {
+    uint32_t tally_lo, tally_hi; // u32[G*N] each: 64-bit fixed-point bins split in two words
+    uint32_t edges;              // f32[N+1]   cell edges; left[i]=edges[i], right[i]=edges[i+1]
+    uint32_t runb;               // u32[N]     material-run bounds of each cell: lo | hi<<16
+    uint32_t jump;               // u64x2[64]  PCG32 jump table (A_b, C_b) for stride*2^b draws
+    uint32_t xs;                 // f32[...]   inv_sigtr[MG] | p_abs[MG] | chi_cdf[MG] | scat_cdf[M*G*G*G]
+    uint32_t fuel;               // u16[NF]    fuel cell indices
+    uint32_t matid;              // u8[N]
+    uint32_t total;
+};
+
+__host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t NF)
+{
+    SmemLayout L;
+    uint32_t off = 0;
+    L.jump = off;     off += 64 * 16;
+    L.tally_lo = off; off += G * N * 4;
+    L.tally_hi = off; off += G * N * 4;
+    L.edges = off;    off += (N + 1) * 4;
+    L.runb = off;     off += N * 4;
+    L.xs = off;       off += (3 * M * G + M * G * G * G) * 4;
+    L.fuel = off;     off += align_up(NF * 2, 4);
+    L.matid = off;    off += align_up(N, 4);
+    L.total = align_up(off, 16);
+    return L;
+}
+
+struct TransportParams {
+    // read-only tables in global memory (device pointers)
+    const float *edges;
+    const uint32_t *runb;
+    const uint8_t *matid;
+    const uint16_t *fuel;
+    const float *xs;
+    const ulonglong2 *jump;
+    uint32_t M, G, N, NF;
+    float boundl, boundr, dx_fuel;
+    uint64_t rng_state; // master stream advanced to history 0 of this generation
+    uint64_t rng_inc;
+    uint64_t hist_begin, hist_end; // this launch covers y in [hist_begin, hist_end)
+    unsigned long long *work;      // chunk cursor, zeroed before launch
+    unsigned long long *tally;     // [G*N] + counters[NRAPS_CT_WORDS]
+    uint32_t *trace;               // [hist_end-hist_begin][NRAPS_TR_WORDS] or nullptr
+    uint32_t chunk;
+    uint32_t max_flights;
+    int32_t scatter_mode, stale_xs;
+};
+
+struct FinalizeParams {
+    const unsigned long long *tally; // [G*N]
+    const float *dx;                 // [N]
+    const uint8_t *matid;            // [N]
+    const float *nusigf_nut;         // nut[MG]
+    const float *sigf;               // sigf[MG]
+    float *terms;                    // scratch [G*N]
+    float *res_flux;                 // [G*N]
+    float *res_fission;              // [N]
+    float *k_hist;                   // [generations]
+    float *k_cur;                    // [1]
+    unsigned long long *counters_total; // [NRAPS_CT_WORDS], summed over generations
+    uint32_t M, G, N;
+    float histories_f32, length, nut_m1, fund;
+    uint64_t gen, skip;
+};
+
+cudaError_t launch_transport(const TransportParams &p, bool trace, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
+cudaError_t prepare_transport(uint32_t smem_bytes);
+cudaError_t launch_finalize(const FinalizeParams &p, cudaStream_t s);
+cudaError_t launch_probe_logf(const float *x, float *out, uint32_t n, cudaStream_t s);
+cudaError_t launch_probe_pcg(uint64_t state, uint64_t inc, uint32_t n, uint32_t *out_u32, float *out_unit, cudaStream_t s);
+
+} // namespace nraps

@@ -1,0 +1,84 @@
+// `nraps` driver: the reference binary's intended pipeline (its commented-out
+// main, src/main.rs:332-364) with the Monte Carlo solver running on a B200:
+//   process_input -> mesh_gen -> monte_carlo -> plot_solution (three CSV files)
+// Usage: nraps [deck] [--out DIR] [--generations N] [--histories N] [--skip N]
+//              [--seed S --stream Q --stride T] [--device D] [--scatter single_xi|rust_pre182|rust_182]
+//              [--fix-stale-xs] [--quiet]
+// The deck defaults to ./TestCaseC.txt like the reference (src/process_input.rs:86).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nraps_host.h"
+
+int main(int argc, char **argv)
+{
+    std::string deck_path = "./TestCaseC.txt", out_dir = ".";
+    nraps_options opt{};
+    opt.stale_xs = 1;
+    long long gens = -1, hist = -1, skip = -1;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&](const char *what) -> const char * {
+            if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", what); std::exit(2); }
+            return argv[++i];
+        };
+        if (a == "--out") out_dir = next("--out");
+        else if (a == "--generations") gens = std::atoll(next("--generations"));
+        else if (a == "--histories") hist = std::atoll(next("--histories"));
+        else if (a == "--skip") skip = std::atoll(next("--skip"));
+        else if (a == "--seed") opt.seed = std::strtoull(next("--seed"), nullptr, 10);
+        else if (a == "--stream") opt.stream = std::strtoull(next("--stream"), nullptr, 10);
+        else if (a == "--stride") opt.stride = std::strtoull(next("--stride"), nullptr, 10);
+        else if (a == "--device") opt.device = std::atoi(next("--device"));
+        else if (a == "--fix-stale-xs") opt.stale_xs = 0;
+        else if (a == "--quiet") opt.quiet = 1;
+        else if (a == "--scatter") {
+            const std::string m = next("--scatter");
+            opt.scatter_mode = m == "rust_pre182" ? NRAPS_SCATTER_RUST_PRE182 : m == "rust_182" ? NRAPS_SCATTER_RUST_182 : NRAPS_SCATTER_SINGLE_XI;
+        } else if (a[0] != '-') deck_path = a;
+        else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+
+    const auto t0 = std::chrono::steady_clock::now();
+    nraps_deck deck;
+    int rc = nraps_process_input(deck_path.c_str(), &deck);
+    if (rc != NRAPS_OK) { std::fprintf(stderr, "process_input(%s): %s\n", deck_path.c_str(), nraps_strerror(rc)); return 1; }
+    if (gens >= 0) deck.generations = (uint64_t)gens;
+    if (hist >= 0) deck.histories = (uint64_t)hist;
+    if (skip >= 0) deck.skip = (uint64_t)skip;
+
+    nraps_mesh mesh;
+    rc = nraps_mesh_gen(deck.matid, deck.n_matid, deck.mpfr, deck.mpwr, deck.numass, deck.dx_fuel, deck.dx_water, &mesh);
+    if (rc != NRAPS_OK) { std::fprintf(stderr, "mesh_gen: %s\n", nraps_strerror(rc)); return 1; }
+
+    nraps_problem prob;
+    rc = nraps_problem_from(&deck, &mesh, 1.0f, &prob); // k_new = 1.0, src/main.rs:337
+    if (rc != NRAPS_OK) { std::fprintf(stderr, "problem: %s\n", nraps_strerror(rc)); return 1; }
+
+    const size_t GN = (size_t)prob.G * prob.N;
+    std::vector<float> flux(GN), avg(GN), fis(prob.N), k(prob.generations), kf(prob.generations);
+    nraps_results res{};
+    res.flux = flux.data(); res.assembly_average = avg.data(); res.fission_source = fis.data();
+    res.k = k.data(); res.k_fund = kf.data();
+    rc = nraps_mc_run(&prob, &opt, &res);
+    if (rc != NRAPS_OK) {
+        std::fprintf(stderr, "monte_carlo: %s %s\n", nraps_strerror(rc), rc == NRAPS_ERR_CUDA ? nraps_last_cuda_error() : "");
+        return 1;
+    }
+    rc = nraps_plot_solution(&res, prob.G, prob.generations, prob.N, (double)mesh.right[mesh.N - 1], out_dir.c_str());
+    if (rc != NRAPS_OK) { std::fprintf(stderr, "plot_solution: %s\n", nraps_strerror(rc)); return 1; }
+
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double total = (double)prob.histories * (double)prob.generations;
+    std::printf("Run was completed in %lld milliseconds \n", (long long)(wall * 1e3)); // src/main.rs:366-369
+    std::fprintf(stderr, "{\"k_fund\": %.7g, \"histories_per_s\": %.6g, \"device_s\": %.6g, \"collisions_per_history\": %.6g}\n",
+                 (double)kf[prob.generations - 1], total / res.seconds_device, res.seconds_device,
+                 (double)res.counters[NRAPS_CT_COLLISIONS] / total);
+    nraps_mesh_free(&mesh);
+    nraps_deck_free(&deck);
+    return 0;
+}

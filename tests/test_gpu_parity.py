@@ -1,0 +1,236 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs.  Integer results (event counts, RNG
+states, fixed-point tally bins) and everything derived from them with the
+reference's binary32 arithmetic (k, flux, fission source, CSV bytes) must be
+BIT-EXACT.  Statistical agreement between independent streams is stated at
+3 sigma combined / per-bin chi-square."""
+import numpy as np
+import pytest
+
+import nraps_b200 as nb
+from nraps_b200 import _lib
+from oracle import host_oracle as ho
+from oracle import oracle as orc
+from tests.util import bits, load_case, oracle_inputs
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def _both(case, *, generations, histories, skip=1, oracle_kw=None, gpu_kw=None, threads=8, **common):
+    v, xs, dx, mesh, fuel = load_case(case)
+    got = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=generations, histories=histories, skip=skip,
+                         want_tally=True, **common, **(gpu_kw or {}))
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    okw = dict(common)
+    if "stream" in okw:
+        okw["seq"] = okw.pop("stream")
+    want = orc.monte_carlo(deck, m, generations=generations, histories=histories, skip=skip, threads=threads,
+                           want_tally=True, **okw, **(oracle_kw or {}))
+    return got, want
+
+
+def _assert_identical(got, want):
+    assert np.array_equal(got.tally_fixed, want.tally_fixed)
+    for name in ("k", "k_fund", "flux", "assembly_average", "fission_source"):
+        assert np.array_equal(bits(getattr(got, name)), bits(getattr(want, name))), name
+    for c in ("histories", "collisions", "flights", "leaks", "truncated"):
+        assert got.counters[c] == want.counters[c], c
+
+
+def test_device_logf_bit_exact():
+    rng = np.random.default_rng(0)
+    k = np.r_[rng.integers(0, 1 << 23, 2_000_000), 0, 1, 2, (1 << 23) - 1, (1 << 22), (1 << 22) - 1, 5931641, 5931642, 5931643]
+    x = ((k.astype(f32) + f32(0.5)) * f32(2.0 ** -23)).astype(f32)
+    got = nb.dev_logf(x)
+    L = orc.lib()
+    want = np.array([L.oracle_logf_f(float(v)) for v in x[:200_000]], f32)
+    assert np.array_equal(bits(got[:200_000]), bits(want))
+    tail = np.array([L.oracle_logf_f(float(v)) for v in x[-9:]], f32)
+    assert np.array_equal(bits(got[-9:]), bits(tail))
+    assert np.max(np.abs(got.astype(np.float64) - np.log(x.astype(np.float64))) / np.spacing(np.abs(np.log(x.astype(np.float64))).astype(f32))) < 1.0
+
+
+def test_device_pcg32_streams():
+    import ctypes as C
+    u, xi = nb.dev_pcg32(42, 54, 152917, 0, 6)
+    assert [hex(v) for v in u] == ["0xa15c02b7", "0x7b47f409", "0xba1d3330", "0x83d2f293", "0xbfa4784b", "0xcbed606e"]
+    for hid in (1, 12345, 10**7 * 200 - 1, 2**40 + 17):
+        u, xi = nb.dev_pcg32(42, 54, 152917, hid, 64)
+        st = (C.c_uint64 * 2)()
+        orc.lib().oracle_pcg32_state(42, 54, (hid * 152917) % 2**64, st)
+        state, inc, out = st[0], st[1], []
+        for _ in range(64):
+            old = state
+            state = (old * 6364136223846793005 + inc) % 2**64
+            xs_ = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
+            rot = old >> 59
+            out.append(((xs_ >> rot) | (xs_ << ((32 - rot) & 31))) & 0xFFFFFFFF)
+        assert u.tolist() == out
+        assert np.array_equal(xi, ((np.array(out, np.uint64) >> 9).astype(f32) + f32(0.5)) * f32(2.0 ** -23))
+        assert np.all((xi > 0) & (xi < 1) & (xi != 0.5))
+
+
+@pytest.mark.parametrize("case,gen", [("a", 0), ("b", 3), ("c", 0), ("c", 7)])
+def test_replay_every_history_bit_exact(case, gen):
+    """Per-history collisions / crossings / flights / reflections, final RNG state, cell, x bits, fate, group."""
+    v, xs, dx, mesh, fuel = load_case(case)
+    H = 100_000
+    with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gen + 1, histories=H, skip=0) as ctx:
+        rec = ctx.trace(gen, 0, H)
+        tally, counters = ctx.read_tally()
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=gen + 1, histories=H, skip=0, threads=8, trace_gen=gen, want_tally=True)
+    assert np.array_equal(rec, want.trace)
+    assert np.array_equal(tally, want.tally_fixed[gen])
+    assert counters["crossings"] == int(want.trace[:, 1].sum()) and counters["collisions"] == int(want.trace[:, 0].sum())
+    assert rec[:, 0].max() > 100 and rec[:, 8].min() == 1  # long tails exist; every history was absorbed
+
+
+@pytest.mark.parametrize("case,H,gens,skip", [("a", 100_000, 6, 4), ("b", 150_000, 3, 1), ("c", 150_000, 3, 1)])
+def test_results_bit_exact(case, H, gens, skip):
+    got, want = _both(case, generations=gens, histories=H, skip=skip)
+    _assert_identical(got, want)
+
+
+def test_csv_output_bytes_identical(tmp_path):
+    got, want = _both("c", generations=4, histories=50_000, skip=1)
+    v, xs, dx, mesh, fuel = load_case("c")
+    nb.plot_solution(got, v.energygroups, 4, len(mesh), float(mesh.mesh_right[-1]), str(tmp_path))
+    files = ho.csv_files(want.flux, want.assembly_average, want.fission_source, want.k, want.k_fund, mesh.mesh_right[-1], len(mesh), 4)
+    for name, text in files.items():
+        assert (tmp_path / name).read_text() == text, name
+
+
+@pytest.mark.parametrize("mode", ["rust_pre182", "rust_182"])
+def test_scatter_probe_orders_bit_exact(mode):
+    got, want = _both("c", generations=2, histories=60_000, scatter_mode=mode)
+    _assert_identical(got, want)
+
+
+def test_fixed_stale_xs_switch_bit_exact():
+    got, want = _both("c", generations=2, histories=60_000, stale_xs=False)
+    _assert_identical(got, want)
+    base, _ = _both("c", generations=2, histories=60_000)
+    assert float(np.mean(got.k)) < float(np.mean(base.k)) - 0.03  # fixing the stale index lowers k_C by ~0.08
+
+
+def test_other_seeds_and_strides_bit_exact():
+    got, want = _both("b", generations=2, histories=40_000, seed=7, stream=11, stride=100_003)
+    _assert_identical(got, want)
+
+
+def _with_bounds(case, boundl, boundr):
+    v, xs, dx, mesh, fuel = load_case(case)
+    v.boundl, v.boundr = boundl, boundr
+    return v, xs, dx, mesh, fuel
+
+
+@pytest.mark.parametrize("bl,br", [(0.0, 0.0), (0.5, 1.0), (1.0, 0.0)])
+def test_vacuum_and_albedo_boundaries_bit_exact(bl, br):
+    args = _with_bounds("a", bl, br)
+    got = nb.monte_carlo(*args, 1.0, generations=2, histories=50_000, skip=1, want_tally=True)
+    deck, m = oracle_inputs(*args)
+    want = orc.monte_carlo(deck, m, generations=2, histories=50_000, skip=1, threads=8, want_tally=True)
+    _assert_identical(got, want)
+    if bl == 0.0 or br == 0.0:
+        assert got.counters["leaks"] > 0
+
+
+def test_launch_geometry_and_sharding_do_not_change_a_bit():
+    v, xs, dx, mesh, fuel = load_case("c")
+    H = 70_001
+    ref = None
+    for kw in [dict(), dict(threads_per_block=256, blocks_per_sm=4, chunk=32), dict(threads_per_block=1024, blocks_per_sm=1, chunk=1000),
+               dict(threads_per_block=64, blocks_per_sm=1, chunk=1)]:
+        with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=H, skip=1, **kw) as ctx:
+            ctx.transport(1)
+            tally, counters = ctx.read_tally()
+            assert counters["histories"] == H
+            if ref is None:
+                ref = tally.copy()
+                # two shards of the same generation sum to the whole (what multi-GPU relies on)
+                ctx.transport(1, 0, 12_345)
+                a, _ = ctx.read_tally()
+                ctx.transport(1, 12_345, H - 12_345)
+                b, _ = ctx.read_tally()
+                assert np.array_equal(a + b, ref)
+                ctx.transport(1, 500, 0)
+                z, cz = ctx.read_tally()
+                assert not z.any() and cz["histories"] == 0
+            assert np.array_equal(tally, ref), kw
+
+
+def test_single_history_and_flight_cap():
+    got, want = _both("a", generations=2, histories=1, skip=1)
+    _assert_identical(got, want)
+    got, want = _both("c", generations=1, histories=5_000, skip=0, max_flights=20)
+    _assert_identical(got, want)
+    assert got.counters["truncated"] > 0
+
+
+def test_fine_mesh_bit_exact():
+    v, xs, dx, mesh, fuel = load_case("c", mpfr=80, mpwr=40)
+    got = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=20_000, skip=1, want_tally=True)
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=2, histories=20_000, skip=1, threads=8, want_tally=True)
+    _assert_identical(got, want)
+
+
+def test_statistical_parity_independent_streams():
+    """k within 3 sigma combined and per-bin chi-square between the GPU (seed 1) and the oracle (seed 2)."""
+    v, xs, dx, mesh, fuel = load_case("c")
+    gens, H = 12, 100_000
+    got = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1, want_tally=True, seed=1, stream=3, stride=152917)
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=gens, histories=H, skip=1, threads=8, want_tally=True, seed=2, seq=5)
+    kg, ko = got.k.astype(np.float64), want.k.astype(np.float64)
+    sigma = np.hypot(kg.std(ddof=1), ko.std(ddof=1)) / np.sqrt(gens)
+    assert abs(kg.mean() - ko.mean()) < 3 * sigma, (kg.mean(), ko.mean(), sigma)
+    tg = got.tally_fixed.astype(np.float64).reshape(gens, -1)
+    to = want.tally_fixed.astype(np.float64).reshape(gens, -1)
+    var = (tg.var(axis=0, ddof=1) + to.var(axis=0, ddof=1)) / gens
+    z2 = (tg.mean(axis=0) - to.mean(axis=0)) ** 2 / var
+    chi2, dof = z2.sum(), z2.size
+    assert abs(chi2 - dof) < 5 * np.sqrt(2 * dof) * 1.2, (chi2, dof)  # ~t-distributed terms: slightly heavier than chi2
+
+
+def test_config3_size_properties():
+    """BASELINE config 3 at full size (10^7 histories/generation): size-independent properties."""
+    v, xs, dx, mesh, fuel = load_case("c")
+    H = 10_000_000
+    with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=200, histories=H, skip=1) as ctx:
+        ctx.transport(199)
+        tally, counters = ctx.read_tally()
+        ctx.finalize_generation(199)
+        k = ctx.fetch().k[199]
+        assert counters["histories"] == H and counters["truncated"] == 0 and counters["leaks"] == 0
+        assert abs(counters["collisions"] / H - 29.55) < 0.05
+        assert abs(float(k) - 1.8226) < 0.004  # survey anchor +- ~6 sigma of one 10^7 generation
+        # determinism: a second pass of the same generation gives the same bins, whatever the scheduling
+        ctx.transport(199)
+        again, _ = ctx.read_tally()
+        assert np.array_equal(tally, again)
+        # k is the nu-fission-weighted tally sum / H (k cancels, src/mc_code.rs:346-351)
+        nusigf = (xs.nut * xs.sigf).reshape(v.energygroups, v.mattypes)[:, mesh.matid]
+        k64 = float((tally.astype(np.float64) * 2.0 ** -28 * nusigf).sum() / H)
+        assert abs(k64 - float(k)) < 2e-5 * k64
+
+
+def test_error_codes():
+    v, xs, dx, mesh, fuel = load_case("a")
+    with pytest.raises(_lib.NrapsError) as e:
+        nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=3, histories=10, skip=3)
+    assert e.value.code == 2  # skip >= generations: the reference panics at k_fund[skip]
+    bad = nb.Mesh(mesh.matid.copy(), mesh.delta_x, mesh.mesh_left, mesh.mesh_right.copy())
+    bad.mesh_right[10] += f32(1e-3)
+    with pytest.raises(_lib.NrapsError) as e:
+        nb.monte_carlo(v, xs, dx, bad, fuel, 1.0, generations=2, histories=10, skip=1)
+    assert e.value.code == 3
+    xs2 = nb.XSData(**{**xs.__dict__, "inv_sigtr": xs.inv_sigtr * f32(-1)})
+    with pytest.raises(_lib.NrapsError) as e:
+        nb.monte_carlo(v, xs2, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1)
+    assert e.value.code == 4
+    with pytest.raises(_lib.NrapsError) as e:
+        nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1, device=99)
+    assert e.value.code == 6

@@ -1,0 +1,174 @@
+"""Host side of the path on CPU: C-ABI symbols, deck parser, mesh_gen, CSV
+output -- product C++ (through libnraps_b200.so) against the numpy restatement
+in oracle/host_oracle.py and the structural fixtures of SURVEY section 8c."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nraps_b200 as nb
+from nraps_b200 import _lib
+from oracle import host_oracle as ho
+from oracle import oracle as orc
+from tests.util import DECKS, ROOT, bits, load_case
+
+f32 = np.float32
+
+
+def test_library_exports_every_declared_symbol():
+    declared = set()
+    for h in ("nraps_mc.h", "nraps_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(nraps_[a-z0-9_]+)\s*\(", src))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.nraps_abi_version() == 1
+
+
+def test_mc_entry_points_fail_loudly_without_arguments_or_gpu():
+    L = _lib.lib()
+    assert L.nraps_mc_run(None, None, None) == 1  # NRAPS_ERR_NULL, before any CUDA call
+    h = C.c_void_p()
+    assert L.nraps_mc_create(None, None, C.byref(h)) == 1
+    assert L.nraps_strerror(5).decode().startswith("tables exceed")
+
+
+@pytest.mark.parametrize("case", "abc")
+def test_process_input_matches_numpy_restatement(case):
+    v, xs, pins, dx, sol, solver = nb.process_input(DECKS[case])
+    d = ho.process_input(DECKS[case])
+    for name in ("analk", "mattypes", "energygroups", "generations", "histories", "skip", "numass", "numrods", "mpfr", "mpwr"):
+        assert getattr(v, name) == getattr(d, name), name
+    for name in ("roddia", "rodpitch", "boundl", "boundr"):
+        assert f32(getattr(v, name)) == getattr(d, name), name
+    assert f32(dx.fuel) == d.dx_fuel and f32(dx.water) == d.dx_water
+    for a, b in [(xs.sigt, d.sigt), (xs.sigs, d.sigs), (xs.mu, d.mu), (xs.siga, d.siga), (xs.sigf, d.sigf),
+                 (xs.nut, d.nut), (xs.chit, d.chit), (xs.scat_matrix, d.scat), (xs.inv_sigtr, d.inv_sigtr)]:
+        assert np.array_equal(bits(a), bits(b))
+    assert np.array_equal(pins, d.matid) and sol == d.solution and solver == d.solver
+    G, M = v.energygroups, v.mattypes
+    assert len(xs.sigt) == M * G and len(xs.scat_matrix) == M * G * G and len(pins) == 70
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference decks only exist in the build container")
+@pytest.mark.parametrize("case", "abc")
+def test_fixture_decks_carry_the_reference_payload(case):
+    ref = nb.process_input(f"/root/reference/TestCase{case.upper()}.txt")
+    fix = nb.process_input(DECKS[case])
+    assert ref[0] == fix[0] and ref[3] == fix[3] and ref[4:] == fix[4:]
+    for name in ("sigt", "sigs", "mu", "siga", "sigf", "nut", "chit", "scat_matrix", "inv_sigtr"):
+        assert np.array_equal(bits(getattr(ref[1], name)), bits(getattr(fix[1], name)))
+    assert np.array_equal(ref[2], fix[2])
+
+
+def test_parser_quirks(tmp_path):
+    """src/process_input.rs:44-83: '#' kills a pending key=value; the byte after a comment line is
+    never inspected; repeated keys concatenate; keys match on (last two chars, length) only."""
+    base = open(DECKS["a"]).read()
+    deck = tmp_path / "quirks.txt"
+    text = base.replace("Histories = 100000\n", "Histories = 5 # trailing comment discards this line\nHistories = 777\n")
+    # the first byte after a comment line is never inspected, so this '#' does not start a comment and the
+    # 4-char key "#kip" lands in the Skip slot ("ip", 4)
+    text = text.replace("Skip = 4\n", "# comment line\n#kip = 4\n")
+    text = text.replace("Generations = 100\n", "xxxxxxxxxns = 100\n")      # 11 chars ending in "ns" == generations
+    deck.write_text(text)
+    v, xs, pins, dx, _, _ = nb.process_input(str(deck))
+    d = ho.process_input(str(deck))
+    assert v.histories == 777 == d.histories
+    assert v.skip == 4 == d.skip
+    assert v.generations == 100 == d.generations
+    assert len(xs.scat_matrix) == 16 and len(pins) == 70  # four Scat lines, two MatID lines concatenated
+
+
+def test_process_input_errors(tmp_path):
+    with pytest.raises(_lib.NrapsError) as e:
+        nb.process_input(str(tmp_path / "missing.txt"))
+    assert e.value.code == 9
+    bad = tmp_path / "bad.txt"
+    bad.write_text(open(DECKS["a"]).read().replace("MPFR = 8", "MPFR = eight"))
+    with pytest.raises(_lib.NrapsError):
+        nb.process_input(str(bad))
+
+
+@pytest.mark.parametrize("case,N,NF,L", [("a", 408, 272, 42.908), ("b", 400, 254, 41.598), ("c", 408, 272, 42.908)])
+def test_mesh_gen_structure(case, N, NF, L):
+    v, xs, dx, mesh, fuel = load_case(case)
+    assert len(mesh) == N and len(fuel) == NF and abs(float(mesh.mesh_right[-1]) - L) < 2e-3
+    assert mesh.mesh_left[0] == 0.0
+    assert np.array_equal(bits(mesh.mesh_right[:-1]), bits(mesh.mesh_left[1:]))  # edges shared bit for bit
+    runs = np.flatnonzero(np.diff(mesh.matid.astype(int))) + 1
+    assert len(runs) + 1 == 69  # 69 material runs in all three decks
+    assert list(mesh.matid[:2]) == [2, 2] and list(mesh.matid[-2:]) == [2, 2]  # edge water runs of 2 cells
+    d = ho.process_input(DECKS[case])
+    m = ho.mesh_gen(d.matid, d.mpfr, d.mpwr, d.numass, d.dx_fuel, d.dx_water)
+    assert np.array_equal(mesh.matid, m[0]) and np.array_equal(fuel, m[4])
+    for a, b in [(mesh.delta_x, m[1]), (mesh.mesh_left, m[2]), (mesh.mesh_right, m[3])]:
+        assert np.array_equal(bits(a), bits(b))
+
+
+def test_mesh_gen_centre_trim_with_control_rods():
+    """in deck B the cut lands inside assembly 2: ... MOX x8, H2O x6, MOX x6, H2O x4 ..."""
+    _, _, _, mesh, _ = load_case("b")
+    m = mesh.matid
+    change = np.flatnonzero(np.diff(m.astype(int))) + 1
+    runs = [(int(m[s]), int(e - s)) for s, e in zip(np.r_[0, change], np.r_[change, len(m)])]
+    mid = next(i for i, (mat, n) in enumerate(runs) if (mat, n) == (2, 6))
+    assert runs[mid - 1] == (1, 8) and runs[mid + 1] == (1, 6) and runs[mid + 2] == (2, 4)
+    assert sum(1 for mat, _ in runs if mat == 3) == 2  # two control-rod pins, meshed at water width (Q10)
+
+
+def test_mesh_gen_fine_mesh_shape():
+    _, _, _, mesh, fuel = load_case("c", mpfr=80, mpwr=40)
+    assert len(mesh) == 4080 and len(fuel) == 2720 and abs(float(mesh.mesh_right[-1]) - 42.907) < 2e-3
+
+
+def test_rust_float_display():
+    rng = np.random.default_rng(5)
+    vals = [0.0, -0.0, 1.0, -1.0, 0.1, 1.5102, 3.3e-7, 1e-10, 4.7727519e19, 123456789.0, 16777216.0, 1e-38, 3.4e38,
+            float("inf"), float("-inf"), float("nan"), 42.908089, 0.30000001192]
+    vals += list(rng.uniform(-2, 2, 300)) + list(10.0 ** rng.uniform(-30, 30, 300)) + list(rng.integers(0, 10**9, 100).astype(float))
+    for v in vals:
+        assert nb.format_f32(v) == ho.rust_f32_display(v), v
+    for v in [42.90808868408203, 0.1, 1e22, 1e-7, 123456789.125, float(f32(41.598076))]:
+        assert nb.format_f64(v) == ho.rust_f64_display(v), v
+    assert nb.format_f32(4.7727519e19) == "47727517000000000000" and nb.format_f32(1.0) == "1" and nb.format_f32(0.0) == "0"
+
+
+def test_plot_solution_files(tmp_path):
+    rng = np.random.default_rng(1)
+    G, N, gens = 4, 37, 9
+    r = nb.SolutionResults(
+        flux=(rng.random((G, N)) * 1e19).astype(f32), assembly_average=rng.random((G, N)).astype(f32),
+        fission_source=np.r_[rng.random(N - 3), 0, 0, 0].astype(f32), k=rng.random(gens).astype(f32) + 1,
+        k_fund=np.r_[0, rng.random(gens - 1) + 1].astype(f32),
+    )
+    L = float(f32(42.908089))
+    nb.plot_solution(r, G, gens, N, L, str(tmp_path))
+    want = ho.csv_files(r.flux, r.assembly_average, r.fission_source, r.k, r.k_fund, L, N, gens)
+    for name, text in want.items():
+        assert (tmp_path / name).read_text() == text, name
+    rows = (tmp_path / "interface.csv").read_text().splitlines()
+    assert len(rows) == 2 * G + 1 and all(len(row.split(",")) == N for row in rows)  # src/plot_solution.rs:43-52
+
+
+def test_average_assembly_and_k_fund_match_oracle():
+    rng = np.random.default_rng(2)
+    fp = C.POINTER(C.c_float)
+    for G, N, numass in [(2, 408, 2), (4, 400, 2), (3, 41, 3)]:
+        flux = (rng.random((G, N)) * 1e18).astype(f32)
+        a, b = np.zeros_like(flux), np.zeros_like(flux)
+        _lib.lib().nraps_average_assembly(flux.ctypes.data_as(fp), G, N, numass, a.ctypes.data_as(fp))
+        orc.lib().oracle_average_assembly(flux.ctypes.data_as(fp), G, N, numass, b.ctypes.data_as(fp))
+        assert np.array_equal(bits(a), bits(b))
+    for gens, skip in [(100, 1), (100, 4), (7, 6), (5, 0)]:
+        k = (rng.random(gens) + 1).astype(f32)
+        a, b = np.zeros(gens, f32), np.zeros(gens, f32)
+        _lib.lib().nraps_k_fund(k.ctypes.data_as(fp), gens, skip, a.ctypes.data_as(fp))
+        orc.lib().oracle_k_fund(k.ctypes.data_as(fp), gens, skip, b.ctypes.data_as(fp))
+        assert np.array_equal(bits(a), bits(b))
+        assert np.all(a[:skip] == 0) and a[skip] == k[skip]

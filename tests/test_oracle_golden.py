@@ -1,0 +1,157 @@
+"""Pins the CPU oracle against every golden vector the reference holds for the
+MC path (src/mc_code.rs:392-556), the commented test_energy (:446-462), and the
+upstream PCG32 demo vector.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+f32 = np.float32
+
+
+def _hit(mu, x, ds, b, end):
+    out = (C.c_float * 3)()
+    orc.lib().oracle_hit_boundary(mu, x, ds, b, end, out)
+    return tuple(out)
+
+
+def test_boundary_vectors():  # src/mc_code.rs:393-413
+    assert _hit(0.5, 0.5, 1.0, 1.0, 1.0) == (-0.5, -0.5, 1.0)
+    assert _hit(-0.5, 0.5, -1.0, 1.0, 0.0) == (0.5, 0.5, 0.0)
+    assert _hit(0.5, 0.5, 0.5, 1.0, 1.0) == (-0.5, 0.0, 1.0)
+    r = _hit(-0.5, 0.5, -0.5, 1.0, 0.0)
+    assert r[0] == 0.5 and r[1] == 0.0 and r[2] == 0.0
+
+
+def test_cross_mesh_vectors():  # src/mc_code.rs:416-426
+    out, idx = (C.c_float * 2)(), C.c_uint64()
+    orc.lib().oracle_cross_mesh(1, 0.5, 0.5, 1.0, 1.0, out, C.byref(idx))
+    assert (out[0], out[1], idx.value) == (0.5, 1.0, 2)
+    orc.lib().oracle_cross_mesh(1, -0.5, 1.0, 0.5, -1.0, out, C.byref(idx))
+    assert (out[0], out[1], idx.value) == (-0.5, 0.5, 0)
+
+
+def test_direction_vectors():  # src/mc_code.rs:429-444
+    for xi, want in [(1.0, 1.0), (0.75, 0.5), (0.5, 0.0), (0.25, -0.5), (0.0, -1.0)]:
+        assert orc.lib().oracle_direction_f(xi) == want
+
+
+XS_A_SIGS = np.array([0.200, 0.200, 0.200, 0.0, 0.80, 0.80, 1.10, 0.1], f32)
+XS_A_SCAT = np.array([0.185, 0.015, 0.000, 0.800, 0.185, 0.015, 0.000, 0.800, 0.170, 0.030, 0.000, 1.100,
+                      0.000, 0.000, 0.000, 0.100], f32)
+
+
+def test_scat_mat_calc_vectors():  # src/mc_code.rs:465-556, exact f32 equality
+    want = {0: [[0.925, 1.0], [0.925, 1.0], [0.85, 1.0], None], 1: [[0.0, 1.0]] * 4}
+    fp = C.POINTER(C.c_float)
+    for g in (0, 1):
+        for mat in range(4):
+            if want[g][mat] is None:
+                continue  # 1/0 -> NaN row, skipped by the reference too
+            out = np.zeros(2, f32)
+            inv = f32(1.0) / XS_A_SIGS[mat + 4 * g]
+            orc.lib().oracle_scat_mat_calc(2, mat, g, inv, XS_A_SCAT.ctypes.data_as(fp), out.ctypes.data_as(fp))
+            assert out.tolist() == [float(f32(v)) for v in want[g][mat]]
+
+
+def test_energy_search_semantics():  # the commented test_energy, src/mc_code.rs:446-462
+    cum = np.array([0.0, 0.0, 0.5, 1.0], f32)
+    fp = cum.ctypes.data_as(C.POINTER(C.c_float))
+    for chi, want in [(1.0, 3), (0.51, 3), (0.5, 2), (0.49, 2), (1e-9, 2)]:
+        assert orc.lib().oracle_energy_search(fp, 4, chi) == want
+
+
+def test_pcg32_upstream_demo_vector():  # pcg-c-basic demo, seed 42 / seq 54
+    out = (C.c_uint32 * 6)()
+    orc.lib().oracle_pcg32_demo(42, 54, 6, out)
+    assert [hex(v) for v in out] == ["0xa15c02b7", "0x7b47f409", "0xba1d3330", "0x83d2f293", "0xbfa4784b", "0xcbed606e"]
+
+
+def test_pcg32_advance_equals_stepping():
+    n = 1000
+    seq = (C.c_uint32 * (n + 3))()
+    orc.lib().oracle_pcg32_demo(7, 9, n + 3, seq)
+    # python model of one step to recover the state after `n` draws
+    mult, mask = 6364136223846793005, (1 << 64) - 1
+    st = (C.c_uint64 * 2)()
+    orc.lib().oracle_pcg32_state(7, 9, 0, st)
+    state, inc = st[0], st[1]
+    for _ in range(n):
+        state = (state * mult + inc) & mask
+    orc.lib().oracle_pcg32_state(7, 9, n, st)
+    assert st[0] == state and st[1] == inc
+    # wrap-around deltas are taken mod 2^64
+    orc.lib().oracle_pcg32_state(7, 9, (1 << 64) - 1, st)
+    back = (st[0] * mult + inc) & mask
+    orc.lib().oracle_pcg32_state(7, 9, 0, st)
+    assert back == st[0]
+
+
+def test_uniform_mapping_never_degenerate():
+    L = orc.lib()
+    for u in [0, 1, 511, 512, 0x7FFFFFFF, 0x80000000, 0x800001FF, 0xFFFFFFFF, 0xFFFFFE00]:
+        xi = L.oracle_unit_f(u)
+        assert 0.0 < xi < 1.0 and xi != 0.5
+        assert L.oracle_direction_f(xi) != 0.0
+    assert L.oracle_unit_f(0) == 2.0 ** -24 and L.oracle_unit_f(0xFFFFFFFF) == 1.0 - 2.0 ** -24
+
+
+def test_logf_accuracy_exhaustive():
+    """All 2^23 uniforms the transport loop can ever feed to ln(): < 1 ulp of libm's double log."""
+    worst = max(orc.lib().oracle_logf_max_ulp(i << 20, 1 << 20) for i in range(8))
+    assert worst < 1.0, worst
+
+
+@pytest.mark.parametrize("case,k_lo,k_hi,coll", [("a", 1.500, 1.520, 18.06), ("b", 1.767, 1.787, 21.75), ("c", 1.812, 1.832, 29.55)])
+def test_oracle_lands_on_survey_anchors(case, k_lo, k_hi, coll):
+    """Sanity ranges from SURVEY 8c (survey-time probe, not goldens): k and collisions/history."""
+    from tests.util import load_case, oracle_inputs
+
+    deck, mesh = oracle_inputs(*load_case(case))
+    r = orc.monte_carlo(deck, mesh, generations=4, histories=50000, skip=1, threads=4)
+    assert k_lo < float(np.mean(r.k)) < k_hi
+    assert abs(r.counters["collisions"] / r.counters["histories"] - coll) < 0.25
+    assert r.counters["histories"] == 4 * 50000 and r.counters["truncated"] == 0 and r.counters["leaks"] == 0
+
+
+def test_oracle_thread_and_shard_invariance():
+    """Fixed-point tallies are exact integers: worker count and sharding cannot change them."""
+    from tests.util import load_case, oracle_inputs
+
+    deck, mesh = oracle_inputs(*load_case("c"))
+    kw = dict(generations=2, histories=20000, skip=1, want_tally=True)
+    one = orc.monte_carlo(deck, mesh, threads=1, **kw)
+    many = orc.monte_carlo(deck, mesh, threads=5, **kw)
+    assert np.array_equal(one.tally_fixed, many.tally_fixed)
+    assert np.array_equal(one.k.view(np.uint32), many.k.view(np.uint32))
+    lo = orc.monte_carlo(deck, mesh, threads=2, hist_begin=0, hist_count=7001, **kw)
+    hi = orc.monte_carlo(deck, mesh, threads=2, hist_begin=7001, hist_count=20000 - 7001, **kw)
+    assert np.array_equal(lo.tally_fixed + hi.tally_fixed, one.tally_fixed)
+
+
+def test_oracle_scatter_modes_agree_for_two_groups():
+    """for G=2 every probe order samples the same distribution."""
+    from tests.util import load_case, oracle_inputs
+
+    deck, mesh = oracle_inputs(*load_case("a"))
+    ks = {}
+    for mode in ("single_xi", "rust_pre182", "rust_182"):
+        r = orc.monte_carlo(deck, mesh, generations=6, histories=40000, skip=1, threads=4, scatter_mode=mode)
+        ks[mode] = (float(np.mean(r.k)), float(np.std(r.k, ddof=1) / np.sqrt(len(r.k))))
+    for mode in ("rust_pre182", "rust_182"):
+        d = abs(ks[mode][0] - ks["single_xi"][0])
+        assert d < 4 * np.hypot(ks[mode][1], ks["single_xi"][1]) + 2e-3, ks
+
+
+def test_oracle_faithful_f32_tallies_close_to_exact():
+    """per-worker f32 tallies (faithful) vs exact fixed-point, same streams."""
+    from tests.util import load_case, oracle_inputs
+
+    deck, mesh = oracle_inputs(*load_case("b"))
+    kw = dict(generations=2, histories=30000, skip=1, threads=3)
+    exact = orc.monte_carlo(deck, mesh, tally_mode="fixed64", **kw)
+    faithful = orc.monte_carlo(deck, mesh, tally_mode="f32_per_worker", **kw)
+    assert np.allclose(exact.k, faithful.k, rtol=2e-5)
+    assert exact.counters == faithful.counters

@@ -132,6 +132,8 @@ int nraps_mc_launch_info(nraps_mc_ctx *ctx, uint32_t out[6]);
 
 /* device-side unit probes for the golden-vector tests (each runs a 1-block kernel) */
 int nraps_dev_logf(const float *x, float *out, uint32_t n, int32_t device);
+/* walk-loop division (hoisted reciprocal) next to the device's IEEE division, for the exactness test */
+int nraps_dev_div(const float *t, const float *mu, float *out_fast, float *out_ieee, uint32_t n, int32_t device);
 int nraps_dev_pcg32(uint64_t seed, uint64_t stream, uint64_t stride, uint64_t hid, uint32_t n,
                     uint32_t *out_u32, float *out_unit, int32_t device);
 

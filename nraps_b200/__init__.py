@@ -7,7 +7,7 @@ through the C ABI in ``include/``; importing this package without that library
 fails on first use.
 """
 from .api import (  # noqa: F401
-    DeltaX, Mesh, MonteCarloContext, SolutionResults, Variables, XSData, dev_logf, dev_pcg32, format_f32, format_f64,
+    DeltaX, Mesh, MonteCarloContext, SolutionResults, Variables, XSData, dev_div, dev_logf, dev_pcg32, format_f32, format_f64,
     make_options, mesh_gen, monte_carlo, plot_solution, process_input,
 )
 from .dist import monte_carlo_distributed, shard_range  # noqa: F401

@@ -77,7 +77,7 @@ class Mesh(C.Structure):
 EXPORTS = [
     "nraps_mc_run", "nraps_mc_create", "nraps_mc_destroy", "nraps_mc_reset", "nraps_mc_transport",
     "nraps_mc_finalize_generation", "nraps_mc_tally_buffer", "nraps_mc_set_tally_buffer", "nraps_mc_read_tally",
-    "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_dev_logf", "nraps_dev_pcg32",
+    "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
     "nraps_strerror", "nraps_last_cuda_error", "nraps_abi_version",
     "nraps_process_input", "nraps_deck_free", "nraps_mesh_gen", "nraps_mesh_free", "nraps_problem_from",
     "nraps_format_f32", "nraps_format_f64", "nraps_plot_solution", "nraps_average_assembly", "nraps_k_fund",
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.nraps_mc_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, vp]
     L.nraps_mc_launch_info.argtypes = [vp, _u32p]
     L.nraps_dev_logf.argtypes = [_fp, _fp, C.c_uint32, C.c_int32]
+    L.nraps_dev_div.argtypes = [_fp, _fp, _fp, _fp, C.c_uint32, C.c_int32]
     L.nraps_dev_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _u32p, _fp, C.c_int32]
     L.nraps_strerror.argtypes = [C.c_int]
     L.nraps_strerror.restype = C.c_char_p

@@ -310,6 +310,15 @@ def dev_logf(x: np.ndarray, device: int = 0) -> np.ndarray:
     return out
 
 
+def dev_div(t: np.ndarray, mu: np.ndarray, device: int = 0):
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    mu = np.ascontiguousarray(mu, dtype=np.float32)
+    fast, ieee = np.empty_like(t), np.empty_like(t)
+    p = lambda a: a.ctypes.data_as(_lib._fp)  # noqa: E731
+    check(lib().nraps_dev_div(p(t), p(mu), p(fast), p(ieee), t.size, device), "nraps_dev_div")
+    return fast, ieee
+
+
 def dev_pcg32(seed: int, stream: int, stride: int, hid: int, n: int, device: int = 0):
     u = np.zeros(n, np.uint32)
     f = np.zeros(n, np.float32)

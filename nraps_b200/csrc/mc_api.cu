@@ -503,6 +503,21 @@ extern "C" int nraps_dev_logf(const float *x, float *out, uint32_t n, int32_t de
     return NRAPS_OK;
 }
 
+extern "C" int nraps_dev_div(const float *t, const float *mu, float *out_fast, float *out_ieee, uint32_t n, int32_t device)
+{
+    if (!t || !mu || !out_fast || !out_ieee) return NRAPS_ERR_NULL;
+    CU(cudaSetDevice(device));
+    float *d[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (auto &p : d) CU(cudaMalloc((void **)&p, std::max<size_t>(1, n) * sizeof(float)));
+    CU(cudaMemcpy(d[0], t, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d[1], mu, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_probe_div(d[0], d[1], d[2], d[3], n, nullptr));
+    CU(cudaMemcpy(out_fast, d[2], n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_ieee, d[3], n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (auto &p : d) cudaFree(p);
+    return NRAPS_OK;
+}
+
 extern "C" int nraps_dev_pcg32(uint64_t seed, uint64_t stream, uint64_t stride, uint64_t hid, uint32_t n,
                                uint32_t *out_u32, float *out_unit, int32_t device)
 {

@@ -76,6 +76,14 @@ __global__ void probe_logf_kernel(const float *x, float *out, uint32_t n)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = mc_logf(x[i]);
 }
 
+__global__ void probe_div_kernel(const float *t, const float *mu, float *out_fast, float *out_ieee, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        out_fast[i] = fast_div(t[i], make_recip(mu[i]));
+        out_ieee[i] = fdiv(t[i], mu[i]);
+    }
+}
+
 __global__ void probe_pcg_kernel(uint64_t state, uint64_t inc, uint32_t n, uint32_t *out_u32, float *out_unit)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -98,6 +106,12 @@ cudaError_t launch_finalize(const FinalizeParams &p, cudaStream_t s)
 cudaError_t launch_probe_logf(const float *x, float *out, uint32_t n, cudaStream_t s)
 {
     probe_logf_kernel<<<148, 256, 0, s>>>(x, out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe_div(const float *t, const float *mu, float *out_fast, float *out_ieee, uint32_t n, cudaStream_t s)
+{
+    probe_div_kernel<<<148, 256, 0, s>>>(t, mu, out_fast, out_ieee, n);
     return cudaGetLastError();
 }
 

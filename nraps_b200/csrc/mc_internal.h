@@ -35,6 +35,7 @@ __host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32
     L.tally_hi = off; off += G * N * 4;
     L.edges = off;    off += (N + 1) * 4;
     L.runb = off;     off += N * 4;
+    off = align_up(off, 16); // float4 rows of the CDF tables
     L.xs = off;       off += (3 * M * G + M * G * G * G) * 4;
     L.fuel = off;     off += align_up(NF * 2, 4);
     L.matid = off;    off += align_up(N, 4);
@@ -84,6 +85,7 @@ cudaError_t launch_transport(const TransportParams &p, bool trace, dim3 grid, di
 cudaError_t prepare_transport(uint32_t smem_bytes);
 cudaError_t launch_finalize(const FinalizeParams &p, cudaStream_t s);
 cudaError_t launch_probe_logf(const float *x, float *out, uint32_t n, cudaStream_t s);
+cudaError_t launch_probe_div(const float *t, const float *mu, float *out_fast, float *out_ieee, uint32_t n, cudaStream_t s);
 cudaError_t launch_probe_pcg(uint64_t state, uint64_t inc, uint32_t n, uint32_t *out_u32, float *out_unit, cudaStream_t s);
 
 } // namespace nraps

@@ -10,9 +10,12 @@
 //
 // Warp structure: every trip of the outer loop each live lane draws one flight,
 // walks cell crossings until its flight ends (collision, material change, leak),
-// then the lanes that collided run the collision stage together.  The walk is
-// bounded by the length of a material run (8 fuel / 4 water cells in the
-// shipped decks), so lanes of a warp stay within a small factor of each other.
+// then the warp reconverges (__syncwarp) and the lanes that collided run the
+// collision stage together.  The walk is bounded by the length of a material
+// run (8 fuel / 4 water cells in the shipped decks), so lanes of a warp stay
+// within a small factor of each other.  profiles/r1a_* is the ncu evidence that
+// drove this shape: without the explicit reconvergence points the compiler let
+// lanes fall out of the walk loop one by one (7.8 of 32 lanes active).
 //
 // Tallies: score -> (u64)(score * 2^28), added to a 64-bit bin kept as two u32
 // words in shared memory (ATOMS.ADD is native for u32 only; f32 and u64 shared
@@ -28,31 +31,49 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-struct Smem {
-    uint32_t *lo, *hi;
-    const float *edges;
-    const uint32_t *runb;
-    const ulonglong2 *jump;
-    const float *inv_sigtr, *p_abs, *chi_cdf, *scat_cdf;
-    const uint16_t *fuel;
-    const uint8_t *matid;
-};
+// shared-space atomics on 32-bit shared addresses (the generic-pointer forms
+// drag a cluster-window address computation into the inner loop)
+__device__ __forceinline__ uint32_t atoms_add(uint32_t saddr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t saddr, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 
-__device__ __forceinline__ void score(const Smem &S, int bin, float v)
+// 64-bit fixed-point bin += score, as two u32 words with an explicit carry
+__device__ __forceinline__ void score(uint32_t lo_base, uint32_t hi_off, int bin, float v)
 {
     const unsigned long long fx = __float2ull_rz(fmul(v, kTallyScale));
     const uint32_t l = (uint32_t)fx;
     uint32_t h = (uint32_t)(fx >> 32);
-    const uint32_t old = atomicAdd(&S.lo[bin], l);
+    const uint32_t a = lo_base + 4u * (uint32_t)bin;
+    const uint32_t old = atoms_add(a, l);
     h += (uint32_t)(old + l < old);
-    if (h) atomicAdd(&S.hi[bin], h);
+    if (h) reds_add(a + hi_off, h);
+}
+
+template <int TG> __device__ __forceinline__ int search_cdf(const float *cdf, int G, float v)
+{
+    if (TG == 4) { // partition_point on 4 entries, probes 2 then 3 or 1 then 0
+        const float4 c = *reinterpret_cast<const float4 *>(cdf);
+        return (c.z < v) ? 3 : ((c.y < v) ? 2 : ((c.x < v) ? 1 : 0));
+    }
+    if (TG == 2) {
+        const float2 c = *reinterpret_cast<const float2 *>(cdf);
+        return ((c.y < v) || (c.x < v)) ? 1 : 0;
+    }
+    return lower_bound_clamped<TG>(cdf, G, v);
 }
 
 template <int TG>
 __device__ __forceinline__ int sample_group(const float *cdf, int G, int mode, uint64_t &rng, uint64_t inc)
 {
     const int n = TG ? TG : G;
-    if (mode == NRAPS_SCATTER_SINGLE_XI) return lower_bound_clamped<TG>(cdf, G, pcg32_unit(rng, inc));
+    if (mode == NRAPS_SCATTER_SINGLE_XI) return search_cdf<TG>(cdf, G, pcg32_unit(rng, inc));
     if (mode == NRAPS_SCATTER_RUST_PRE182) { // a fresh draw per probe, pre-1.82 probe order
         int size = n, left = 0, right = n;
         while (left < right) {
@@ -73,6 +94,18 @@ __device__ __forceinline__ int sample_group(const float *cdf, int G, int mode, u
     return res < n - 1 ? res : n - 1;
 }
 
+// apply the jump maps selected by the set bits of `steps` (each map = stride * 2^b draws)
+__device__ __forceinline__ uint64_t jump_ahead(uint64_t state, uint64_t steps, const ulonglong2 *jump)
+{
+    while (steps) {
+        const int b = __ffsll((long long)steps) - 1;
+        steps &= steps - 1;
+        const ulonglong2 J = jump[b];
+        state = J.x * state + J.y;
+    }
+    return state;
+}
+
 enum { EV_NONE = 0, EV_COLLIDE = 1, EV_MATCHANGE = 2 };
 
 template <int TG, bool TRACE>
@@ -83,33 +116,34 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     const int M = (int)P.M, N = (int)P.N;
     const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF);
 
-    Smem S;
-    S.lo = reinterpret_cast<uint32_t *>(smem_raw + L.tally_lo);
-    S.hi = reinterpret_cast<uint32_t *>(smem_raw + L.tally_hi);
-    float *w_edges = reinterpret_cast<float *>(smem_raw + L.edges);
-    uint32_t *w_runb = reinterpret_cast<uint32_t *>(smem_raw + L.runb);
-    ulonglong2 *w_jump = reinterpret_cast<ulonglong2 *>(smem_raw + L.jump);
-    float *w_xs = reinterpret_cast<float *>(smem_raw + L.xs);
-    uint16_t *w_fuel = reinterpret_cast<uint16_t *>(smem_raw + L.fuel);
-    uint8_t *w_matid = smem_raw + L.matid;
+    uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw + L.tally_lo);
+    uint32_t *s_hi = reinterpret_cast<uint32_t *>(smem_raw + L.tally_hi);
+    float *s_edges = reinterpret_cast<float *>(smem_raw + L.edges);
+    uint32_t *s_runb = reinterpret_cast<uint32_t *>(smem_raw + L.runb);
+    ulonglong2 *s_jump = reinterpret_cast<ulonglong2 *>(smem_raw + L.jump);
+    float *s_xs = reinterpret_cast<float *>(smem_raw + L.xs);
+    uint16_t *s_fuel = reinterpret_cast<uint16_t *>(smem_raw + L.fuel);
+    uint8_t *s_matid = smem_raw + L.matid;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int GN = G * N, MG = M * G;
-    for (int i = tid; i < GN; i += nthr) { S.lo[i] = 0u; S.hi[i] = 0u; }
-    for (int i = tid; i <= N; i += nthr) w_edges[i] = P.edges[i];
-    for (int i = tid; i < N; i += nthr) { w_runb[i] = P.runb[i]; w_matid[i] = P.matid[i]; }
-    for (int i = tid; i < (int)P.NF; i += nthr) w_fuel[i] = P.fuel[i];
-    for (int i = tid; i < 3 * MG + MG * G * G; i += nthr) w_xs[i] = P.xs[i];
-    for (int i = tid; i < 64; i += nthr) w_jump[i] = P.jump[i];
+    for (int i = tid; i < GN; i += nthr) { s_lo[i] = 0u; s_hi[i] = 0u; }
+    for (int i = tid; i <= N; i += nthr) s_edges[i] = P.edges[i];
+    for (int i = tid; i < N; i += nthr) { s_runb[i] = P.runb[i]; s_matid[i] = P.matid[i]; }
+    for (int i = tid; i < (int)P.NF; i += nthr) s_fuel[i] = P.fuel[i];
+    for (int i = tid; i < 3 * MG + MG * G * G; i += nthr) s_xs[i] = P.xs[i];
+    for (int i = tid; i < 64; i += nthr) s_jump[i] = P.jump[i];
     __syncthreads();
-    S.edges = w_edges; S.runb = w_runb; S.jump = w_jump; S.fuel = w_fuel; S.matid = w_matid;
-    S.inv_sigtr = w_xs; S.p_abs = w_xs + MG; S.chi_cdf = w_xs + 2 * MG; S.scat_cdf = w_xs + 3 * MG;
+    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_chi = s_xs + 2 * MG, *s_scat = s_xs + 3 * MG;
+    const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(s_lo);
+    const uint32_t hi_off = L.tally_hi - L.tally_lo;
 
     const unsigned lane = tid & 31;
     const uint64_t inc = P.rng_inc;
 
-    // warp-uniform cursor over the chunk of history indices this warp owns
-    uint64_t w_next = 0, w_end = 0;
+    // warp-uniform cursor over the chunk of history indices this warp owns, and
+    // the master stream positioned at history w_next
+    uint64_t w_next = 0, w_end = 0, w_state = 0;
     bool exhausted = false;
 
     // lane state: one neutron
@@ -121,6 +155,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     uint32_t c_hist = 0, c_coll = 0, c_cross = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0;
 
     for (;;) {
+        __syncwarp();
         // ---------------- SPAWN: hand fresh history indices to dead lanes
         const unsigned need = __ballot_sync(kFull, !alive);
         if (need) {
@@ -130,140 +165,152 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 base = __shfl_sync(kFull, base, 0);
                 const uint64_t b = P.hist_begin + base;
                 if (b >= P.hist_end) exhausted = true;
-                else { w_next = b; w_end = (b + P.chunk < P.hist_end) ? b + P.chunk : P.hist_end; }
+                else {
+                    w_next = b;
+                    w_end = (b + P.chunk < P.hist_end) ? b + P.chunk : P.hist_end;
+                    w_state = jump_ahead(P.rng_state, b, s_jump); // once per chunk, warp-uniform
+                }
             }
             const uint32_t avail = (uint32_t)(w_end - w_next);
             if (avail) {
                 const uint32_t rank = __popc(need & ((1u << lane) - 1u));
                 if (!alive && rank < avail) {
                     y = w_next + rank;
-                    // per-history stream: master advanced by y*stride draws (jump maps commute)
-                    rng = P.rng_state;
-                    for (uint64_t h = y; h;) {
-                        const int b = __ffsll((long long)h) - 1;
-                        h &= h - 1;
-                        const ulonglong2 J = S.jump[b];
-                        rng = J.x * rng + J.y;
-                    }
+                    // per-history stream = master advanced by y*stride draws; jump maps commute, so
+                    // start from the chunk cursor and add the (small) rank
+                    rng = jump_ahead(w_state, rank, s_jump);
                     // draw order cell, position, mu, chi (src/mc_code.rs:46-51)
                     const uint32_t u = pcg32_next(rng, inc);
-                    cell = S.fuel[__umulhi(u, P.NF)];
+                    cell = s_fuel[__umulhi(u, P.NF)];
                     const float xi_pos = pcg32_unit(rng, inc);
                     mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
                     const float xi_chi = pcg32_unit(rng, inc);
-                    mat = S.matid[cell];
-                    g = lower_bound_clamped<TG>(S.chi_cdf + mat * G, G, xi_chi);
+                    mat = s_matid[cell];
+                    g = search_cdf<TG>(s_chi + mat * G, G, xi_chi);
                     xsg = g;
-                    x = fadd(S.edges[cell], fmul(xi_pos, P.dx_fuel));
-                    const uint32_t rb = S.runb[cell];
+                    x = fadd(s_edges[cell], fmul(xi_pos, P.dx_fuel));
+                    const uint32_t rb = s_runb[cell];
                     run_lo = (int)(rb & 0xffffu);
                     run_hi = (int)(rb >> 16);
                     h_coll = h_cross = h_flight = h_refl = 0;
                     alive = true;
                 }
                 const uint32_t want = __popc(need);
-                w_next += want < avail ? want : avail;
+                const uint32_t took = want < avail ? want : avail;
+                w_next += took;
+                w_state = jump_ahead(w_state, took, s_jump);
             } else if (need == kFull) {
                 break; // no work left anywhere and every lane is dead
             }
         }
+        __syncwarp();
 
+        uint32_t fate = 0;
+        int ev = EV_NONE;
+        float end = 0.f;
+        Recip rc{1.f, 1.f};
         if (alive) {
-            uint32_t fate = 0;
-            int ev = EV_NONE;
-            float end = 0.f;
             if (h_flight >= P.max_flights) {
                 fate = NRAPS_FATE_TRUNCATED;
             } else {
                 // ------------ FLIGHT: signed x-displacement to the next collision
-                ds = fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), S.inv_sigtr[mat + M * xsg]);
+                ds = fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), s_inv_sigtr[mat + M * xsg]);
                 ++h_flight;
                 // ------------ WALK: cell by cell inside one material run
-                bool fwd = mu >= 0.0f;
+                rc = make_recip(mu);
+                int fwd = mu >= 0.0f ? 1 : 0;
+                int dir = 2 * fwd - 1;
+                int wall = fwd ? N - 1 : 0;
+                int run_exit = fwd ? run_hi : run_lo - 1;
+                const int gN = g * N;
                 for (;;) {
                     end = fadd(x, ds);
-                    const float edge = S.edges[cell + (fwd ? 1 : 0)];
+                    const float edge = s_edges[cell + fwd];
                     const float t = fsub(x, edge);
-                    const bool at_wall = fwd ? (cell == N - 1 && end > edge) : (cell == 0 && edge > end);
-                    if (at_wall) {
-                        score(S, g * N + cell, fabsf(fdiv(t, mu)));
-                        const float b = fwd ? P.boundr : P.boundl;
-                        if (b > 0.0f) { // hit_boundary
-                            mu = fmul(mu, -b);
-                            ds = fmul(fadd(ds, t), -b);
-                            x = edge;
-                            fwd = mu >= 0.0f;
-                            if (TRACE) ++h_refl;
-                            continue;
+                    if (cell == wall) { // domain boundary cell: src/mc_code.rs:159-170
+                        const bool beyond = fwd ? (end > edge) : (edge > end);
+                        if (beyond) {
+                            score(lo_base, hi_off, gN + cell, fabsf(fdiv(t, mu)));
+                            const float b = fwd ? P.boundr : P.boundl;
+                            if (b > 0.0f) { // hit_boundary
+                                mu = fmul(mu, -b);
+                                ds = fmul(fadd(ds, t), -b);
+                                x = edge;
+                                rc = make_recip(mu);
+                                fwd = mu >= 0.0f ? 1 : 0;
+                                dir = 2 * fwd - 1;
+                                wall = fwd ? N - 1 : 0;
+                                run_exit = fwd ? run_hi : run_lo - 1;
+                                if (TRACE) ++h_refl;
+                                continue;
+                            }
+                            fate = NRAPS_FATE_LEAKED;
+                            break;
                         }
-                        fate = NRAPS_FATE_LEAKED;
-                        break;
                     }
-                    if (fabsf(fsub(end, x)) > fabsf(t)) { // cross_mesh; |edge - x| == |x - edge|
-                        score(S, g * N + cell, fabsf(fdiv(t, mu)));
-                        ds = fadd(ds, t);
-                        x = edge;
-                        cell += fwd ? 1 : -1;
-                        if (TRACE) ++h_cross;
-                        if (cell < run_lo || cell >= run_hi) { ev = EV_MATCHANGE; break; }
-                    } else {
-                        ev = EV_COLLIDE;
-                        break;
-                    }
+                    if (!(fabsf(fsub(end, x)) > fabsf(t))) { ev = EV_COLLIDE; break; }
+                    // cross_mesh, src/mc_code.rs:171-181 (|edge - x| == |x - edge| exactly)
+                    score(lo_base, hi_off, gN + cell, fabsf(fast_div(t, rc)));
+                    ds = fadd(ds, t);
+                    x = edge;
+                    cell += dir;
+                    if (TRACE) ++h_cross;
+                    if (cell == run_exit) { ev = EV_MATCHANGE; break; }
                 }
             }
+        }
+        __syncwarp();
 
-            // ---------------- COLLIDE / material change
-            if (ev == EV_COLLIDE) {
-                score(S, g * N + cell, fabsf(fdiv(fsub(x, end), mu)));
-                ++h_coll;
-                const int xs = mat + M * xsg; // stale group index, src/mc_code.rs:147
-                const float xi_int = pcg32_unit(rng, inc);
-                const float mu_new = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
-                const int g_new = sample_group<TG>(S.scat_cdf + ((mat * G + g) * G + xsg) * G, G, P.scatter_mode, rng, inc);
-                if (xi_int < S.p_abs[xs]) {
-                    fate = NRAPS_FATE_ABSORBED;
-                } else {
-                    x = end;
-                    g = g_new;
-                    mu = mu_new;
-                    if (!P.stale_xs) xsg = g;
-                }
-            } else if (ev == EV_MATCHANGE) {
-                if ((unsigned)cell >= (unsigned)N) {
-                    fate = NRAPS_FATE_TRUNCATED; // unreachable for validated input
-                    cell = cell < 0 ? 0 : N - 1;
-                } else {
-                    mat = S.matid[cell];
-                    xsg = g;
-                    const uint32_t rb = S.runb[cell];
-                    run_lo = (int)(rb & 0xffffu);
-                    run_hi = (int)(rb >> 16);
-                }
+        // ---------------- COLLIDE / material change
+        if (ev == EV_COLLIDE) {
+            score(lo_base, hi_off, g * N + cell, fabsf(fast_div(fsub(x, end), rc)));
+            ++h_coll;
+            const int xs = mat + M * xsg; // stale group index, src/mc_code.rs:147
+            const float xi_int = pcg32_unit(rng, inc);
+            const float mu_new = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
+            const int g_new = sample_group<TG>(s_scat + ((mat * G + g) * G + xsg) * G, G, P.scatter_mode, rng, inc);
+            if (xi_int < s_p_abs[xs]) {
+                fate = NRAPS_FATE_ABSORBED;
+            } else {
+                x = end;
+                g = g_new;
+                mu = mu_new;
+                if (!P.stale_xs) xsg = g;
             }
+        } else if (ev == EV_MATCHANGE) {
+            if ((unsigned)cell >= (unsigned)N) {
+                fate = NRAPS_FATE_TRUNCATED; // unreachable for validated input
+                cell = cell < 0 ? 0 : N - 1;
+            } else {
+                mat = s_matid[cell];
+                xsg = g;
+                const uint32_t rb = s_runb[cell];
+                run_lo = (int)(rb & 0xffffu);
+                run_hi = (int)(rb >> 16);
+            }
+        }
 
-            if (fate) {
-                alive = false;
-                ++c_hist;
-                c_coll += h_coll;
-                c_flight += h_flight;
-                c_leak += (fate == NRAPS_FATE_LEAKED);
-                c_trunc += (fate == NRAPS_FATE_TRUNCATED);
-                if (TRACE) {
-                    c_cross += h_cross; c_refl += h_refl;
-                    if (P.trace) {
-                        uint32_t *t = P.trace + (y - P.hist_begin) * NRAPS_TR_WORDS;
-                        t[NRAPS_TR_COLLISIONS] = h_coll;
-                        t[NRAPS_TR_CROSSINGS] = h_cross;
-                        t[NRAPS_TR_FLIGHTS] = h_flight;
-                        t[NRAPS_TR_REFLECTIONS] = h_refl;
-                        t[NRAPS_TR_RNG_LO] = (uint32_t)rng;
-                        t[NRAPS_TR_RNG_HI] = (uint32_t)(rng >> 32);
-                        t[NRAPS_TR_CELL] = (uint32_t)cell;
-                        t[NRAPS_TR_XBITS] = __float_as_uint(x);
-                        t[NRAPS_TR_FATE] = fate;
-                        t[NRAPS_TR_GROUP] = (uint32_t)g;
-                    }
+        if (fate) {
+            alive = false;
+            ++c_hist;
+            c_coll += h_coll;
+            c_flight += h_flight;
+            c_leak += (fate == NRAPS_FATE_LEAKED);
+            c_trunc += (fate == NRAPS_FATE_TRUNCATED);
+            if (TRACE) {
+                c_cross += h_cross; c_refl += h_refl;
+                if (P.trace) {
+                    uint32_t *t = P.trace + (y - P.hist_begin) * NRAPS_TR_WORDS;
+                    t[NRAPS_TR_COLLISIONS] = h_coll;
+                    t[NRAPS_TR_CROSSINGS] = h_cross;
+                    t[NRAPS_TR_FLIGHTS] = h_flight;
+                    t[NRAPS_TR_REFLECTIONS] = h_refl;
+                    t[NRAPS_TR_RNG_LO] = (uint32_t)rng;
+                    t[NRAPS_TR_RNG_HI] = (uint32_t)(rng >> 32);
+                    t[NRAPS_TR_CELL] = (uint32_t)cell;
+                    t[NRAPS_TR_XBITS] = __float_as_uint(x);
+                    t[NRAPS_TR_FATE] = fate;
+                    t[NRAPS_TR_GROUP] = (uint32_t)g;
                 }
             }
         }
@@ -272,7 +319,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     // ---------------- flush: block bins -> global 64-bit bins, lane counters -> global
     __syncthreads();
     for (int i = tid; i < GN; i += nthr) {
-        const unsigned long long v = ((unsigned long long)S.hi[i] << 32) + S.lo[i];
+        const unsigned long long v = ((unsigned long long)s_hi[i] << 32) + s_lo[i];
         if (v) atomicAdd(&P.tally[i], v);
     }
     unsigned long long *ct = P.tally + GN;

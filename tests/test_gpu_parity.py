@@ -51,6 +51,25 @@ def test_device_logf_bit_exact():
     assert np.max(np.abs(got.astype(np.float64) - np.log(x.astype(np.float64))) / np.spacing(np.abs(np.log(x.astype(np.float64))).astype(f32))) < 1.0
 
 
+def test_walk_division_is_ieee_exact():
+    """The hoisted-reciprocal division of the walk loop equals the device's (and numpy's) correctly
+    rounded division on the operand domain of the path: |mu| in [2^-23, 1], t = 0 or 1e-14 <= |t| <= 64."""
+    rng = np.random.default_rng(3)
+    n = 4_000_000
+    mu = (2.0 * ((rng.integers(0, 1 << 23, n).astype(f32) + f32(0.5)) * f32(2.0 ** -23)) - 1.0).astype(f32)
+    t = np.concatenate([
+        rng.uniform(-0.12, 0.12, n // 4), rng.uniform(-64, 64, n // 4),
+        (10.0 ** rng.uniform(-14, 1.8, n // 4)) * rng.choice([-1, 1], n // 4), np.zeros(n // 8),
+        rng.choice([0.1175, 0.0805, -0.1175, -0.0805, 0.11749995, 0.08049999], n // 8),
+    ]).astype(f32)
+    mu[:8] = f32([2.0 ** -23, -(2.0 ** -23), 1 - 2.0 ** -23, -(1 - 2.0 ** -23), 2.0 ** -22, 0.5, -0.5, 3 * 2.0 ** -23])
+    fast, ieee = nb.dev_div(t, mu)
+    # the path only ever scores |t / mu|, so the sign of a zero quotient is immaterial
+    bad = np.flatnonzero(bits(np.abs(fast)) != bits(np.abs(ieee)))
+    assert bad.size == 0, (bad.size, t[bad[:5]], mu[bad[:5]], fast[bad[:5]], ieee[bad[:5]])
+    assert np.array_equal(bits(np.abs(ieee)), bits(np.abs((t / mu).astype(f32))))
+
+
 def test_device_pcg32_streams():
     import ctypes as C
     u, xi = nb.dev_pcg32(42, 54, 152917, 0, 6)

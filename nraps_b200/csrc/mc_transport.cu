@@ -44,16 +44,22 @@ __device__ __forceinline__ void reds_add(uint32_t saddr, uint32_t v)
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
-// 64-bit fixed-point bin += score, as two u32 words with an explicit carry
-__device__ __forceinline__ void score(uint32_t lo_base, uint32_t hi_off, int bin, float v)
+__device__ __forceinline__ float lds_f32(uint32_t saddr)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+
+// 64-bit fixed-point bin += score, as two u32 words with an explicit carry;
+// `a` is the shared address of the low word, the high word sits hi_off bytes above
+__device__ __forceinline__ void score(uint32_t a, uint32_t hi_off, float v)
 {
     const unsigned long long fx = __float2ull_rz(fmul(v, kTallyScale));
-    const uint32_t l = (uint32_t)fx;
-    uint32_t h = (uint32_t)(fx >> 32);
-    const uint32_t a = lo_base + 4u * (uint32_t)bin;
+    const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
     const uint32_t old = atoms_add(a, l);
-    h += (uint32_t)(old + l < old);
-    if (h) reds_add(a + hi_off, h);
+    const bool carry = (uint32_t)(old + l) < l;
+    if (carry | (h != 0u)) reds_add(a + hi_off, h + (carry ? 1u : 0u));
 }
 
 template <int TG> __device__ __forceinline__ int search_cdf(const float *cdf, int G, float v)
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_chi = s_xs + 2 * MG, *s_scat = s_xs + 3 * MG;
     const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(s_lo);
     const uint32_t hi_off = L.tally_hi - L.tally_lo;
+    const uint32_t edges_base = (uint32_t)__cvta_generic_to_shared(s_edges);
 
     const unsigned lane = tid & 31;
     const uint64_t inc = P.rng_inc;
@@ -209,6 +216,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
         int ev = EV_NONE;
         float end = 0.f;
         Recip rc{1.f, 1.f};
+        bool crossed = false;
         if (alive) {
             if (h_flight >= P.max_flights) {
                 fate = NRAPS_FATE_TRUNCATED;
@@ -216,22 +224,28 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 // ------------ FLIGHT: signed x-displacement to the next collision
                 ds = fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), s_inv_sigtr[mat + M * xsg]);
                 ++h_flight;
-                // ------------ WALK: cell by cell inside one material run
+                // ------------ WALK: cell by cell inside one material run.  Single-exit loop with
+                // running shared addresses: ~30 SASS instructions per crossing (profiles/r1c_*).
                 rc = make_recip(mu);
                 int fwd = mu >= 0.0f ? 1 : 0;
                 int dir = 2 * fwd - 1;
                 int wall = fwd ? N - 1 : 0;
                 int run_exit = fwd ? run_hi : run_lo - 1;
-                const int gN = g * N;
-                for (;;) {
+                uint32_t e_addr = edges_base + 4u * (uint32_t)(cell + fwd); // edge ahead of the neutron
+                uint32_t t_addr = lo_base + 4u * (uint32_t)(g * N + cell);  // low word of tally[g][cell]
+                bool cont;
+                do {
                     end = fadd(x, ds);
-                    const float edge = s_edges[cell + fwd];
+                    const float edge = lds_f32(e_addr);
                     const float t = fsub(x, edge);
+                    crossed = fabsf(fsub(end, x)) > fabsf(t); // |edge - x| == |x - edge| exactly
+                    cont = false;
                     if (cell == wall) { // domain boundary cell: src/mc_code.rs:159-170
                         const bool beyond = fwd ? (end > edge) : (edge > end);
                         if (beyond) {
-                            score(lo_base, hi_off, gN + cell, fabsf(fdiv(t, mu)));
+                            score(t_addr, hi_off, fabsf(fdiv(t, mu)));
                             const float b = fwd ? P.boundr : P.boundl;
+                            crossed = false;
                             if (b > 0.0f) { // hit_boundary
                                 mu = fmul(mu, -b);
                                 ds = fmul(fadd(ds, t), -b);
@@ -241,29 +255,33 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                                 dir = 2 * fwd - 1;
                                 wall = fwd ? N - 1 : 0;
                                 run_exit = fwd ? run_hi : run_lo - 1;
+                                e_addr = edges_base + 4u * (uint32_t)(cell + fwd);
                                 if (TRACE) ++h_refl;
-                                continue;
+                                cont = true;
+                            } else {
+                                fate = NRAPS_FATE_LEAKED;
                             }
-                            fate = NRAPS_FATE_LEAKED;
-                            break;
                         }
                     }
-                    if (!(fabsf(fsub(end, x)) > fabsf(t))) { ev = EV_COLLIDE; break; }
-                    // cross_mesh, src/mc_code.rs:171-181 (|edge - x| == |x - edge| exactly)
-                    score(lo_base, hi_off, gN + cell, fabsf(fast_div(t, rc)));
-                    ds = fadd(ds, t);
-                    x = edge;
-                    cell += dir;
-                    if (TRACE) ++h_cross;
-                    if (cell == run_exit) { ev = EV_MATCHANGE; break; }
-                }
+                    if (crossed) { // cross_mesh, src/mc_code.rs:171-181
+                        score(t_addr, hi_off, fabsf(fast_div(t, rc)));
+                        ds = fadd(ds, t);
+                        x = edge;
+                        cell += dir;
+                        e_addr += 4 * dir;
+                        t_addr += 4 * dir;
+                        if (TRACE) ++h_cross;
+                        cont = cell != run_exit;
+                    }
+                } while (cont);
+                if (!fate) ev = crossed ? EV_MATCHANGE : EV_COLLIDE;
             }
         }
         __syncwarp();
 
         // ---------------- COLLIDE / material change
         if (ev == EV_COLLIDE) {
-            score(lo_base, hi_off, g * N + cell, fabsf(fast_div(fsub(x, end), rc)));
+            score(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, fabsf(fast_div(fsub(x, end), rc)));
             ++h_coll;
             const int xs = mat + M * xsg; // stale group index, src/mc_code.rs:147
             const float xi_int = pcg32_unit(rng, inc);

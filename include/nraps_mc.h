@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NRAPS_ABI_VERSION 1
+#define NRAPS_ABI_VERSION 2
 #define NRAPS_TALLY_FRAC_BITS 28 /* tallies are exact integers in 2^-28 cm */
 
 enum {
@@ -75,6 +75,8 @@ typedef struct nraps_options {
     int32_t blocks_per_sm;         /* 0 = auto */
     int32_t chunk;                 /* histories a warp claims per global atomic; 0 = auto */
     int32_t quiet;                 /* 0 = print "running MC code" (src/mc_code.rs:292) */
+    int32_t bank_cap;              /* fission_bank: sites kept per history, 1..255; 0 = 8 */
+    int32_t reserved0;
     uint64_t max_flights;          /* per-history safety cap; 0 = 1<<24               */
 } nraps_options;
 
@@ -100,6 +102,8 @@ typedef struct nraps_results {
     uint64_t *tally_fixed;          /* optional [generations][G][N], 2^-28 units (forces a sync per generation) */
     uint64_t counters[NRAPS_CT_WORDS]; /* summed over generations; crossings/flights/reflections only in trace runs */
     double seconds_device;          /* CUDA-event time of the generation loop */
+    uint64_t *bank_sizes;           /* optional [generations]: sites banked by each generation (fission_bank mode) */
+    double *entropy;                /* optional [generations]: Shannon entropy (bits) of that bank over mesh cells */
 } nraps_results;
 
 typedef struct nraps_mc_ctx nraps_mc_ctx;
@@ -127,6 +131,16 @@ int nraps_mc_fetch(nraps_mc_ctx *ctx, nraps_results *r, void *stream);          
 /* replay: run [hist_begin, hist_begin+hist_count) of `gen` and return one record per history (synchronous) */
 int nraps_mc_trace(nraps_mc_ctx *ctx, uint64_t gen, uint64_t hist_begin, uint64_t hist_count,
                    uint32_t *host_records, void *stream);
+/*
+ * fission_bank source mode (power iteration; no reference counterpart).  After transport of generation g:
+ *   bank_compact    -> this rank's sites in canonical (history, site) order, (cell << 32 | x bits) each
+ *   bank_local      -> device pointer + count of that dense local bank (synchronous)
+ *   bank_set_source -> the bank generation g+1 samples from: NULL = the local bank (single GPU), or the
+ *                      caller's all-gathered bank (rank order); also records bank size and entropy of `gen`
+ */
+int nraps_mc_bank_compact(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
+int nraps_mc_bank_local(nraps_mc_ctx *ctx, void **device_sites, uint64_t *count, void *stream);
+int nraps_mc_bank_set_source(nraps_mc_ctx *ctx, uint64_t gen, const void *device_sites, uint64_t count, void *stream);
 /* launch geometry chosen for this context: {grid, block, dynamic smem bytes, blocks/SM, SM count, chunk} */
 int nraps_mc_launch_info(nraps_mc_ctx *ctx, uint32_t out[6]);
 

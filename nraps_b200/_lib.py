@@ -40,7 +40,8 @@ class Options(C.Structure):
         ("seed", C.c_uint64), ("stream", C.c_uint64), ("stride", C.c_uint64),
         ("device", C.c_int32), ("scatter_mode", C.c_int32), ("stale_xs", C.c_int32), ("source_mode", C.c_int32),
         ("tracking_mode", C.c_int32), ("kernel_variant", C.c_int32), ("threads_per_block", C.c_int32),
-        ("blocks_per_sm", C.c_int32), ("chunk", C.c_int32), ("quiet", C.c_int32), ("max_flights", C.c_uint64),
+        ("blocks_per_sm", C.c_int32), ("chunk", C.c_int32), ("quiet", C.c_int32), ("bank_cap", C.c_int32),
+        ("reserved0", C.c_int32), ("max_flights", C.c_uint64),
     ]
 
 
@@ -48,6 +49,7 @@ class Results(C.Structure):
     _fields_ = [
         ("flux", _fp), ("assembly_average", _fp), ("fission_source", _fp), ("k", _fp), ("k_fund", _fp),
         ("tally_fixed", _u64p), ("counters", C.c_uint64 * CT_WORDS), ("seconds_device", C.c_double),
+        ("bank_sizes", _u64p), ("entropy", C.POINTER(C.c_double)),
     ]
 
 
@@ -77,7 +79,8 @@ class Mesh(C.Structure):
 EXPORTS = [
     "nraps_mc_run", "nraps_mc_create", "nraps_mc_destroy", "nraps_mc_reset", "nraps_mc_transport",
     "nraps_mc_finalize_generation", "nraps_mc_tally_buffer", "nraps_mc_set_tally_buffer", "nraps_mc_read_tally",
-    "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
+    "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_mc_bank_compact", "nraps_mc_bank_local",
+    "nraps_mc_bank_set_source", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
     "nraps_strerror", "nraps_last_cuda_error", "nraps_abi_version",
     "nraps_process_input", "nraps_deck_free", "nraps_mesh_gen", "nraps_mesh_free", "nraps_problem_from",
     "nraps_format_f32", "nraps_format_f64", "nraps_plot_solution", "nraps_average_assembly", "nraps_k_fund",
@@ -109,6 +112,9 @@ def lib() -> C.CDLL:
     L.nraps_mc_fetch.argtypes = [vp, C.POINTER(Results), vp]
     L.nraps_mc_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, vp]
     L.nraps_mc_launch_info.argtypes = [vp, _u32p]
+    L.nraps_mc_bank_compact.argtypes = [vp, C.c_uint64, vp]
+    L.nraps_mc_bank_local.argtypes = [vp, C.POINTER(vp), _u64p, vp]
+    L.nraps_mc_bank_set_source.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp]
     L.nraps_dev_logf.argtypes = [_fp, _fp, C.c_uint32, C.c_int32]
     L.nraps_dev_div.argtypes = [_fp, _fp, _fp, _fp, C.c_uint32, C.c_int32]
     L.nraps_dev_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _u32p, _fp, C.c_int32]

@@ -86,6 +86,8 @@ class SolutionResults:  # src/main.rs:77-83
     counters: dict = field(default_factory=dict)
     seconds_device: float = 0.0
     tally_fixed: np.ndarray | None = None
+    bank_sizes: np.ndarray | None = None  # fission_bank mode: sites banked per generation
+    entropy: np.ndarray | None = None     # fission_bank mode: Shannon entropy (bits) of each bank over cells
 
 
 def _np(ptr, n, dtype):
@@ -134,6 +136,13 @@ def mesh_gen(matid, variables: Variables, deltax: DeltaX):
         lib().nraps_mesh_free(C.byref(m))
 
 
+class _DevArray:
+    """__cuda_array_interface__ view of n int64 words at a raw device pointer."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
 class _Marshalled:
     """Keeps the numpy buffers a Problem points into alive."""
 
@@ -166,12 +175,13 @@ class _Marshalled:
 
 def make_options(*, seed=0, stream=0, stride=0, device=0, scatter_mode="single_xi", stale_xs=True,
                  source_mode="uniform_fuel", tracking_mode="surface", kernel_variant="fused", threads_per_block=0,
-                 blocks_per_sm=0, chunk=0, quiet=True, max_flights=0) -> Options:
+                 blocks_per_sm=0, chunk=0, quiet=True, max_flights=0, bank_cap=0) -> Options:
     return Options(
         seed=seed, stream=stream, stride=stride, device=device, scatter_mode=SCATTER_MODES[scatter_mode],
         stale_xs=int(bool(stale_xs)), source_mode=SOURCE_MODES[source_mode], tracking_mode=TRACKING_MODES[tracking_mode],
         kernel_variant=KERNEL_VARIANTS[kernel_variant], threads_per_block=threads_per_block,
-        blocks_per_sm=blocks_per_sm, chunk=chunk, quiet=int(bool(quiet)), max_flights=max_flights,
+        blocks_per_sm=blocks_per_sm, chunk=chunk, quiet=int(bool(quiet)), bank_cap=bank_cap, reserved0=0,
+        max_flights=max_flights,
     )
 
 
@@ -183,15 +193,19 @@ class _ResultBuffers:
         self.k = np.zeros(gens, np.float32)
         self.kf = np.zeros(gens, np.float32)
         self.tally = np.zeros((gens, G, N), np.uint64) if want_tally else None
+        self.bank_sizes = np.zeros(gens, np.uint64)
+        self.entropy = np.zeros(gens, np.float64)
         p = lambda a, t=C.c_float: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
         self.c = Results(flux=p(self.flux), assembly_average=p(self.avg), fission_source=p(self.fis), k=p(self.k),
-                         k_fund=p(self.kf), tally_fixed=p(self.tally, C.c_uint64) if want_tally else None)
+                         k_fund=p(self.kf), tally_fixed=p(self.tally, C.c_uint64) if want_tally else None,
+                         bank_sizes=p(self.bank_sizes, C.c_uint64), entropy=p(self.entropy, C.c_double))
 
     def solution(self) -> SolutionResults:
         return SolutionResults(
             flux=self.flux, assembly_average=self.avg, fission_source=self.fis, k=self.k, k_fund=self.kf,
             counters={n: int(self.c.counters[i]) for i, n in enumerate(CT_NAMES)},
-            seconds_device=float(self.c.seconds_device), tally_fixed=self.tally,
+            seconds_device=float(self.c.seconds_device), tally_fixed=self.tally, bank_sizes=self.bank_sizes,
+            entropy=self.entropy,
         )
 
 
@@ -268,6 +282,36 @@ class MonteCarloContext:
         check(lib().nraps_mc_trace(self._h, gen, hist_begin, hist_count, rec.ctypes.data_as(C.POINTER(C.c_uint32)),
                                    C.c_void_p(stream)), "nraps_mc_trace")
         return rec
+
+    # ---- fission_bank source mode
+    def bank_compact(self, gen: int, stream=None):
+        check(lib().nraps_mc_bank_compact(self._h, gen, C.c_void_p(stream)), "nraps_mc_bank_compact")
+
+    def bank_local(self, stream=None):
+        """(device pointer, count) of this rank's dense bank (synchronises the stream)."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        check(lib().nraps_mc_bank_local(self._h, C.byref(ptr), C.byref(n), C.c_void_p(stream)), "nraps_mc_bank_local")
+        return ptr.value, n.value
+
+    def bank_set_source(self, gen: int, tensor=None, stream=None):
+        """Bank that generation gen+1 samples from: None = the local bank, else an int64 CUDA tensor of sites."""
+        if tensor is None:
+            ptr, n = None, 0
+        else:
+            assert tensor.is_cuda and tensor.element_size() == 8 and tensor.is_contiguous()
+            self._src = tensor  # keep alive until replaced
+            ptr, n = tensor.data_ptr(), tensor.numel()
+        check(lib().nraps_mc_bank_set_source(self._h, gen, C.c_void_p(ptr), n, C.c_void_p(stream)), "nraps_mc_bank_set_source")
+
+    def read_bank(self, stream=None) -> np.ndarray:
+        """Host copy of the local dense bank (tests)."""
+        import torch
+
+        ptr, n = self.bank_local(stream)
+        if n == 0:
+            return np.zeros(0, np.uint64)
+        view = torch.as_tensor(_DevArray(ptr, n), device=f"cuda:{self._o.device}")
+        return view.cpu().numpy().view(np.uint64).copy()
 
     def fetch(self, stream=None) -> SolutionResults:
         rb = _ResultBuffers(self.G, self.N, self.generations)

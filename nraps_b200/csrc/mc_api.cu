@@ -105,6 +105,21 @@ struct nraps_mc_ctx {
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
     uint32_t *d_trace = nullptr;
     uint64_t trace_cap = 0;
+
+    // fission_bank source mode
+    bool bank_mode = false;
+    uint32_t bank_cap = 8;
+    uint64_t bank_hist_cap = 0, dense_cap = 0; // histories / sites the buffers below are sized for
+    unsigned long long *d_slots = nullptr, *d_block_sums = nullptr, *d_dense[2] = {nullptr, nullptr};
+    unsigned long long *d_bank_count = nullptr;  // [3]: count of dense[0], dense[1], external source
+    unsigned long long *d_bank_sizes = nullptr;  // [generations]
+    double *d_entropy = nullptr;                 // [generations]
+    uint8_t *d_counts = nullptr;
+    uint32_t *d_hist = nullptr;
+    int bank_which = 0;                          // dense buffer the next compaction writes
+    const unsigned long long *src_bank = nullptr, *src_count_ptr = nullptr;
+    uint64_t ext_count_host = 0;
+    uint64_t last_shard = 0;
 };
 
 namespace {
@@ -121,8 +136,8 @@ int validate(const nraps_problem *p, const nraps_options *o)
         return NRAPS_ERR_SHAPE;
     if ((uint64_t)p->M * p->G * p->G * p->G > 8192) return NRAPS_ERR_TOO_LARGE;
     if (o->scatter_mode < 0 || o->scatter_mode > NRAPS_SCATTER_RUST_182) return NRAPS_ERR_OPTION;
-    if (o->source_mode != NRAPS_SOURCE_UNIFORM_FUEL || o->tracking_mode != NRAPS_TRACK_SURFACE ||
-        o->kernel_variant != NRAPS_KERNEL_FUSED)
+    if (o->source_mode < 0 || o->source_mode > NRAPS_SOURCE_FISSION_BANK || o->tracking_mode != NRAPS_TRACK_SURFACE ||
+        o->kernel_variant != NRAPS_KERNEL_FUSED || o->bank_cap < 0 || o->bank_cap > 255)
         return NRAPS_ERR_OPTION;
     for (uint32_t i = 0; i < p->N; ++i) {
         if (p->matid[i] >= p->M) return NRAPS_ERR_MESH;
@@ -147,12 +162,40 @@ void free_ctx(nraps_mc_ctx *c)
     cudaFree(c->d_tally_own); cudaFree(c->d_work); cudaFree(c->d_counters_total);
     cudaFree(c->d_terms); cudaFree(c->d_res_flux); cudaFree(c->d_res_fission); cudaFree(c->d_k_hist); cudaFree(c->d_k_cur);
     cudaFree(c->d_trace);
+    cudaFree(c->d_slots); cudaFree(c->d_block_sums); cudaFree(c->d_dense[0]); cudaFree(c->d_dense[1]);
+    cudaFree(c->d_bank_count); cudaFree(c->d_bank_sizes); cudaFree(c->d_entropy); cudaFree(c->d_counts); cudaFree(c->d_hist);
     delete c;
+}
+
+// (re)size the per-history slot rows and the dense banks for a shard of `count` histories
+int ensure_bank(nraps_mc_ctx *c, uint64_t count)
+{
+    if (count <= c->bank_hist_cap) return NRAPS_OK;
+    cudaFree(c->d_slots); cudaFree(c->d_counts); cudaFree(c->d_block_sums); cudaFree(c->d_dense[0]); cudaFree(c->d_dense[1]);
+    c->d_slots = c->d_block_sums = c->d_dense[0] = c->d_dense[1] = nullptr;
+    c->d_counts = nullptr;
+    c->bank_hist_cap = 0;
+    const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
+    c->dense_cap = 3 * count + 1024; // a bank larger than 3 sites per history is truncated (k / k_prev > 3)
+    CU(cudaMalloc((void **)&c->d_slots, padded * c->bank_cap * sizeof(unsigned long long)));
+    CU(cudaMalloc((void **)&c->d_counts, padded));
+    CU(cudaMalloc((void **)&c->d_block_sums, (padded / kBankTile) * sizeof(unsigned long long)));
+    CU(cudaMalloc((void **)&c->d_dense[0], c->dense_cap * sizeof(unsigned long long)));
+    CU(cudaMalloc((void **)&c->d_dense[1], c->dense_cap * sizeof(unsigned long long)));
+    c->bank_hist_cap = count;
+    return NRAPS_OK;
 }
 
 int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count, bool trace, cudaStream_t s)
 {
     if (begin > c->histories || count > c->histories - begin) return NRAPS_ERR_SHAPE;
+    c->last_shard = count;
+    if (c->bank_mode) {
+        int rc = ensure_bank(c, count);
+        if (rc != NRAPS_OK) return rc;
+        const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
+        if (padded) CU(cudaMemsetAsync(c->d_counts, 0, padded, s));
+    }
     const uint64_t words = (uint64_t)c->G * c->N + NRAPS_CT_WORDS;
     CU(cudaMemsetAsync(c->d_tally, 0, words * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
@@ -172,7 +215,9 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
-    CU(launch_transport(P, trace, dim3(c->grid), dim3(c->block), c->layout.total, s));
+    P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
+    P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
+    CU(launch_transport(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
     return NRAPS_OK;
 }
 
@@ -230,6 +275,8 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     c->layout = L;
     c->max_flights = (uint32_t)std::min<uint64_t>(o->max_flights ? o->max_flights : (1ull << 24), 0xffffffffull);
     c->chunk = o->chunk > 0 ? (uint32_t)o->chunk : 64u;
+    c->bank_mode = (o->source_mode == NRAPS_SOURCE_FISSION_BANK);
+    c->bank_cap = o->bank_cap > 0 ? (uint32_t)o->bank_cap : 8u;
 
     // launch geometry: persistent grid, a multiple of the SM count
     uint32_t bps = o->blocks_per_sm > 0 ? (uint32_t)o->blocks_per_sm : 2u;
@@ -253,11 +300,12 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     }
     for (uint32_t j = 0; j < NF; ++j) fuel[j] = (uint16_t)p->fuel_indices[j];
 
-    std::vector<float> xs(3 * MG + MG * G * G);
-    float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *scat_cdf = chi_cdf + MG;
+    std::vector<float> xs(4 * MG + MG * G * G);
+    float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *nusigf = chi_cdf + MG, *scat_cdf = nusigf + MG;
     for (uint32_t i = 0; i < MG; ++i) {
         inv_sigtr[i] = p->inv_sigtr[i];
         p_abs[i] = p->siga[i] / p->sigt[i];
+        nusigf[i] = p->nut[i] * p->sigf[i];
     }
     for (uint32_t m = 0; m < M; ++m) {
         float cum = 0.0f;
@@ -298,6 +346,10 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     ok(cudaMalloc((void **)&c->d_res_fission, N * sizeof(float)));
     ok(cudaMalloc((void **)&c->d_k_hist, c->generations * sizeof(float)));
     ok(cudaMalloc((void **)&c->d_k_cur, sizeof(float)));
+    ok(cudaMalloc((void **)&c->d_bank_count, 3 * sizeof(unsigned long long)));
+    ok(cudaMalloc((void **)&c->d_bank_sizes, c->generations * sizeof(unsigned long long)));
+    ok(cudaMalloc((void **)&c->d_entropy, c->generations * sizeof(double)));
+    ok(cudaMalloc((void **)&c->d_hist, N * sizeof(uint32_t)));
     ok(prepare_transport(L.total));
     if (e != cudaSuccess) {
         free_ctx(c);
@@ -329,6 +381,10 @@ extern "C" int nraps_mc_reset(nraps_mc_ctx *c, float k0, void *stream)
     CU(cudaMemsetAsync(c->d_res_fission, 0, c->N * sizeof(float), s));
     CU(cudaMemsetAsync(c->d_k_hist, 0, c->generations * sizeof(float), s));
     CU(cudaMemsetAsync(c->d_counters_total, 0, NRAPS_CT_WORDS * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(c->d_bank_count, 0, 3 * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(c->d_bank_sizes, 0, c->generations * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(c->d_entropy, 0, c->generations * sizeof(double), s));
+    c->src_bank = nullptr; c->src_count_ptr = nullptr; c->bank_which = 0;
     CU(cudaMemcpyAsync(c->d_k_cur, &k0, sizeof(float), cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s)); // k0 lives on the caller's stack
     return NRAPS_OK;
@@ -396,6 +452,8 @@ extern "C" int nraps_mc_fetch(nraps_mc_ctx *c, nraps_results *r, void *stream)
     CU(cudaMemcpyAsync(r->fission_source, c->d_res_fission, c->N * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(r->k, c->d_k_hist, c->generations * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(r->counters, c->d_counters_total, NRAPS_CT_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (r->bank_sizes) CU(cudaMemcpyAsync(r->bank_sizes, c->d_bank_sizes, c->generations * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (r->entropy) CU(cudaMemcpyAsync(r->entropy, c->d_entropy, c->generations * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     // average_assembly (src/mc_code.rs:259-274) and k_fund (:368-376): O(G*N), O(gens^2) host work
     const uint32_t span = c->N / c->numass;
@@ -441,6 +499,55 @@ extern "C" int nraps_mc_trace(nraps_mc_ctx *c, uint64_t gen, uint64_t hist_begin
     return NRAPS_OK;
 }
 
+extern "C" int nraps_mc_bank_compact(nraps_mc_ctx *c, uint64_t gen, void *stream)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    if (!c->bank_mode || gen >= c->generations) return NRAPS_ERR_STATE;
+    CU(cudaSetDevice(c->device));
+    BankParams B{};
+    const uint64_t padded = (c->last_shard + kBankTile - 1) / kBankTile * kBankTile;
+    B.counts = c->d_counts; B.slots = c->d_slots; B.dense = c->d_dense[c->bank_which];
+    B.block_sums = c->d_block_sums; B.count_out = c->d_bank_count + c->bank_which;
+    B.n_hist = c->last_shard; B.dense_cap = c->dense_cap; B.cap = c->bank_cap; B.n_tiles = (uint32_t)(padded / kBankTile);
+    CU(launch_bank_compact(B, static_cast<cudaStream_t>(stream)));
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_bank_local(nraps_mc_ctx *c, void **device_sites, uint64_t *count, void *stream)
+{
+    if (!c || !device_sites || !count) return NRAPS_ERR_NULL;
+    if (!c->bank_mode) return NRAPS_ERR_STATE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU(cudaSetDevice(c->device));
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, c->d_bank_count + c->bank_which, sizeof(n), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *device_sites = c->d_dense[c->bank_which];
+    *count = n;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_bank_set_source(nraps_mc_ctx *c, uint64_t gen, const void *device_sites, uint64_t count, void *stream)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    if (!c->bank_mode || gen >= c->generations) return NRAPS_ERR_STATE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU(cudaSetDevice(c->device));
+    if (device_sites) { // caller-owned (all-gathered) bank; must stay valid until the next transport has finished
+        if (count >> 32) return NRAPS_ERR_TOO_LARGE; // site index = (u32 * count) >> 32
+        c->ext_count_host = count;
+        CU(cudaMemcpyAsync(c->d_bank_count + 2, &c->ext_count_host, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        c->src_bank = static_cast<const unsigned long long *>(device_sites);
+        c->src_count_ptr = c->d_bank_count + 2;
+    } else {
+        c->src_bank = c->d_dense[c->bank_which];
+        c->src_count_ptr = c->d_bank_count + c->bank_which;
+    }
+    c->bank_which ^= 1;
+    CU(launch_bank_entropy(c->src_bank, c->src_count_ptr, c->d_hist, c->N, c->d_entropy + gen, c->d_bank_sizes + gen, s));
+    return NRAPS_OK;
+}
+
 extern "C" int nraps_mc_launch_info(nraps_mc_ctx *c, uint32_t out[6])
 {
     if (!c || !out) return NRAPS_ERR_NULL;
@@ -480,6 +587,10 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
             std::memcpy(r->tally_fixed + gen * GN, words.data(), GN * sizeof(uint64_t));
         }
         if ((rc = nraps_mc_finalize_generation(c, gen, s)) != NRAPS_OK) return bail(rc);
+        if (c->bank_mode) {
+            if ((rc = nraps_mc_bank_compact(c, gen, s)) != NRAPS_OK) return bail(rc);
+            if ((rc = nraps_mc_bank_set_source(c, gen, nullptr, 0, s)) != NRAPS_OK) return bail(rc);
+        }
     }
     cudaEventRecord(e1, s);
     if ((rc = nraps_mc_fetch(c, r, s)) != NRAPS_OK) return bail(rc);

@@ -18,7 +18,7 @@ struct SmemLayout {
     uint32_t edges;              // f32[N+1]   cell edges; left[i]=edges[i], right[i]=edges[i+1]
     uint32_t runb;               // u32[N]     material-run bounds of each cell: lo | hi<<16
     uint32_t jump;               // u64x2[64]  PCG32 jump table (A_b, C_b) for stride*2^b draws
-    uint32_t xs;                 // f32[...]   inv_sigtr[MG] | p_abs[MG] | chi_cdf[MG] | scat_cdf[M*G*G*G]
+    uint32_t xs;                 // f32[...]   inv_sigtr[MG] | p_abs[MG] | chi_cdf[MG] | nusigf[MG] | scat_cdf[M*G*G*G]
     uint32_t fuel;               // u16[NF]    fuel cell indices
     uint32_t matid;              // u8[N]
     uint32_t total;
@@ -36,7 +36,7 @@ __host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32
     L.edges = off;    off += (N + 1) * 4;
     L.runb = off;     off += N * 4;
     off = align_up(off, 16); // float4 rows of the CDF tables
-    L.xs = off;       off += (3 * M * G + M * G * G * G) * 4;
+    L.xs = off;       off += (4 * M * G + M * G * G * G) * 4;
     L.fuel = off;     off += align_up(NF * 2, 4);
     L.matid = off;    off += align_up(N, 4);
     L.total = align_up(off, 16);
@@ -62,7 +62,25 @@ struct TransportParams {
     uint32_t chunk;
     uint32_t max_flights;
     int32_t scatter_mode, stale_xs;
+    // fission_bank source mode
+    const unsigned long long *src_bank;      // dense sites (cell << 32 | x bits) feeding this generation, or nullptr
+    const unsigned long long *src_count_ptr; // device scalar: number of sites in src_bank
+    unsigned long long *slots;               // [hist_end-hist_begin][bank_cap] sites produced, by history
+    uint8_t *counts;                         // [hist_end-hist_begin]
+    const float *k_cur;                      // device scalar: k of the previous generation
+    uint32_t bank_cap;
 };
+
+struct BankParams {
+    const uint8_t *counts;            // [n_hist padded to kBankTile]
+    const unsigned long long *slots;  // [n_hist][cap]
+    unsigned long long *dense;        // [dense_cap]
+    unsigned long long *block_sums;   // [n_tiles]
+    unsigned long long *count_out;    // device scalar
+    uint64_t n_hist, dense_cap;
+    uint32_t cap, n_tiles;
+};
+constexpr uint32_t kBankTile = 16384; // histories per block of the compaction kernels (1024 threads x 16)
 
 struct FinalizeParams {
     const unsigned long long *tally; // [G*N]
@@ -81,7 +99,10 @@ struct FinalizeParams {
     uint64_t gen, skip;
 };
 
-cudaError_t launch_transport(const TransportParams &p, bool trace, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
+cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
+cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s);
+cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
+                                double *entropy_out, unsigned long long *size_out, cudaStream_t s);
 cudaError_t prepare_transport(uint32_t smem_bytes);
 cudaError_t launch_finalize(const FinalizeParams &p, cudaStream_t s);
 cudaError_t launch_probe_logf(const float *x, float *out, uint32_t n, cudaStream_t s);

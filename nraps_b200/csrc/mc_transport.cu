@@ -114,7 +114,7 @@ __device__ __forceinline__ uint64_t jump_ahead(uint64_t state, uint64_t steps, c
 
 enum { EV_NONE = 0, EV_COLLIDE = 1, EV_MATCHANGE = 2 };
 
-template <int TG, bool TRACE>
+template <int TG, bool TRACE, bool BANK>
 __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -137,10 +137,14 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     for (int i = tid; i <= N; i += nthr) s_edges[i] = P.edges[i];
     for (int i = tid; i < N; i += nthr) { s_runb[i] = P.runb[i]; s_matid[i] = P.matid[i]; }
     for (int i = tid; i < (int)P.NF; i += nthr) s_fuel[i] = P.fuel[i];
-    for (int i = tid; i < 3 * MG + MG * G * G; i += nthr) s_xs[i] = P.xs[i];
+    for (int i = tid; i < 4 * MG + MG * G * G; i += nthr) s_xs[i] = P.xs[i];
     for (int i = tid; i < 64; i += nthr) s_jump[i] = P.jump[i];
     __syncthreads();
-    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_chi = s_xs + 2 * MG, *s_scat = s_xs + 3 * MG;
+    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_chi = s_xs + 2 * MG, *s_nusigf = s_xs + 3 * MG,
+                *s_scat = s_xs + 4 * MG;
+    // fission_bank mode: sites are banked with weight nu*Sigma_f * inv_sigtr / k_prev; an empty bank => uniform source
+    const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
+    const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
     const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(s_lo);
     const uint32_t hi_off = L.tally_hi - L.tally_lo;
     const uint32_t edges_base = (uint32_t)__cvta_generic_to_shared(s_edges);
@@ -158,8 +162,8 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     uint64_t rng = 0, y = 0;
     float x = 0.f, mu = 1.f, ds = 0.f;
     int cell = 0, g = 0, xsg = 0, mat = 0, run_lo = 0, run_hi = 0;
-    uint32_t h_coll = 0, h_cross = 0, h_flight = 0, h_refl = 0; // this history
-    uint32_t c_hist = 0, c_coll = 0, c_cross = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0;
+    uint32_t h_coll = 0, h_cross = 0, h_flight = 0, h_refl = 0, h_bank = 0; // this history
+    uint32_t c_hist = 0, c_coll = 0, c_cross = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0, c_bank = 0;
 
     for (;;) {
         __syncwarp();
@@ -186,16 +190,25 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     // per-history stream = master advanced by y*stride draws; jump maps commute, so
                     // start from the chunk cursor and add the (small) rank
                     rng = jump_ahead(w_state, rank, s_jump);
-                    // draw order cell, position, mu, chi (src/mc_code.rs:46-51)
                     const uint32_t u = pcg32_next(rng, inc);
-                    cell = s_fuel[__umulhi(u, P.NF)];
-                    const float xi_pos = pcg32_unit(rng, inc);
-                    mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
+                    if (BANK && src_count) {
+                        // fission_bank source: site index, mu, chi (the site carries position and cell)
+                        const unsigned long long site = __ldg(P.src_bank + (((unsigned long long)u * src_count) >> 32));
+                        cell = (int)(site >> 32);
+                        x = __uint_as_float((uint32_t)site);
+                        mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
+                    } else {
+                        // draw order cell, position, mu, chi (src/mc_code.rs:46-51)
+                        cell = s_fuel[__umulhi(u, P.NF)];
+                        const float xi_pos = pcg32_unit(rng, inc);
+                        mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
+                        x = fadd(s_edges[cell], fmul(xi_pos, P.dx_fuel));
+                    }
                     const float xi_chi = pcg32_unit(rng, inc);
                     mat = s_matid[cell];
                     g = search_cdf<TG>(s_chi + mat * G, G, xi_chi);
                     xsg = g;
-                    x = fadd(s_edges[cell], fmul(xi_pos, P.dx_fuel));
+                    h_bank = 0;
                     const uint32_t rb = s_runb[cell];
                     run_lo = (int)(rb & 0xffffu);
                     run_hi = (int)(rb >> 16);
@@ -287,6 +300,18 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
             const float xi_int = pcg32_unit(rng, inc);
             const float mu_new = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
             const int g_new = sample_group<TG>(s_scat + ((mat * G + g) * G + xsg) * G, G, P.scatter_mode, rng, inc);
+            if (BANK) {
+                const float nusigf = s_nusigf[mat + M * g];
+                if (nusigf > 0.0f) {
+                    const float wgt = fmul(fmul(nusigf, s_inv_sigtr[xs]), inv_k);
+                    const uint32_t n = (uint32_t)__float2int_rz(fadd(wgt, pcg32_unit(rng, inc)));
+                    const unsigned long long site = ((unsigned long long)(uint32_t)cell << 32) | __float_as_uint(end);
+                    for (uint32_t j = 0; j < n; ++j) {
+                        if (h_bank < P.bank_cap) P.slots[(y - P.hist_begin) * P.bank_cap + h_bank] = site;
+                        ++h_bank;
+                    }
+                }
+            }
             if (xi_int < s_p_abs[xs]) {
                 fate = NRAPS_FATE_ABSORBED;
             } else {
@@ -315,6 +340,11 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
             c_flight += h_flight;
             c_leak += (fate == NRAPS_FATE_LEAKED);
             c_trunc += (fate == NRAPS_FATE_TRUNCATED);
+            if (BANK) {
+                const uint32_t kept = h_bank < P.bank_cap ? h_bank : P.bank_cap;
+                P.counts[y - P.hist_begin] = (uint8_t)kept;
+                c_bank += kept;
+            }
             if (TRACE) {
                 c_cross += h_cross; c_refl += h_refl;
                 if (P.trace) {
@@ -341,9 +371,9 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
         if (v) atomicAdd(&P.tally[i], v);
     }
     unsigned long long *ct = P.tally + GN;
-    uint32_t vals[7] = {c_hist, c_coll, c_cross, c_flight, c_refl, c_leak, c_trunc};
+    uint32_t vals[8] = {c_hist, c_coll, c_cross, c_flight, c_refl, c_leak, c_trunc, c_bank};
 #pragma unroll
-    for (int c = 0; c < 7; ++c) {
+    for (int c = 0; c < 8; ++c) {
         unsigned long long v = vals[c];
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -352,16 +382,26 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
 }
 
 template <int TG>
-cudaError_t launch_g(const TransportParams &p, bool trace, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
+cudaError_t launch_g(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
 {
-    if (trace) transport_kernel<TG, true><<<grid, block, smem, s>>>(p);
-    else transport_kernel<TG, false><<<grid, block, smem, s>>>(p);
+    if (bank) {
+        if (trace) transport_kernel<TG, true, true><<<grid, block, smem, s>>>(p);
+        else transport_kernel<TG, false, true><<<grid, block, smem, s>>>(p);
+    } else {
+        if (trace) transport_kernel<TG, true, false><<<grid, block, smem, s>>>(p);
+        else transport_kernel<TG, false, false><<<grid, block, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 
-template <int TG, bool TRACE> cudaError_t set_smem(uint32_t bytes)
+template <int TG> cudaError_t set_smem(uint32_t bytes)
 {
-    return cudaFuncSetAttribute(transport_kernel<TG, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e;
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if ((e = cudaFuncSetAttribute(transport_kernel<TG, false, false>, attr, (int)bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(transport_kernel<TG, true, false>, attr, (int)bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(transport_kernel<TG, false, true>, attr, (int)bytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(transport_kernel<TG, true, true>, attr, (int)bytes);
 }
 
 } // namespace
@@ -369,20 +409,17 @@ template <int TG, bool TRACE> cudaError_t set_smem(uint32_t bytes)
 cudaError_t prepare_transport(uint32_t smem_bytes)
 {
     cudaError_t e;
-    if ((e = set_smem<2, false>(smem_bytes)) != cudaSuccess) return e;
-    if ((e = set_smem<2, true>(smem_bytes)) != cudaSuccess) return e;
-    if ((e = set_smem<4, false>(smem_bytes)) != cudaSuccess) return e;
-    if ((e = set_smem<4, true>(smem_bytes)) != cudaSuccess) return e;
-    if ((e = set_smem<0, false>(smem_bytes)) != cudaSuccess) return e;
-    return set_smem<0, true>(smem_bytes);
+    if ((e = set_smem<2>(smem_bytes)) != cudaSuccess) return e;
+    if ((e = set_smem<4>(smem_bytes)) != cudaSuccess) return e;
+    return set_smem<0>(smem_bytes);
 }
 
-cudaError_t launch_transport(const TransportParams &p, bool trace, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
+cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
 {
     switch (p.G) {
-    case 2: return launch_g<2>(p, trace, grid, block, smem, s);
-    case 4: return launch_g<4>(p, trace, grid, block, smem, s);
-    default: return launch_g<0>(p, trace, grid, block, smem, s);
+    case 2: return launch_g<2>(p, trace, bank, grid, block, smem, s);
+    case 4: return launch_g<4>(p, trace, bank, grid, block, smem, s);
+    default: return launch_g<0>(p, trace, bank, grid, block, smem, s);
     }
 }
 

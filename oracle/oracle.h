@@ -46,7 +46,7 @@ typedef struct {
     int32_t threads;            /* 0 => hardware_concurrency-1 (mc_code.rs:302) */
     int32_t source_mode;
     int32_t tracking_mode;
-    int32_t reserved;
+    int32_t bank_cap;           /* fission_bank: max sites kept per history (0 => 8) */
     uint64_t hist_begin, hist_count; /* sub-range of each generation; count 0 => all */
     uint64_t max_flights;            /* per-history safety cap, 0 => 1<<24    */
 } oracle_options;
@@ -75,7 +75,10 @@ typedef struct {
     uint32_t *trace;                /* optional [hist_count][ORACLE_TR_WORDS] */
     uint64_t trace_gen;
     uint64_t counters[ORACLE_CT_WORDS]; /* summed over all generations      */
-    uint64_t *bank_sizes;           /* optional [gens], fission_bank mode   */
+    uint64_t *bank_sizes;           /* optional [gens], fission_bank mode: sites banked by each generation */
+    uint64_t *bank_sites;           /* optional: dense bank produced by generation `bank_gen`, (cell << 32 | x bits) */
+    uint64_t bank_sites_cap, bank_gen;
+    double *entropy;                /* optional [gens]: Shannon entropy (bits) of the banked sites over cells */
     double seconds_transport;       /* wall time inside the history loops   */
 } oracle_results;
 

@@ -48,7 +48,7 @@ class Options(C.Structure):
         ("seed", C.c_uint64), ("seq", C.c_uint64), ("stride", C.c_uint64),
         ("scatter_mode", C.c_int32), ("stale_xs", C.c_int32), ("tally_mode", C.c_int32),
         ("inclusive_ranges", C.c_int32), ("threads", C.c_int32), ("source_mode", C.c_int32),
-        ("tracking_mode", C.c_int32), ("reserved", C.c_int32),
+        ("tracking_mode", C.c_int32), ("bank_cap", C.c_int32),
         ("hist_begin", C.c_uint64), ("hist_count", C.c_uint64), ("max_flights", C.c_uint64),
     ]
 
@@ -58,6 +58,8 @@ class Results(C.Structure):
         ("flux", _fp), ("assembly_average", _fp), ("fission_source", _fp), ("k", _fp), ("k_fund", _fp),
         ("tally_fixed", C.POINTER(C.c_uint64)), ("trace", C.POINTER(C.c_uint32)), ("trace_gen", C.c_uint64),
         ("counters", C.c_uint64 * CT_WORDS), ("bank_sizes", C.POINTER(C.c_uint64)),
+        ("bank_sites", C.POINTER(C.c_uint64)), ("bank_sites_cap", C.c_uint64), ("bank_gen", C.c_uint64),
+        ("entropy", C.POINTER(C.c_double)),
         ("seconds_transport", C.c_double),
     ]
 
@@ -120,6 +122,8 @@ class OracleOutput:
     bank_sizes: np.ndarray | None
     seconds_transport: float
     threads: int = 0
+    bank_sites: np.ndarray | None = None
+    entropy: np.ndarray | None = None
     extra: dict = field(default_factory=dict)
 
 
@@ -127,7 +131,7 @@ def monte_carlo(deck, mesh, *, generations=None, histories=None, skip=None, k0=1
                 seed=42, seq=54, stride=152917, scatter_mode="single_xi", stale_xs=True,
                 tally_mode="fixed64", inclusive_ranges=False, threads=1, source_mode="uniform_fuel",
                 tracking_mode="surface", hist_begin=0, hist_count=0, max_flights=0,
-                want_tally=False, trace_gen=None) -> OracleOutput:
+                want_tally=False, trace_gen=None, bank_cap=0, bank_gen=None) -> OracleOutput:
     """Run the CPU oracle.  ``deck`` is a host_oracle.Deck-like object (attribute
     access), ``mesh`` the tuple returned by ``mesh_gen``."""
     cell_mat, dx, left, right, fuel = mesh
@@ -153,7 +157,7 @@ def monte_carlo(deck, mesh, *, generations=None, histories=None, skip=None, k0=1
     o = Options(
         seed=seed, seq=seq, stride=stride, scatter_mode=SCATTER_MODES[scatter_mode], stale_xs=int(bool(stale_xs)),
         tally_mode=TALLY_MODES[tally_mode], inclusive_ranges=int(bool(inclusive_ranges)), threads=int(threads),
-        source_mode=SOURCE_MODES[source_mode], tracking_mode=TRACKING_MODES[tracking_mode], reserved=0,
+        source_mode=SOURCE_MODES[source_mode], tracking_mode=TRACKING_MODES[tracking_mode], bank_cap=int(bank_cap),
         hist_begin=int(hist_begin), hist_count=int(hist_count), max_flights=int(max_flights),
     )
     nh = int(hist_count) if hist_count else H
@@ -165,11 +169,16 @@ def monte_carlo(deck, mesh, *, generations=None, histories=None, skip=None, k0=1
     tally = np.zeros((gens, G, N), np.uint64) if want_tally else None
     trace = np.zeros((nh, TR_WORDS), np.uint32) if trace_gen is not None else None
     banks = np.zeros(gens, np.uint64)
+    entropy = np.zeros(gens, np.float64)
+    sites_cap = nh * (int(bank_cap) or 8) if bank_gen is not None else 0
+    sites = np.zeros(max(1, sites_cap), np.uint64)
     r = Results(
         flux=_p(flux), assembly_average=_p(avg), fission_source=_p(fis), k=_p(k), k_fund=_p(kf),
         tally_fixed=_p(tally, C.c_uint64) if tally is not None else None,
         trace=_p(trace, C.c_uint32) if trace is not None else None,
         trace_gen=int(trace_gen or 0), bank_sizes=_p(banks, C.c_uint64),
+        bank_sites=_p(sites, C.c_uint64) if bank_gen is not None else None, bank_sites_cap=sites_cap,
+        bank_gen=int(bank_gen or 0), entropy=_p(entropy, C.c_double),
     )
     rc = lib().oracle_monte_carlo(C.byref(p), C.byref(o), C.byref(r))
     if rc != 0:
@@ -178,4 +187,5 @@ def monte_carlo(deck, mesh, *, generations=None, histories=None, skip=None, k0=1
         flux=flux, assembly_average=avg, fission_source=fis, k=k, k_fund=kf, tally_fixed=tally, trace=trace,
         counters={n: int(r.counters[i]) for i, n in enumerate(CT_NAMES)}, bank_sizes=banks,
         seconds_transport=float(r.seconds_transport), threads=int(threads),
+        bank_sites=sites[: int(banks[bank_gen])] if bank_gen is not None else None, entropy=entropy,
     )

@@ -38,7 +38,15 @@ typedef struct {
     oracle_pcg32 master;
     uint64_t gen;
     uint64_t max_flights;
-    /* derived once; pure functions of the tables, same f32 ops as the reference */
+    /* fission_bank source mode (new capability, no reference counterpart) */
+    int bank_mode;
+    float inv_k;               /* 1 / k of the previous generation: keeps the bank near H sites */
+    const uint64_t *src_bank;  /* dense bank feeding this generation, NULL => uniform_fuel source */
+    uint64_t src_count;
+    uint64_t *slots;           /* [hist_count][bank_cap] sites of this generation, by history */
+    uint8_t *counts;           /* [hist_count] */
+    uint32_t bank_cap;
+    uint64_t slot_base;        /* history index of slot row 0 */
 } run_shared;
 
 typedef struct {
@@ -50,6 +58,13 @@ typedef struct {
     uint32_t *trace;       /* base of the generation's trace array or NULL */
     uint64_t trace_base;   /* history index of trace row 0 */
 } worker;
+
+/* optional diagnostics for kernel design (single-threaded runs only): crossings-per-flight histogram by group */
+static int g_diag = 0;
+static uint64_t g_diag_hist[8][130];
+static uint64_t g_diag_coll[8];
+void oracle_diag_enable(int on) { g_diag = on; memset(g_diag_hist, 0, sizeof g_diag_hist); memset(g_diag_coll, 0, sizeof g_diag_coll); }
+void oracle_diag_read(uint64_t *hist /*[8][130]*/, uint64_t *coll /*[8]*/) { memcpy(hist, g_diag_hist, sizeof g_diag_hist); memcpy(coll, g_diag_coll, sizeof g_diag_coll); }
 
 /* ---- reference helpers, one function per reference function ------------- */
 
@@ -198,13 +213,27 @@ static inline __attribute__((always_inline)) void run_history(worker *w, uint64_
     uint64_t hid = sh->gen * p->histories + y;
     oracle_pcg32_advance(&rng, hid * o->stride);
 
-    /* draw order: cell, position, mu, chi */
     uint32_t u = oracle_pcg32_next(&rng);
-    uint64_t cell = p->fuel_indices[((uint64_t)u * (uint64_t)p->NF) >> 32];
-    float xi_pos = oracle_uniform(&rng);
-    float mu = oracle_direction(oracle_uniform(&rng));
-    uint32_t g = oracle_energy(p, oracle_uniform(&rng), cell);
-    float x = p->left[cell] + (xi_pos * p->dx_fuel);
+    uint64_t cell;
+    float x, mu;
+    uint32_t g;
+    if (sh->src_bank) {
+        /* fission_bank source: site index, mu, chi (no position draw) */
+        uint64_t site = sh->src_bank[((uint64_t)u * sh->src_count) >> 32];
+        uint32_t xb = (uint32_t)site;
+        cell = site >> 32;
+        memcpy(&x, &xb, 4);
+        mu = oracle_direction(oracle_uniform(&rng));
+        g = oracle_energy(p, oracle_uniform(&rng), cell);
+    } else {
+        /* draw order: cell, position, mu, chi */
+        cell = p->fuel_indices[((uint64_t)u * (uint64_t)p->NF) >> 32];
+        float xi_pos = oracle_uniform(&rng);
+        mu = oracle_direction(oracle_uniform(&rng));
+        g = oracle_energy(p, oracle_uniform(&rng), cell);
+        x = p->left[cell] + (xi_pos * p->dx_fuel);
+    }
+    uint32_t n_bank = 0;
 
     uint32_t n_coll = 0, n_cross = 0, n_flight = 0, n_refl = 0, fate = 0;
     const uint64_t max_flights = sh->max_flights;
@@ -218,6 +247,7 @@ static inline __attribute__((always_inline)) void run_history(worker *w, uint64_
         uint32_t xs = mat + M * g;
         float ds = mu * -oracle_logf(oracle_uniform(&rng)) * p->inv_sigtr[xs];
         ++n_flight;
+        uint32_t diag_k = 0;
         for (;;) {
             float end_x = x + ds;
             float mesh_end = (mu >= 0.0f) ? p->right[cell] : p->left[cell];
@@ -242,17 +272,34 @@ static inline __attribute__((always_inline)) void run_history(worker *w, uint64_
                 float dsx[2];
                 oracle_cross_mesh(cell, mu, x, mesh_end, ds, dsx, &cell);
                 ds = dsx[0]; x = dsx[1];
-                ++n_cross;
-                if (prev_mat != p->matid[cell]) break; /* alive, new flight */
+                ++n_cross; ++diag_k;
+                if (prev_mat != p->matid[cell]) { if (g_diag) g_diag_hist[g & 7][diag_k > 129 ? 129 : diag_k]++; break; } /* alive, new flight */
             } else {
                 /* mc_code.rs:183-209 */
                 score(w, g, cell, fabsf((x - end_x) / mu));
                 ++n_coll;
+                if (g_diag) { g_diag_hist[g & 7][diag_k > 129 ? 129 : diag_k]++; g_diag_coll[g & 7]++; diag_k = 0; }
                 oracle_scat_mat_calc(G, p->matid[cell], g, 1.0f / p->sigs[xs], p->scat, cdf);
                 float xi_int = oracle_uniform(&rng);
                 float absorption = p->siga[xs] / p->sigt[xs];
                 float mu_new = 2.0f * oracle_uniform(&rng) - 1.0f;
                 uint32_t g_new = sample_group(cdf, G, o->scatter_mode, &rng);
+                if (sh->bank_mode) {
+                    /* collision estimator of the fission source: nu*Sigma_f(mat, g) per unit track length over the
+                     * collision density 1/inv_sigtr[xs] the flight was sampled with, normalised by the last k */
+                    float nusigf = p->nut[p->matid[cell] + M * g] * p->sigf[p->matid[cell] + M * g];
+                    if (nusigf > 0.0f) {
+                        float wgt = nusigf * p->inv_sigtr[xs] * sh->inv_k;
+                        uint32_t n = (uint32_t)(int32_t)(wgt + oracle_uniform(&rng));
+                        uint32_t xb;
+                        memcpy(&xb, &end_x, 4);
+                        for (uint32_t j = 0; j < n; ++j) {
+                            if (n_bank < sh->bank_cap)
+                                sh->slots[(y - sh->slot_base) * sh->bank_cap + n_bank] = ((uint64_t)cell << 32) | xb;
+                            ++n_bank;
+                        }
+                    }
+                }
                 if (xi_int < absorption) {
                     alive = 0; fate = ORACLE_FATE_ABSORBED;
                     break;
@@ -275,6 +322,11 @@ static inline __attribute__((always_inline)) void run_history(worker *w, uint64_
     w->counters[ORACLE_CT_REFLECTIONS] += n_refl;
     w->counters[ORACLE_CT_LEAKS] += (fate == ORACLE_FATE_LEAKED);
     w->counters[ORACLE_CT_TRUNCATED] += (fate == ORACLE_FATE_TRUNCATED);
+    if (sh->bank_mode) {
+        uint32_t kept = n_bank < sh->bank_cap ? n_bank : sh->bank_cap;
+        sh->counts[y - sh->slot_base] = (uint8_t)kept;
+        w->counters[ORACLE_CT_BANKED] += kept;
+    }
     if (w->trace) {
         uint32_t *t = w->trace + (y - w->trace_base) * ORACLE_TR_WORDS;
         uint32_t xb;
@@ -343,7 +395,7 @@ int oracle_monte_carlo(const oracle_problem *p, const oracle_options *o, oracle_
 {
     if (!p || !o || !r) return -1;
     if (p->G < 2 /* mc_code.rs:356 indexes nut[M*1] */ || p->G > 256 || p->M == 0 || p->N == 0 || p->NF == 0 || p->numass == 0) return -2;
-    if (o->source_mode != ORACLE_SOURCE_UNIFORM_FUEL || o->tracking_mode != ORACLE_TRACK_SURFACE) return -3;
+    if (o->source_mode < 0 || o->source_mode > ORACLE_SOURCE_FISSION_BANK || o->tracking_mode != ORACLE_TRACK_SURFACE) return -3;
     const uint32_t G = p->G, M = p->M;
     const uint64_t N = p->N, GN = (uint64_t)G * N;
 
@@ -378,11 +430,25 @@ int oracle_monte_carlo(const oracle_problem *p, const oracle_options *o, oracle_
     memset(r->counters, 0, sizeof(r->counters));
     r->seconds_transport = 0.0;
 
+    sh.bank_mode = (o->source_mode == ORACLE_SOURCE_FISSION_BANK);
+    sh.bank_cap = o->bank_cap > 0 ? (uint32_t)o->bank_cap : 8u;
+    if (sh.bank_cap > 255) sh.bank_cap = 255;
+    sh.src_bank = NULL; sh.src_count = 0; sh.slots = NULL; sh.counts = NULL; sh.slot_base = h0;
+    uint64_t *bank_cur = NULL, *bank_next = NULL, *cell_hist = NULL;
+    if (sh.bank_mode) {
+        sh.slots = (uint64_t *)malloc(hc * sh.bank_cap * sizeof(uint64_t));
+        sh.counts = (uint8_t *)calloc(hc, 1);
+        bank_next = (uint64_t *)malloc(hc * sh.bank_cap * sizeof(uint64_t));
+        bank_cur = (uint64_t *)malloc(hc * sh.bank_cap * sizeof(uint64_t));
+        cell_hist = (uint64_t *)calloc(N, sizeof(uint64_t));
+    }
+
     float k_new = p->k0;
     for (uint64_t x = 0; x < p->generations; ++x) {
         float k = k_new;
         k_new = 0.0f;
         sh.gen = x;
+        sh.inv_k = 1.0f / k;
 
         /* static contiguous ranges, mc_code.rs:303-307 */
         uint64_t per = hc / (uint64_t)T;
@@ -410,6 +476,29 @@ int oracle_monte_carlo(const oracle_problem *p, const oracle_options *o, oracle_
                 for (uint64_t i = 0; i < GN; ++i) tally[i] += w->tally_f32[i];
         }
         r->seconds_transport += now_s() - t0;
+        if (sh.bank_mode) {
+            /* compaction in canonical (history, site) order, then the bank feeds the next generation */
+            uint64_t n_sites = 0;
+            memset(cell_hist, 0, N * sizeof(uint64_t));
+            for (uint64_t y = 0; y < hc; ++y)
+                for (uint32_t j = 0; j < sh.counts[y]; ++j) {
+                    uint64_t site = sh.slots[y * sh.bank_cap + j];
+                    bank_next[n_sites++] = site;
+                    cell_hist[site >> 32]++;
+                }
+            if (r->bank_sizes) r->bank_sizes[x] = n_sites;
+            if (r->entropy) {
+                double e = 0.0;
+                for (uint64_t i = 0; i < N; ++i)
+                    if (cell_hist[i]) { double pr = (double)cell_hist[i] / (double)n_sites; e -= pr * log2(pr); }
+                r->entropy[x] = e;
+            }
+            if (r->bank_sites && r->bank_gen == x)
+                memcpy(r->bank_sites, bank_next, (n_sites < r->bank_sites_cap ? n_sites : r->bank_sites_cap) * sizeof(uint64_t));
+            uint64_t *tmp = bank_cur; bank_cur = bank_next; bank_next = tmp;
+            sh.src_bank = n_sites ? bank_cur : NULL; /* an empty bank falls back to the uniform source */
+            sh.src_count = n_sites;
+        }
         if (o->tally_mode == ORACLE_TALLY_FIXED64) {
             for (uint64_t i = 0; i < GN; ++i) tally[i] = (float)((double)tally_fixed[i] * (1.0 / 268435456.0));
             if (r->tally_fixed) memcpy(r->tally_fixed + x * GN, tally_fixed, GN * sizeof(uint64_t));
@@ -444,5 +533,6 @@ int oracle_monte_carlo(const oracle_problem *p, const oracle_options *o, oracle_
         free(ws[t].tally_f32);
     }
     free(ws); free(th); free(tally_fixed); free(tally);
+    free(sh.slots); free(sh.counts); free(bank_cur); free(bank_next); free(cell_hist);
     return 0;
 }

@@ -22,6 +22,7 @@ struct NrapsOptions {
     seed: u64, stream: u64, stride: u64,
     device: i32, scatter_mode: i32, stale_xs: i32, source_mode: i32, tracking_mode: i32,
     kernel_variant: i32, threads_per_block: i32, blocks_per_sm: i32, chunk: i32, quiet: i32,
+    bank_cap: i32, reserved0: i32,
     max_flights: u64,
 }
 
@@ -29,6 +30,7 @@ struct NrapsOptions {
 struct NrapsResults {
     flux: *mut f32, assembly_average: *mut f32, fission_source: *mut f32, k: *mut f32, k_fund: *mut f32,
     tally_fixed: *mut u64, counters: [u64; 8], seconds_device: f64,
+    bank_sizes: *mut u64, entropy: *mut f64,
 }
 
 extern "C" {
@@ -72,7 +74,7 @@ pub fn monte_carlo(
     let mut r = NrapsResults {
         flux: flux.as_mut_ptr(), assembly_average: avg.as_mut_ptr(), fission_source: fission.as_mut_ptr(),
         k: k.as_mut_ptr(), k_fund: k_fund.as_mut_ptr(), tally_fixed: std::ptr::null_mut(), counters: [0; 8],
-        seconds_device: 0.0,
+        seconds_device: 0.0, bank_sizes: std::ptr::null_mut(), entropy: std::ptr::null_mut(),
     };
     let rc = unsafe { nraps_mc_run(&p, &o, &mut r) };
     if rc != 0 {

@@ -253,3 +253,50 @@ def test_error_codes():
     with pytest.raises(_lib.NrapsError) as e:
         nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1, device=99)
     assert e.value.code == 6
+
+
+# ---------------------------------------------------------------- fission_bank source mode (new capability)
+@pytest.mark.parametrize("case", ["b", "c"])
+def test_fission_bank_mode_bit_exact(case):
+    """Power iteration: bank sizes, bank contents (canonical order), entropy and every result equal the oracle's."""
+    v, xs, dx, mesh, fuel = load_case(case)
+    gens, H = 5, 60_000
+    got = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1, want_tally=True,
+                         source_mode="fission_bank")
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=gens, histories=H, skip=1, threads=8, want_tally=True,
+                           source_mode="fission_bank")
+    _assert_identical(got, want)
+    assert np.array_equal(got.bank_sizes, want.bank_sizes) and got.counters["banked"] == want.counters["banked"]
+    assert np.allclose(got.entropy, want.entropy, rtol=0, atol=1e-12)
+    assert 0.9 * H < got.bank_sizes[-1] < 1.1 * H and got.bank_sizes[0] > 1.5 * H  # first bank is k0-normalised
+
+
+def test_fission_bank_contents_and_sharding():
+    v, xs, dx, mesh, fuel = load_case("c")
+    H = 40_000
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=2, histories=H, skip=0, threads=8, source_mode="fission_bank", bank_gen=1)
+    with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=H, skip=0, source_mode="fission_bank") as ctx:
+        for gen in range(2):
+            ctx.transport(gen)
+            ctx.finalize_generation(gen)
+            ctx.bank_compact(gen)
+            if gen == 1:
+                bank = ctx.read_bank()
+            ctx.bank_set_source(gen)
+        res = ctx.fetch()
+    assert np.array_equal(bank, want.bank_sites)
+    assert np.array_equal(res.bank_sizes, want.bank_sizes)
+    cells = (bank >> np.uint64(32)).astype(np.int64)
+    assert np.isin(mesh.matid[cells], [0, 1]).all()  # sites only where nu*Sigma_f > 0
+
+
+def test_fission_bank_shifts_k_like_the_survey_probe():
+    """true source iteration raises k_C by ~2.4 % over the reference's flat fuel source."""
+    v, xs, dx, mesh, fuel = load_case("c")
+    flat = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=14, histories=200_000, skip=1)
+    bank = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=14, histories=200_000, skip=1, source_mode="fission_bank")
+    ratio = float(bank.k[6:].mean() / flat.k[6:].mean())
+    assert 1.018 < ratio < 1.030, ratio
+    assert bank.entropy[0] > bank.entropy[-1] > 7.5  # source settles from flat towards the fundamental mode

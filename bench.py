@@ -45,6 +45,11 @@ def workload(name: str):
         args = load_case("c", mpfr=80, mpwr=40)
         desc = "config4: TestCaseC XS, fine mesh MPFR=80/MPWR=40 (G=4, N=4080 cells), 1e8 histories/generation total (strong scaling)"
         per_gpu = 100_000_000
+    elif name == "config5":
+        args = load_case("c")
+        desc = ("config5: TestCaseC XS+geometry (G=4, N=408), 1.25e8 histories/generation/GPU, fission_bank source "
+                "(power iteration), NCCL all-gather of the bank each generation (weak scaling)")
+        per_gpu = 125_000_000
     else:
         raise SystemExit(f"unknown workload {name}")
     return args, desc, per_gpu
@@ -170,18 +175,22 @@ def run_ours(a):
 
     args, desc, per_gpu = workload(a.workload)
     v, xs, dx, mesh, fuel = args
-    H = a.histories if a.histories else (per_gpu * world if a.workload == "config3" else per_gpu)
-    scaling = "weak" if a.workload == "config3" else "strong"
+    H = a.histories if a.histories else (per_gpu if a.workload == "config4" else per_gpu * world)
+    scaling = "strong" if a.workload == "config4" else "weak"
+    source_mode = "fission_bank" if a.workload == "config5" else "uniform_fuel"
     K, W = a.steps, a.warmup
     gens_total = W + K
 
-    opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk)
+    opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode)
     ctx = nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens_total, histories=H, skip=1, **opts)
     tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{local}")
     ctx.use_tally_tensor(tally)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
     begin, count = shard_range(H, rank, world)
+    from nraps_b200.dist import make_bank_callback
+
+    bank = make_bank_callback(ctx, world, local, stream) if source_mode == "fission_bank" else None
 
     def step(gen, ev=None):
         flush.zero_()
@@ -193,6 +202,8 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(tally)
         ctx.finalize_generation(gen, stream)
+        if bank is not None:
+            bank(gen)
 
     def fence():
         if world > 1:
@@ -240,6 +251,8 @@ def run_ours(a):
         d2h = 4 * (G * N + N + K) + 64                           # flux, fission source, k, counters
         peak, peak_src = peaks()
         b_hist = RECORD_BYTES + 2 * RECORD_BYTES * coll_per_hist
+        if bank is not None:
+            b_hist += 12 + 12 * res.counters["banked"] / max(1, res.counters["histories"])  # source read + bank write, SURVEY 8d
         hist_per_launch = count
         achieved = b_hist * hist_per_launch / (ms_kernel * 1e-3) / 1e9
         line = {
@@ -247,12 +260,12 @@ def run_ours(a):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "histories_per_generation": H, "histories_per_gpu": count, "generations_timed": K,
-                       "source_mode": "uniform_fuel", "parallelism": f"history-sharded x{world}, int64 tally all-reduce per generation",
+                       "source_mode": source_mode, "parallelism": f"history-sharded x{world}, int64 tally all-reduce per generation",
                        "launch": info, "l2": "256 MiB device memset between steps inside the timed region (kernel inputs are ~12 KB of tables)"},
             "clocks": clocks,
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "note": "one monte_carlo() call: context create + table upload + K generations + result download; bytes are per run / K"},
-            "gpu_launches": 2 * K,
+            "gpu_launches": (2 + (5 if bank is not None else 0)) * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "kernel": "transport_kernel<4,false>", "kernel_ms": ms_kernel,
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
@@ -281,7 +294,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config3", choices=["config3", "config4"])
+    ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"])
     ap.add_argument("--histories", type=int, default=0, help="override histories per generation (total)")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)

@@ -67,6 +67,39 @@ def run_generations(engine: GenerationEngine, tally, rank: int, world: int, *, a
             bank(gen)
 
 
+def make_bank_callback(ctx, world: int, device: int, stream):
+    """bank(gen) for run_generations on GPUs: compact locally, all-gather over NCCL, install as next source."""
+    import torch
+    import torch.distributed as dist
+
+    from .api import _DevArray
+
+    dev = f"cuda:{device}"
+
+    def counts_fn(n):
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        out = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return [int(v) for v in out.tolist()]
+
+    def padded_fn(padded, max_n):
+        out = torch.empty(world * max_n, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, padded)
+        return out.view(world, max_n)
+
+    def bank(gen):
+        ctx.bank_compact(gen, stream)
+        if world == 1:
+            ctx.bank_set_source(gen, None, stream)
+            return
+        ptr, n = ctx.bank_local(stream)
+        local = torch.as_tensor(_DevArray(ptr, n), device=dev) if n else torch.zeros(0, dtype=torch.int64, device=dev)
+        full, _ = gather_bank(local, world, counts_fn, padded_fn)
+        ctx.bank_set_source(gen, full.contiguous() if full.numel() else None, stream)
+
+    return bank
+
+
 def monte_carlo_distributed(variables, xsdata, delta_x, meshid, fuel_indices, k_new: float = 1.0, *, generations=None,
                             histories=None, skip=None, **options):
     """`monte_carlo` across the ranks of the default torch.distributed group (NCCL, one GPU per rank)."""
@@ -84,32 +117,7 @@ def monte_carlo_distributed(variables, xsdata, delta_x, meshid, fuel_indices, k_
             tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{device}")
             ctx.use_tally_tensor(tally)
             stream = torch.cuda.current_stream().cuda_stream
-            bank = None
-            if options.get("source_mode") == "fission_bank":
-                from .api import _DevArray
-
-                def counts_fn(n):
-                    t = torch.tensor([n], dtype=torch.int64, device=f"cuda:{device}")
-                    out = torch.empty(world, dtype=torch.int64, device=f"cuda:{device}")
-                    dist.all_gather_into_tensor(out, t)
-                    return [int(v) for v in out.tolist()]
-
-                def padded_fn(padded, max_n):
-                    out = torch.empty(world * max_n, dtype=torch.int64, device=f"cuda:{device}")
-                    dist.all_gather_into_tensor(out, padded)
-                    return out.view(world, max_n)
-
-                def bank(gen):
-                    ctx.bank_compact(gen, stream)
-                    if world == 1:
-                        ctx.bank_set_source(gen, None, stream)
-                        return
-                    ptr, n = ctx.bank_local(stream)
-                    local = (torch.as_tensor(_DevArray(ptr, n), device=f"cuda:{device}") if n
-                             else torch.zeros(0, dtype=torch.int64, device=f"cuda:{device}"))
-                    full, _ = gather_bank(local, world, counts_fn, padded_fn)
-                    ctx.bank_set_source(gen, full.contiguous() if full.numel() else None, stream)
-
+            bank = make_bank_callback(ctx, world, device, stream) if options.get("source_mode") == "fission_bank" else None
             run_generations(ctx, tally, rank, world, all_reduce=lambda t: dist.all_reduce(t), stream=stream, bank=bank)
             return ctx.fetch(stream)
         finally:

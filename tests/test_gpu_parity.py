@@ -4,6 +4,8 @@ states, fixed-point tally bins) and everything derived from them with the
 reference's binary32 arithmetic (k, flux, fission source, CSV bytes) must be
 BIT-EXACT.  Statistical agreement between independent streams is stated at
 3 sigma combined / per-bin chi-square."""
+import os
+
 import numpy as np
 import pytest
 
@@ -300,3 +302,40 @@ def test_fission_bank_shifts_k_like_the_survey_probe():
     ratio = float(bank.k[6:].mean() / flat.k[6:].mean())
     assert 1.018 < ratio < 1.030, ratio
     assert bank.entropy[0] > bank.entropy[-1] > 7.5  # source settles from flat towards the fundamental mode
+
+
+def _dist_worker(rank, world, port, out_dir, mode):
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    v, xs, dx, mesh, fuel = load_case("c")
+    res = nb.monte_carlo_distributed(v, xs, dx, mesh, fuel, 1.0, generations=4, histories=50_001, skip=1, device=rank,
+                                     source_mode=mode)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), k=res.k, flux=res.flux, bank=res.bank_sizes, ent=res.entropy,
+             coll=res.counters["collisions"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["uniform_fuel", "fission_bank"])
+def test_two_gpus_equal_one_gpu_bit_for_bit(tmp_path, mode):
+    """History sharding + NCCL all-reduce (+ bank all-gather): identical to the single-GPU run on every rank."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_dist_worker, args=(2, 29650 + (os.getpid() % 200), str(tmp_path), mode), nprocs=2, join=True)
+    v, xs, dx, mesh, fuel = load_case("c")
+    one = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=4, histories=50_001, skip=1, source_mode=mode)
+    for r in range(2):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(bits(z["k"]), bits(one.k)) and np.array_equal(bits(z["flux"]), bits(one.flux))
+        assert np.array_equal(z["bank"], one.bank_sizes) and np.allclose(z["ent"], one.entropy, atol=1e-12, rtol=0)
+        assert int(z["coll"]) == one.counters["collisions"]

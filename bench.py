@@ -181,7 +181,8 @@ def run_ours(a):
     K, W = a.steps, a.warmup
     gens_total = W + K
 
-    opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode)
+    opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode,
+                tracking_mode=a.tracking)
     ctx = nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens_total, histories=H, skip=1, **opts)
     tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{local}")
     ctx.use_tally_tensor(tally)
@@ -260,14 +261,14 @@ def run_ours(a):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "histories_per_generation": H, "histories_per_gpu": count, "generations_timed": K,
-                       "source_mode": source_mode, "parallelism": f"history-sharded x{world}, int64 tally all-reduce per generation",
+                       "source_mode": source_mode, "tracking_mode": a.tracking, "parallelism": f"history-sharded x{world}, int64 tally all-reduce per generation",
                        "launch": info, "l2": "256 MiB device memset between steps inside the timed region (kernel inputs are ~12 KB of tables)"},
             "clocks": clocks,
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "note": "one monte_carlo() call: context create + table upload + K generations + result download; bytes are per run / K"},
             "gpu_launches": (2 + (5 if bank is not None else 0)) * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "transport_kernel<4,false>", "kernel_ms": ms_kernel,
+                         "peak_source": peak_src, "kernel": ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if bank is not None else "false"), "kernel_ms": ms_kernel,
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
                          "note": "algorithmic bytes = 24 + 48*collisions/history (SURVEY 8d bank model); the fused kernel keeps "
                                  "particles in registers so real DRAM traffic is far lower: the kernel is issue/shared-memory bound"},
@@ -299,6 +300,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--tracking", default="surface", choices=["surface", "woodcock"],
+                    help="surface = the reference's cell-by-cell tracking (headline, bit-comparable); woodcock = delta tracking")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

@@ -99,7 +99,10 @@ struct nraps_mc_ctx {
     float *d_edges = nullptr, *d_xs = nullptr, *d_dx = nullptr, *d_nut = nullptr, *d_sigf = nullptr;
     uint32_t *d_runb = nullptr;
     uint8_t *d_matid = nullptr;
-    uint16_t *d_fuel = nullptr;
+    uint16_t *d_fuel = nullptr, *d_bucket = nullptr;
+    uint32_t NB = 0;
+    float inv_h = 0.0f;
+    bool woodcock = false;
     ulonglong2 *d_jump = nullptr;
     unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
@@ -136,7 +139,7 @@ int validate(const nraps_problem *p, const nraps_options *o)
         return NRAPS_ERR_SHAPE;
     if ((uint64_t)p->M * p->G * p->G * p->G > 8192) return NRAPS_ERR_TOO_LARGE;
     if (o->scatter_mode < 0 || o->scatter_mode > NRAPS_SCATTER_RUST_182) return NRAPS_ERR_OPTION;
-    if (o->source_mode < 0 || o->source_mode > NRAPS_SOURCE_FISSION_BANK || o->tracking_mode != NRAPS_TRACK_SURFACE ||
+    if (o->source_mode < 0 || o->source_mode > NRAPS_SOURCE_FISSION_BANK || o->tracking_mode < 0 || o->tracking_mode > NRAPS_TRACK_WOODCOCK ||
         o->kernel_variant != NRAPS_KERNEL_FUSED || o->bank_cap < 0 || o->bank_cap > 255)
         return NRAPS_ERR_OPTION;
     for (uint32_t i = 0; i < p->N; ++i) {
@@ -158,7 +161,7 @@ void free_ctx(nraps_mc_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_edges); cudaFree(c->d_xs); cudaFree(c->d_dx); cudaFree(c->d_nut); cudaFree(c->d_sigf);
-    cudaFree(c->d_runb); cudaFree(c->d_matid); cudaFree(c->d_fuel); cudaFree(c->d_jump);
+    cudaFree(c->d_runb); cudaFree(c->d_matid); cudaFree(c->d_fuel); cudaFree(c->d_jump); cudaFree(c->d_bucket);
     cudaFree(c->d_tally_own); cudaFree(c->d_work); cudaFree(c->d_counters_total);
     cudaFree(c->d_terms); cudaFree(c->d_res_flux); cudaFree(c->d_res_fission); cudaFree(c->d_k_hist); cudaFree(c->d_k_cur);
     cudaFree(c->d_trace);
@@ -203,7 +206,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
 
     TransportParams P{};
     P.edges = c->d_edges; P.runb = c->d_runb; P.matid = c->d_matid; P.fuel = c->d_fuel; P.xs = c->d_xs; P.jump = c->d_jump;
-    P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF;
+    P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF; P.NB = c->NB; P.bucket = c->d_bucket; P.inv_h = c->inv_h;
     P.boundl = c->boundl; P.boundr = c->boundr; P.dx_fuel = c->dx_fuel;
     // history (gen, y) owns the stream position (gen*H + y)*stride; the kernel adds the y part
     uint64_t jm, jp;
@@ -217,7 +220,8 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
     P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
-    CU(launch_transport(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
+    if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
+    else CU(launch_transport(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
     return NRAPS_OK;
 }
 
@@ -251,7 +255,15 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     if (rc != NRAPS_OK) return rc;
 
     const uint32_t M = p->M, G = p->G, N = p->N, NF = p->NF, MG = M * G;
-    const SmemLayout L = make_layout(M, G, N, NF);
+    // Woodcock: position buckets no wider than the narrowest cell, so a bucket overlaps at most two cells
+    const bool woodcock = (o->tracking_mode == NRAPS_TRACK_WOODCOCK);
+    uint32_t NB = 0;
+    if (woodcock) {
+        float min_dx = p->right[0] - p->left[0];
+        for (uint32_t i = 0; i < N; ++i) min_dx = std::min(min_dx, p->right[i] - p->left[i]);
+        NB = (uint32_t)std::min(16384.0, std::max(1.0, std::ceil((double)p->right[N - 1] / (double)min_dx)));
+    }
+    const SmemLayout L = make_layout(M, G, N, NF, NB);
     if (L.total > kMaxSmem) return NRAPS_ERR_TOO_LARGE;
 
     int ndev = 0;
@@ -300,12 +312,35 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     }
     for (uint32_t j = 0; j < NF; ++j) fuel[j] = (uint16_t)p->fuel_indices[j];
 
-    std::vector<float> xs(4 * MG + MG * G * G);
-    float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *nusigf = chi_cdf + MG, *scat_cdf = nusigf + MG;
+    std::vector<float> xs(xs_floats(M, G));
+    float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *nusigf = chi_cdf + MG, *sigtr = nusigf + MG,
+          *scat_cdf = sigtr + MG, *inv_maj = scat_cdf + MG * G * G;
     for (uint32_t i = 0; i < MG; ++i) {
         inv_sigtr[i] = p->inv_sigtr[i];
         p_abs[i] = p->siga[i] / p->sigt[i];
         nusigf[i] = p->nut[i] * p->sigf[i];
+        const float prod = p->mu[i] * p->sigs[i];
+        sigtr[i] = p->sigt[i] - prod; // the expression inside inv_sigtr, src/process_input.rs:152-156
+    }
+    {   // majorant of every (stale group, current group) pair over the materials present in the mesh
+        std::vector<char> present(M, 0);
+        for (uint32_t i = 0; i < N; ++i) present[p->matid[i]] = 1;
+        for (uint32_t ga = 0; ga < G; ++ga)
+            for (uint32_t gb = 0; gb < G; ++gb) {
+                float mx = 0.0f;
+                for (uint32_t m = 0; m < M; ++m) {
+                    if (!present[m]) continue;
+                    mx = std::max(mx, std::max(sigtr[m + M * ga], sigtr[m + M * gb]));
+                }
+                inv_maj[ga * G + gb] = 1.0f / mx;
+            }
+    }
+    std::vector<uint16_t> bucket(NB);
+    for (uint32_t b = 0; b < NB; ++b) {
+        const double xb = (double)b * (double)p->right[N - 1] / (double)NB;
+        uint32_t cidx = 0;
+        while (cidx + 1 < N && (double)p->right[cidx] <= xb) ++cidx;
+        bucket[b] = (uint16_t)cidx;
     }
     for (uint32_t m = 0; m < M; ++m) {
         float cum = 0.0f;
@@ -336,7 +371,7 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return r == cudaSuccess; };
     ok(upload(&c->d_edges, edges)); ok(upload(&c->d_runb, runb)); ok(upload(&c->d_matid, matid));
-    ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump));
+    ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump)); ok(upload(&c->d_bucket, bucket));
     ok(upload(&c->d_dx, dx)); ok(upload(&c->d_nut, nut)); ok(upload(&c->d_sigf, sigf));
     ok(cudaMalloc((void **)&c->d_tally_own, (GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
     ok(cudaMalloc((void **)&c->d_work, sizeof(unsigned long long)));
@@ -350,7 +385,9 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     ok(cudaMalloc((void **)&c->d_bank_sizes, c->generations * sizeof(unsigned long long)));
     ok(cudaMalloc((void **)&c->d_entropy, c->generations * sizeof(double)));
     ok(cudaMalloc((void **)&c->d_hist, N * sizeof(uint32_t)));
-    ok(prepare_transport(L.total));
+    ok(woodcock ? prepare_woodcock(L.total) : prepare_transport(L.total));
+    c->NB = NB; c->woodcock = woodcock;
+    c->inv_h = NB ? (float)((double)NB / (double)p->right[N - 1]) : 0.0f;
     if (e != cudaSuccess) {
         free_ctx(c);
         return cuda_fail(e, "nraps_mc_create");

@@ -21,12 +21,16 @@ struct SmemLayout {
     uint32_t xs;                 // f32[...]   inv_sigtr[MG] | p_abs[MG] | chi_cdf[MG] | nusigf[MG] | scat_cdf[M*G*G*G]
     uint32_t fuel;               // u16[NF]    fuel cell indices
     uint32_t matid;              // u8[N]
+    uint32_t bucket;             // u16[NB]    Woodcock: first-guess cell of each position bucket
     uint32_t total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t NF)
+// floats in the XS block: inv_sigtr | p_abs | chi_cdf | nusigf | sigtr [MG each] | scat_cdf [M*G^3] | inv_maj [G*G]
+__host__ __device__ inline uint32_t xs_floats(uint32_t M, uint32_t G) { return 5 * M * G + M * G * G * G + G * G; }
+
+__host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t NF, uint32_t NB)
 {
     SmemLayout L;
     uint32_t off = 0;
@@ -36,9 +40,10 @@ __host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32
     L.edges = off;    off += (N + 1) * 4;
     L.runb = off;     off += N * 4;
     off = align_up(off, 16); // float4 rows of the CDF tables
-    L.xs = off;       off += (4 * M * G + M * G * G * G) * 4;
+    L.xs = off;       off += xs_floats(M, G) * 4;
     L.fuel = off;     off += align_up(NF * 2, 4);
     L.matid = off;    off += align_up(N, 4);
+    L.bucket = off;   off += align_up(NB * 2, 4);
     L.total = align_up(off, 16);
     return L;
 }
@@ -51,8 +56,9 @@ struct TransportParams {
     const uint16_t *fuel;
     const float *xs;
     const ulonglong2 *jump;
-    uint32_t M, G, N, NF;
-    float boundl, boundr, dx_fuel;
+    const uint16_t *bucket;  // [NB] Woodcock position buckets (NB = 0 in surface mode)
+    uint32_t M, G, N, NF, NB;
+    float boundl, boundr, dx_fuel, inv_h;
     uint64_t rng_state; // master stream advanced to history 0 of this generation
     uint64_t rng_inc;
     uint64_t hist_begin, hist_end; // this launch covers y in [hist_begin, hist_end)
@@ -100,6 +106,8 @@ struct FinalizeParams {
 };
 
 cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
+cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
+cudaError_t prepare_woodcock(uint32_t smem_bytes);
 cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s);
 cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
                                 double *entropy_out, unsigned long long *size_out, cudaStream_t s);

@@ -1,0 +1,149 @@
+// Lane-level building blocks shared by the transport kernels (surface tracking
+// in mc_transport.cu, Woodcock delta tracking in mc_woodcock.cu).
+#pragma once
+#include "mc_device.cuh"
+#include "mc_internal.h"
+
+namespace nraps {
+
+static constexpr unsigned kFull = 0xffffffffu;
+
+// shared-space atomics on 32-bit shared addresses (the generic-pointer forms
+// drag a cluster-window address computation into the inner loop)
+static __device__ __forceinline__ uint32_t atoms_add(uint32_t saddr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+    return old;
+}
+static __device__ __forceinline__ void reds_add(uint32_t saddr, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+static __device__ __forceinline__ float lds_f32(uint32_t saddr)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+
+// 64-bit fixed-point bin += score, as two u32 words with an explicit carry;
+// `a` is the shared address of the low word, the high word sits hi_off bytes above
+static __device__ __forceinline__ void score(uint32_t a, uint32_t hi_off, float v)
+{
+    const unsigned long long fx = __float2ull_rz(fmul(v, kTallyScale));
+    const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
+    const uint32_t old = atoms_add(a, l);
+    const bool carry = (uint32_t)(old + l) < l;
+    if (carry | (h != 0u)) reds_add(a + hi_off, h + (carry ? 1u : 0u));
+}
+
+template <int TG> static __device__ __forceinline__ int search_cdf(const float *cdf, int G, float v)
+{
+    if (TG == 4) { // partition_point on 4 entries, probes 2 then 3 or 1 then 0
+        const float4 c = *reinterpret_cast<const float4 *>(cdf);
+        return (c.z < v) ? 3 : ((c.y < v) ? 2 : ((c.x < v) ? 1 : 0));
+    }
+    if (TG == 2) {
+        const float2 c = *reinterpret_cast<const float2 *>(cdf);
+        return ((c.y < v) || (c.x < v)) ? 1 : 0;
+    }
+    return lower_bound_clamped<TG>(cdf, G, v);
+}
+
+template <int TG>
+static __device__ __forceinline__ int sample_group(const float *cdf, int G, int mode, uint64_t &rng, uint64_t inc)
+{
+    const int n = TG ? TG : G;
+    if (mode == NRAPS_SCATTER_SINGLE_XI) return search_cdf<TG>(cdf, G, pcg32_unit(rng, inc));
+    if (mode == NRAPS_SCATTER_RUST_PRE182) { // a fresh draw per probe, pre-1.82 probe order
+        int size = n, left = 0, right = n;
+        while (left < right) {
+            const int mid = left + size / 2;
+            if (cdf[mid] < pcg32_unit(rng, inc)) left = mid + 1;
+            else right = mid;
+            size = right - left;
+        }
+        return left < n - 1 ? left : n - 1;
+    }
+    int size = n, base = 0; // rustc >= 1.82 probe order
+    while (size > 1) {
+        const int half = size / 2, mid = base + half;
+        if (cdf[mid] < pcg32_unit(rng, inc)) base = mid;
+        size -= half;
+    }
+    const int res = base + (cdf[base] < pcg32_unit(rng, inc) ? 1 : 0);
+    return res < n - 1 ? res : n - 1;
+}
+
+// apply the jump maps selected by the set bits of `steps` (each map = stride * 2^b draws)
+static __device__ __forceinline__ uint64_t jump_ahead(uint64_t state, uint64_t steps, const ulonglong2 *jump)
+{
+    while (steps) {
+        const int b = __ffsll((long long)steps) - 1;
+        steps &= steps - 1;
+        const ulonglong2 J = jump[b];
+        state = J.x * state + J.y;
+    }
+    return state;
+}
+
+
+// Block prologue shared by both kernels: carve the shared-memory image and fill it from global memory.
+struct SmemView {
+    uint32_t *lo, *hi;
+    float *edges;
+    uint32_t *runb;
+    ulonglong2 *jump;
+    float *xs;
+    uint16_t *fuel;
+    uint8_t *matid;
+    uint16_t *bucket;
+};
+
+static __device__ __forceinline__ SmemView load_block_tables(unsigned char *smem_raw, const TransportParams &P, const SmemLayout &L)
+{
+    SmemView S;
+    S.lo = reinterpret_cast<uint32_t *>(smem_raw + L.tally_lo);
+    S.hi = reinterpret_cast<uint32_t *>(smem_raw + L.tally_hi);
+    S.edges = reinterpret_cast<float *>(smem_raw + L.edges);
+    S.runb = reinterpret_cast<uint32_t *>(smem_raw + L.runb);
+    S.jump = reinterpret_cast<ulonglong2 *>(smem_raw + L.jump);
+    S.xs = reinterpret_cast<float *>(smem_raw + L.xs);
+    S.fuel = reinterpret_cast<uint16_t *>(smem_raw + L.fuel);
+    S.matid = smem_raw + L.matid;
+    S.bucket = reinterpret_cast<uint16_t *>(smem_raw + L.bucket);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int G = (int)P.G, M = (int)P.M, N = (int)P.N, GN = G * N, MG = M * G;
+    for (int i = tid; i < GN; i += nthr) { S.lo[i] = 0u; S.hi[i] = 0u; }
+    for (int i = tid; i <= N; i += nthr) S.edges[i] = P.edges[i];
+    for (int i = tid; i < N; i += nthr) { S.runb[i] = P.runb[i]; S.matid[i] = P.matid[i]; }
+    for (int i = tid; i < (int)P.NF; i += nthr) S.fuel[i] = P.fuel[i];
+    for (int i = tid; i < (int)xs_floats(P.M, P.G); i += nthr) S.xs[i] = P.xs[i];
+    for (int i = tid; i < 64; i += nthr) S.jump[i] = P.jump[i];
+    for (int i = tid; i < (int)P.NB; i += nthr) S.bucket[i] = P.bucket[i];
+    __syncthreads();
+    return S;
+}
+
+// Block epilogue: shared bins -> global 64-bit bins, lane counters -> global counters.
+static __device__ __forceinline__ void flush_block(const SmemView &S, const TransportParams &P, const uint32_t (&vals)[8])
+{
+    const int tid = threadIdx.x, nthr = blockDim.x, GN = (int)(P.G * P.N);
+    __syncthreads();
+    for (int i = tid; i < GN; i += nthr) {
+        const unsigned long long v = ((unsigned long long)S.hi[i] << 32) + S.lo[i];
+        if (v) atomicAdd(&P.tally[i], v);
+    }
+    unsigned long long *ct = P.tally + GN;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        unsigned long long v = vals[c];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if ((tid & 31) == 0 && v) atomicAdd(&ct[c], v);
+    }
+}
+
+} // namespace nraps

@@ -22,95 +22,11 @@
 // atomics compile to CAS loops on sm_100a).  Integer sums are associative, so
 // the result is independent of lane / block / GPU scheduling and bit-identical
 // to the oracle's.
-#include "mc_device.cuh"
-#include "mc_internal.h"
+#include "mc_lane.cuh"
 
 namespace nraps {
 
 namespace {
-
-constexpr unsigned kFull = 0xffffffffu;
-
-// shared-space atomics on 32-bit shared addresses (the generic-pointer forms
-// drag a cluster-window address computation into the inner loop)
-__device__ __forceinline__ uint32_t atoms_add(uint32_t saddr, uint32_t v)
-{
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ void reds_add(uint32_t saddr, uint32_t v)
-{
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ float lds_f32(uint32_t saddr)
-{
-    float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
-    return v;
-}
-
-// 64-bit fixed-point bin += score, as two u32 words with an explicit carry;
-// `a` is the shared address of the low word, the high word sits hi_off bytes above
-__device__ __forceinline__ void score(uint32_t a, uint32_t hi_off, float v)
-{
-    const unsigned long long fx = __float2ull_rz(fmul(v, kTallyScale));
-    const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
-    const uint32_t old = atoms_add(a, l);
-    const bool carry = (uint32_t)(old + l) < l;
-    if (carry | (h != 0u)) reds_add(a + hi_off, h + (carry ? 1u : 0u));
-}
-
-template <int TG> __device__ __forceinline__ int search_cdf(const float *cdf, int G, float v)
-{
-    if (TG == 4) { // partition_point on 4 entries, probes 2 then 3 or 1 then 0
-        const float4 c = *reinterpret_cast<const float4 *>(cdf);
-        return (c.z < v) ? 3 : ((c.y < v) ? 2 : ((c.x < v) ? 1 : 0));
-    }
-    if (TG == 2) {
-        const float2 c = *reinterpret_cast<const float2 *>(cdf);
-        return ((c.y < v) || (c.x < v)) ? 1 : 0;
-    }
-    return lower_bound_clamped<TG>(cdf, G, v);
-}
-
-template <int TG>
-__device__ __forceinline__ int sample_group(const float *cdf, int G, int mode, uint64_t &rng, uint64_t inc)
-{
-    const int n = TG ? TG : G;
-    if (mode == NRAPS_SCATTER_SINGLE_XI) return search_cdf<TG>(cdf, G, pcg32_unit(rng, inc));
-    if (mode == NRAPS_SCATTER_RUST_PRE182) { // a fresh draw per probe, pre-1.82 probe order
-        int size = n, left = 0, right = n;
-        while (left < right) {
-            const int mid = left + size / 2;
-            if (cdf[mid] < pcg32_unit(rng, inc)) left = mid + 1;
-            else right = mid;
-            size = right - left;
-        }
-        return left < n - 1 ? left : n - 1;
-    }
-    int size = n, base = 0; // rustc >= 1.82 probe order
-    while (size > 1) {
-        const int half = size / 2, mid = base + half;
-        if (cdf[mid] < pcg32_unit(rng, inc)) base = mid;
-        size -= half;
-    }
-    const int res = base + (cdf[base] < pcg32_unit(rng, inc) ? 1 : 0);
-    return res < n - 1 ? res : n - 1;
-}
-
-// apply the jump maps selected by the set bits of `steps` (each map = stride * 2^b draws)
-__device__ __forceinline__ uint64_t jump_ahead(uint64_t state, uint64_t steps, const ulonglong2 *jump)
-{
-    while (steps) {
-        const int b = __ffsll((long long)steps) - 1;
-        steps &= steps - 1;
-        const ulonglong2 J = jump[b];
-        state = J.x * state + J.y;
-    }
-    return state;
-}
 
 enum { EV_NONE = 0, EV_COLLIDE = 1, EV_MATCHANGE = 2 };
 
@@ -120,28 +36,19 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G;
     const int M = (int)P.M, N = (int)P.N;
-    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF);
+    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB);
 
-    uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw + L.tally_lo);
-    uint32_t *s_hi = reinterpret_cast<uint32_t *>(smem_raw + L.tally_hi);
-    float *s_edges = reinterpret_cast<float *>(smem_raw + L.edges);
-    uint32_t *s_runb = reinterpret_cast<uint32_t *>(smem_raw + L.runb);
-    ulonglong2 *s_jump = reinterpret_cast<ulonglong2 *>(smem_raw + L.jump);
-    float *s_xs = reinterpret_cast<float *>(smem_raw + L.xs);
-    uint16_t *s_fuel = reinterpret_cast<uint16_t *>(smem_raw + L.fuel);
-    uint8_t *s_matid = smem_raw + L.matid;
-
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int GN = G * N, MG = M * G;
-    for (int i = tid; i < GN; i += nthr) { s_lo[i] = 0u; s_hi[i] = 0u; }
-    for (int i = tid; i <= N; i += nthr) s_edges[i] = P.edges[i];
-    for (int i = tid; i < N; i += nthr) { s_runb[i] = P.runb[i]; s_matid[i] = P.matid[i]; }
-    for (int i = tid; i < (int)P.NF; i += nthr) s_fuel[i] = P.fuel[i];
-    for (int i = tid; i < 4 * MG + MG * G * G; i += nthr) s_xs[i] = P.xs[i];
-    for (int i = tid; i < 64; i += nthr) s_jump[i] = P.jump[i];
-    __syncthreads();
+    const SmemView S = load_block_tables(smem_raw, P, L);
+    uint32_t *s_lo = S.lo;
+    const float *s_edges = S.edges, *s_xs = S.xs;
+    const uint32_t *s_runb = S.runb;
+    const ulonglong2 *s_jump = S.jump;
+    const uint16_t *s_fuel = S.fuel;
+    const uint8_t *s_matid = S.matid;
+    const int tid = threadIdx.x;
+    const int MG = M * G;
     const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_chi = s_xs + 2 * MG, *s_nusigf = s_xs + 3 * MG,
-                *s_scat = s_xs + 4 * MG;
+                *s_scat = s_xs + 5 * MG;
     // fission_bank mode: sites are banked with weight nu*Sigma_f * inv_sigtr / k_prev; an empty bank => uniform source
     const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
     const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
@@ -364,21 +271,8 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
         }
     }
 
-    // ---------------- flush: block bins -> global 64-bit bins, lane counters -> global
-    __syncthreads();
-    for (int i = tid; i < GN; i += nthr) {
-        const unsigned long long v = ((unsigned long long)s_hi[i] << 32) + s_lo[i];
-        if (v) atomicAdd(&P.tally[i], v);
-    }
-    unsigned long long *ct = P.tally + GN;
-    uint32_t vals[8] = {c_hist, c_coll, c_cross, c_flight, c_refl, c_leak, c_trunc, c_bank};
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        unsigned long long v = vals[c];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        if (lane == 0 && v) atomicAdd(&ct[c], v);
-    }
+    const uint32_t vals[8] = {c_hist, c_coll, c_cross, c_flight, c_refl, c_leak, c_trunc, c_bank};
+    flush_block(S, P, vals);
 }
 
 template <int TG>

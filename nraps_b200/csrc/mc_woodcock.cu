@@ -1,0 +1,255 @@
+// Woodcock delta tracking with a collision-estimator tally: the tracking the
+// north star names.  No surface crossings: a flight is sampled against the
+// majorant of the two energy groups in play, every tentative collision scores
+// 1/Sigma_maj into the cell it lands in (unbiased track-length estimate) and is
+// accepted as a real collision with probability sigtr/Sigma_maj.  Cost per
+// history is independent of the mesh (36 tentative collisions on deck C against
+// 364 cell crossings; 3642 on the fine mesh) and every lane of a warp executes
+// the same short loop body, so SIMT efficiency is high by construction.
+//
+// Same source, collision physics, draw order inside a collision, stale
+// cross-section group (the group index set when a material run is
+// entered is kept until the neutron leaves that run) and bank rules as the
+// surface kernel; statistically equivalent to the reference, bit-identical to
+// the oracle's Woodcock mode (oracle/oracle_mc.c: run_history_woodcock).
+#include "mc_lane.cuh"
+
+namespace nraps {
+
+namespace {
+
+template <int TG, bool TRACE, bool BANK>
+__global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int G = TG ? TG : (int)P.G;
+    const int M = (int)P.M, N = (int)P.N, NB = (int)P.NB;
+    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB);
+    const SmemView S = load_block_tables(smem_raw, P, L);
+    const float *s_edges = S.edges, *s_xs = S.xs;
+    const uint32_t *s_runb = S.runb;
+    const ulonglong2 *s_jump = S.jump;
+    const uint16_t *s_fuel = S.fuel, *s_bucket = S.bucket;
+    const uint8_t *s_matid = S.matid;
+    const int tid = threadIdx.x, MG = M * G;
+    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_chi = s_xs + 2 * MG, *s_nusigf = s_xs + 3 * MG,
+                *s_sigtr = s_xs + 4 * MG, *s_scat = s_xs + 5 * MG, *s_inv_maj = s_xs + 5 * MG + MG * G * G;
+    const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
+    const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
+    const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(S.lo);
+    const uint32_t hi_off = L.tally_hi - L.tally_lo;
+    const float len = s_edges[N];
+
+    const unsigned lane = tid & 31;
+    const uint64_t inc = P.rng_inc;
+    uint64_t w_next = 0, w_end = 0, w_state = 0;
+    bool exhausted = false;
+
+    bool alive = false, left = false;
+    uint64_t rng = 0, y = 0;
+    float x = 0.f, mu = 1.f;
+    int cell = 0, g = 0, xsg = 0, home_lo = 0, home_hi = 0;
+    uint32_t h_coll = 0, h_flight = 0, h_refl = 0, h_bank = 0;
+    uint32_t c_hist = 0, c_coll = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0, c_bank = 0;
+
+    for (;;) {
+        __syncwarp();
+        // ---------------- SPAWN (identical to the surface kernel)
+        const unsigned need = __ballot_sync(kFull, !alive);
+        if (need) {
+            if (w_next == w_end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(P.work, (unsigned long long)P.chunk);
+                base = __shfl_sync(kFull, base, 0);
+                const uint64_t b = P.hist_begin + base;
+                if (b >= P.hist_end) exhausted = true;
+                else {
+                    w_next = b;
+                    w_end = (b + P.chunk < P.hist_end) ? b + P.chunk : P.hist_end;
+                    w_state = jump_ahead(P.rng_state, b, s_jump);
+                }
+            }
+            const uint32_t avail = (uint32_t)(w_end - w_next);
+            if (avail) {
+                const uint32_t rank = __popc(need & ((1u << lane) - 1u));
+                if (!alive && rank < avail) {
+                    y = w_next + rank;
+                    rng = jump_ahead(w_state, rank, s_jump);
+                    const uint32_t u = pcg32_next(rng, inc);
+                    if (BANK && src_count) {
+                        const unsigned long long site = __ldg(P.src_bank + (((unsigned long long)u * src_count) >> 32));
+                        cell = (int)(site >> 32);
+                        x = __uint_as_float((uint32_t)site);
+                        mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
+                    } else {
+                        cell = s_fuel[__umulhi(u, P.NF)];
+                        const float xi_pos = pcg32_unit(rng, inc);
+                        mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
+                        x = fadd(s_edges[cell], fmul(xi_pos, P.dx_fuel));
+                    }
+                    g = search_cdf<TG>(s_chi + s_matid[cell] * G, G, pcg32_unit(rng, inc));
+                    xsg = g;
+                    const uint32_t rb = s_runb[cell];
+                    home_lo = (int)(rb & 0xffffu);
+                    home_hi = (int)(rb >> 16);
+                    left = false;
+                    h_coll = h_flight = h_refl = h_bank = 0;
+                    alive = true;
+                }
+                const uint32_t want = __popc(need);
+                const uint32_t took = want < avail ? want : avail;
+                w_next += took;
+                w_state = jump_ahead(w_state, took, s_jump);
+            } else if (need == kFull) {
+                break;
+            }
+        }
+        __syncwarp();
+
+        // ---------------- FLIGHT to the next tentative collision
+        uint32_t fate = 0;
+        bool accepted = false;
+        int mat = 0, g_eff = 0;
+        if (alive) {
+            if (h_flight >= P.max_flights) {
+                fate = NRAPS_FATE_TRUNCATED;
+            } else {
+                const float inv_maj = s_inv_maj[xsg * G + g];
+                float xn = fadd(x, fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), inv_maj));
+                ++h_flight;
+                while (xn < 0.0f || xn > len) { // albedo walls; rare
+                    const bool lo_wall = xn < 0.0f;
+                    const float wall = lo_wall ? 0.0f : len, b = lo_wall ? P.boundl : P.boundr;
+                    if (!(b > 0.0f)) { fate = NRAPS_FATE_LEAKED; break; }
+                    const float rem = fsub(xn, wall);
+                    mu = fmul(mu, -b);
+                    xn = fadd(wall, fmul(rem, -b));
+                    if (lo_wall ? (home_lo != 0) : (home_hi != N)) left = true;
+                    ++h_refl;
+                }
+                if (!fate) {
+                    // cell containing xn: bucket guess, then exact correction against the edges
+                    int c = __float2int_rz(fmul(xn, P.inv_h));
+                    c = s_bucket[c < NB - 1 ? c : NB - 1];
+                    while (c < N - 1 && s_edges[c + 1] <= xn) ++c;
+                    while (c > 0 && s_edges[c] > xn) --c;
+                    cell = c;
+                    x = xn;
+                    left = left || cell < home_lo || cell >= home_hi;
+                    mat = s_matid[cell];
+                    g_eff = left ? g : xsg;
+                    score(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, inv_maj);
+                    accepted = pcg32_unit(rng, inc) < fmul(s_sigtr[mat + M * g_eff], inv_maj);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---------------- COLLIDE: real collisions only (src/mc_code.rs:183-209)
+        if (accepted) {
+            ++h_coll;
+            const int xs = mat + M * g_eff;
+            const float xi_int = pcg32_unit(rng, inc);
+            const float mu_new = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
+            const int g_new = sample_group<TG>(s_scat + ((mat * G + g) * G + g_eff) * G, G, P.scatter_mode, rng, inc);
+            if (BANK) {
+                const float nusigf = s_nusigf[mat + M * g];
+                if (nusigf > 0.0f) {
+                    const float wgt = fmul(fmul(nusigf, s_inv_sigtr[xs]), inv_k);
+                    const uint32_t n = (uint32_t)__float2int_rz(fadd(wgt, pcg32_unit(rng, inc)));
+                    const unsigned long long site = ((unsigned long long)(uint32_t)cell << 32) | __float_as_uint(x);
+                    for (uint32_t j = 0; j < n; ++j) {
+                        if (h_bank < P.bank_cap) P.slots[(y - P.hist_begin) * P.bank_cap + h_bank] = site;
+                        ++h_bank;
+                    }
+                }
+            }
+            if (xi_int < s_p_abs[xs]) {
+                fate = NRAPS_FATE_ABSORBED;
+            } else {
+                g = g_new;
+                mu = mu_new;
+                xsg = P.stale_xs ? g_eff : g;
+                const uint32_t rb = s_runb[cell];
+                home_lo = (int)(rb & 0xffffu);
+                home_hi = (int)(rb >> 16);
+                left = false;
+            }
+        }
+
+        if (fate) {
+            alive = false;
+            ++c_hist;
+            c_coll += h_coll;
+            c_flight += h_flight;
+            c_refl += h_refl;
+            c_leak += (fate == NRAPS_FATE_LEAKED);
+            c_trunc += (fate == NRAPS_FATE_TRUNCATED);
+            if (BANK) {
+                const uint32_t kept = h_bank < P.bank_cap ? h_bank : P.bank_cap;
+                P.counts[y - P.hist_begin] = (uint8_t)kept;
+                c_bank += kept;
+            }
+            if (TRACE && P.trace) {
+                uint32_t *t = P.trace + (y - P.hist_begin) * NRAPS_TR_WORDS;
+                t[NRAPS_TR_COLLISIONS] = h_coll;
+                t[NRAPS_TR_CROSSINGS] = 0u;
+                t[NRAPS_TR_FLIGHTS] = h_flight;
+                t[NRAPS_TR_REFLECTIONS] = h_refl;
+                t[NRAPS_TR_RNG_LO] = (uint32_t)rng;
+                t[NRAPS_TR_RNG_HI] = (uint32_t)(rng >> 32);
+                t[NRAPS_TR_CELL] = (uint32_t)cell;
+                t[NRAPS_TR_XBITS] = __float_as_uint(x);
+                t[NRAPS_TR_FATE] = fate;
+                t[NRAPS_TR_GROUP] = (uint32_t)g;
+            }
+        }
+    }
+
+    const uint32_t vals[8] = {c_hist, c_coll, 0u, c_flight, c_refl, c_leak, c_trunc, c_bank};
+    flush_block(S, P, vals);
+}
+
+template <int TG>
+cudaError_t launch_g(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
+{
+    if (bank) {
+        if (trace) woodcock_kernel<TG, true, true><<<grid, block, smem, s>>>(p);
+        else woodcock_kernel<TG, false, true><<<grid, block, smem, s>>>(p);
+    } else {
+        if (trace) woodcock_kernel<TG, true, false><<<grid, block, smem, s>>>(p);
+        else woodcock_kernel<TG, false, false><<<grid, block, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+template <int TG> cudaError_t set_smem(uint32_t bytes)
+{
+    cudaError_t e;
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if ((e = cudaFuncSetAttribute(woodcock_kernel<TG, false, false>, attr, (int)bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(woodcock_kernel<TG, true, false>, attr, (int)bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(woodcock_kernel<TG, false, true>, attr, (int)bytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(woodcock_kernel<TG, true, true>, attr, (int)bytes);
+}
+
+} // namespace
+
+cudaError_t prepare_woodcock(uint32_t smem_bytes)
+{
+    cudaError_t e;
+    if ((e = set_smem<2>(smem_bytes)) != cudaSuccess) return e;
+    if ((e = set_smem<4>(smem_bytes)) != cudaSuccess) return e;
+    return set_smem<0>(smem_bytes);
+}
+
+cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
+{
+    switch (p.G) {
+    case 2: return launch_g<2>(p, trace, bank, grid, block, smem, s);
+    case 4: return launch_g<4>(p, trace, bank, grid, block, smem, s);
+    default: return launch_g<0>(p, trace, bank, grid, block, smem, s);
+    }
+}
+
+} // namespace nraps

@@ -47,6 +47,10 @@ typedef struct {
     uint8_t *counts;           /* [hist_count] */
     uint32_t bank_cap;
     uint64_t slot_base;        /* history index of slot row 0 */
+    /* Woodcock delta tracking (new capability named by the north star) */
+    const float *sigtr;        /* [M*G]  sigt - mu*sigs, the collision density flights are sampled with */
+    const float *inv_maj;      /* [G*G]  1 / max over present materials of max(sigtr[m][a], sigtr[m][b]) */
+    const uint32_t *run_lo, *run_hi; /* [N] cell bounds of each cell's material run */
 } run_shared;
 
 typedef struct {
@@ -344,10 +348,152 @@ static inline __attribute__((always_inline)) void run_history(worker *w, uint64_
     }
 }
 
+/* cell containing x: number of interior edges <= x */
+static inline uint64_t locate_cell(const oracle_problem *p, float x)
+{
+    uint64_t lo = 0, hi = p->N - 1; /* interior edges are right[0 .. N-2] */
+    while (lo < hi) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (p->right[mid] <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+/*
+ * One history under Woodcock delta tracking with a collision-estimator tally.
+ * Statistically equivalent to run_history (same source, same collision physics
+ * including the stale cross-section group of SURVEY 9-Q1: the group index set on
+ * entering a material run is kept until the neutron leaves that run), but no
+ * surface crossings: flights are sampled against the majorant of the two groups
+ * in play, every tentative collision scores 1/Sigma_maj (an unbiased track-length
+ * estimate), and it is accepted as real with probability sigtr/Sigma_maj.
+ */
+static inline __attribute__((always_inline)) void run_history_woodcock(worker *w, uint64_t y)
+{
+    const run_shared *sh = w->sh;
+    const oracle_problem *p = sh->p;
+    const oracle_options *o = sh->o;
+    const uint32_t G = p->G, M = p->M;
+    const uint64_t N = p->N;
+    const float L = p->right[N - 1];
+
+    oracle_pcg32 rng = sh->master;
+    oracle_pcg32_advance(&rng, (sh->gen * p->histories + y) * o->stride);
+    uint32_t u = oracle_pcg32_next(&rng);
+    uint64_t cell;
+    float x, mu;
+    uint32_t g;
+    if (sh->src_bank) {
+        uint64_t site = sh->src_bank[((uint64_t)u * sh->src_count) >> 32];
+        uint32_t xb = (uint32_t)site;
+        cell = site >> 32;
+        memcpy(&x, &xb, 4);
+        mu = oracle_direction(oracle_uniform(&rng));
+        g = oracle_energy(p, oracle_uniform(&rng), cell);
+    } else {
+        cell = p->fuel_indices[((uint64_t)u * (uint64_t)p->NF) >> 32];
+        float xi_pos = oracle_uniform(&rng);
+        mu = oracle_direction(oracle_uniform(&rng));
+        g = oracle_energy(p, oracle_uniform(&rng), cell);
+        x = p->left[cell] + (xi_pos * p->dx_fuel);
+    }
+    uint32_t xsg = g, home_lo = sh->run_lo[cell], home_hi = sh->run_hi[cell];
+    int left = 0;
+    uint32_t n_coll = 0, n_flight = 0, n_refl = 0, n_bank = 0, fate = 0;
+    float cdf[256];
+
+    for (;;) {
+        if (n_flight >= sh->max_flights) { fate = ORACLE_FATE_TRUNCATED; break; }
+        const float inv_maj = sh->inv_maj[xsg * G + g];
+        float ds = mu * -oracle_logf(oracle_uniform(&rng)) * inv_maj;
+        float xn = x + ds;
+        ++n_flight;
+        while (xn < 0.0f || xn > L) { /* albedo walls, SURVEY 9-Q8 */
+            const int lo_wall = xn < 0.0f;
+            const float wall = lo_wall ? 0.0f : L, b = lo_wall ? p->boundl : p->boundr;
+            if (!(b > 0.0f)) { fate = ORACLE_FATE_LEAKED; break; }
+            const float rem = xn - wall;
+            mu = mu * (-b);
+            xn = wall + rem * (-b);
+            if (lo_wall ? (home_lo != 0) : (home_hi != N)) left = 1;
+            ++n_refl;
+        }
+        if (fate) break;
+        cell = locate_cell(p, xn);
+        x = xn;
+        if (cell < home_lo || cell >= home_hi) left = 1;
+        const uint32_t mat = p->matid[cell];
+        const uint32_t g_eff = left ? g : xsg;
+        const uint32_t xs = mat + M * g_eff;
+        score(w, g, cell, inv_maj);
+        if (oracle_uniform(&rng) < sh->sigtr[xs] * inv_maj) {
+            /* real collision: same physics and draw order as mc_code.rs:183-209 */
+            ++n_coll;
+            oracle_scat_mat_calc(G, mat, g, 1.0f / p->sigs[xs], p->scat, cdf);
+            float xi_int = oracle_uniform(&rng);
+            float absorption = p->siga[xs] / p->sigt[xs];
+            float mu_new = 2.0f * oracle_uniform(&rng) - 1.0f;
+            uint32_t g_new = sample_group(cdf, G, o->scatter_mode, &rng);
+            if (sh->bank_mode) {
+                float nusigf = p->nut[mat + M * g] * p->sigf[mat + M * g];
+                if (nusigf > 0.0f) {
+                    float wgt = nusigf * p->inv_sigtr[xs] * sh->inv_k;
+                    uint32_t n = (uint32_t)(int32_t)(wgt + oracle_uniform(&rng));
+                    uint32_t xb;
+                    memcpy(&xb, &x, 4);
+                    for (uint32_t j = 0; j < n; ++j) {
+                        if (n_bank < sh->bank_cap)
+                            sh->slots[(y - sh->slot_base) * sh->bank_cap + n_bank] = ((uint64_t)cell << 32) | xb;
+                        ++n_bank;
+                    }
+                }
+            }
+            if (xi_int < absorption) { fate = ORACLE_FATE_ABSORBED; break; }
+            g = g_new;
+            mu = mu_new;
+            xsg = o->stale_xs ? g_eff : g;
+            home_lo = sh->run_lo[cell];
+            home_hi = sh->run_hi[cell];
+            left = 0;
+        }
+    }
+
+    w->counters[ORACLE_CT_HISTORIES] += 1;
+    w->counters[ORACLE_CT_COLLISIONS] += n_coll;
+    w->counters[ORACLE_CT_FLIGHTS] += n_flight;
+    w->counters[ORACLE_CT_REFLECTIONS] += n_refl;
+    w->counters[ORACLE_CT_LEAKS] += (fate == ORACLE_FATE_LEAKED);
+    w->counters[ORACLE_CT_TRUNCATED] += (fate == ORACLE_FATE_TRUNCATED);
+    if (sh->bank_mode) {
+        uint32_t kept = n_bank < sh->bank_cap ? n_bank : sh->bank_cap;
+        sh->counts[y - sh->slot_base] = (uint8_t)kept;
+        w->counters[ORACLE_CT_BANKED] += kept;
+    }
+    if (w->trace) {
+        uint32_t *t = w->trace + (y - w->trace_base) * ORACLE_TR_WORDS;
+        uint32_t xb;
+        memcpy(&xb, &x, 4);
+        t[ORACLE_TR_COLLISIONS] = n_coll;
+        t[ORACLE_TR_CROSSINGS] = 0;
+        t[ORACLE_TR_FLIGHTS] = n_flight;
+        t[ORACLE_TR_REFLECTIONS] = n_refl;
+        t[ORACLE_TR_RNG_LO] = (uint32_t)rng.state;
+        t[ORACLE_TR_RNG_HI] = (uint32_t)(rng.state >> 32);
+        t[ORACLE_TR_CELL] = (uint32_t)cell;
+        t[ORACLE_TR_XBITS] = xb;
+        t[ORACLE_TR_FATE] = fate;
+        t[ORACLE_TR_GROUP] = g;
+    }
+}
+
 /* particle_lifetime, mc_code.rs:215-257 */
 ORACLE_HOT static void run_range(worker *w)
 {
-    for (uint64_t y = w->start; y < w->end; ++y) run_history(w, y);
+    if (w->sh->o->tracking_mode == ORACLE_TRACK_WOODCOCK)
+        for (uint64_t y = w->start; y < w->end; ++y) run_history_woodcock(w, y);
+    else
+        for (uint64_t y = w->start; y < w->end; ++y) run_history(w, y);
 }
 
 static void *worker_main(void *arg)
@@ -395,7 +541,7 @@ int oracle_monte_carlo(const oracle_problem *p, const oracle_options *o, oracle_
 {
     if (!p || !o || !r) return -1;
     if (p->G < 2 /* mc_code.rs:356 indexes nut[M*1] */ || p->G > 256 || p->M == 0 || p->N == 0 || p->NF == 0 || p->numass == 0) return -2;
-    if (o->source_mode < 0 || o->source_mode > ORACLE_SOURCE_FISSION_BANK || o->tracking_mode != ORACLE_TRACK_SURFACE) return -3;
+    if (o->source_mode < 0 || o->source_mode > ORACLE_SOURCE_FISSION_BANK || o->tracking_mode < 0 || o->tracking_mode > ORACLE_TRACK_WOODCOCK) return -3;
     const uint32_t G = p->G, M = p->M;
     const uint64_t N = p->N, GN = (uint64_t)G * N;
 
@@ -429,6 +575,33 @@ int oracle_monte_carlo(const oracle_problem *p, const oracle_options *o, oracle_
     for (uint64_t i = 0; i < p->generations; ++i) { r->k[i] = 0.0f; r->k_fund[i] = 0.0f; }
     memset(r->counters, 0, sizeof(r->counters));
     r->seconds_transport = 0.0;
+
+    /* Woodcock tables */
+    float *sigtr = (float *)malloc((size_t)M * G * sizeof(float));
+    float *inv_maj = (float *)malloc((size_t)G * G * sizeof(float));
+    uint32_t *run_lo = (uint32_t *)malloc(N * sizeof(uint32_t)), *run_hi = (uint32_t *)malloc(N * sizeof(uint32_t));
+    {
+        int present[256] = {0};
+        for (uint64_t i = 0; i < N; ++i) present[p->matid[i]] = 1;
+        for (uint32_t i = 0; i < M * G; ++i) sigtr[i] = p->sigt[i] - p->mu[i] * p->sigs[i];
+        for (uint32_t a = 0; a < G; ++a)
+            for (uint32_t b = 0; b < G; ++b) {
+                float mx = 0.0f;
+                for (uint32_t m = 0; m < M; ++m) {
+                    if (!present[m]) continue;
+                    if (sigtr[m + M * a] > mx) mx = sigtr[m + M * a];
+                    if (sigtr[m + M * b] > mx) mx = sigtr[m + M * b];
+                }
+                inv_maj[a * G + b] = 1.0f / mx;
+            }
+        for (uint64_t i = 0; i < N;) {
+            uint64_t j = i;
+            while (j < N && p->matid[j] == p->matid[i]) ++j;
+            for (uint64_t q = i; q < j; ++q) { run_lo[q] = (uint32_t)i; run_hi[q] = (uint32_t)j; }
+            i = j;
+        }
+    }
+    sh.sigtr = sigtr; sh.inv_maj = inv_maj; sh.run_lo = run_lo; sh.run_hi = run_hi;
 
     sh.bank_mode = (o->source_mode == ORACLE_SOURCE_FISSION_BANK);
     sh.bank_cap = o->bank_cap > 0 ? (uint32_t)o->bank_cap : 8u;
@@ -534,5 +707,6 @@ int oracle_monte_carlo(const oracle_problem *p, const oracle_options *o, oracle_
     }
     free(ws); free(th); free(tally_fixed); free(tally);
     free(sh.slots); free(sh.counts); free(bank_cur); free(bank_next); free(cell_hist);
+    free(sigtr); free(inv_maj); free(run_lo); free(run_hi);
     return 0;
 }

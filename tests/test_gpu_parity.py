@@ -339,3 +339,56 @@ def test_two_gpus_equal_one_gpu_bit_for_bit(tmp_path, mode):
         assert np.array_equal(bits(z["k"]), bits(one.k)) and np.array_equal(bits(z["flux"]), bits(one.flux))
         assert np.array_equal(z["bank"], one.bank_sizes) and np.allclose(z["ent"], one.entropy, atol=1e-12, rtol=0)
         assert int(z["coll"]) == one.counters["collisions"]
+
+
+# ---------------------------------------------------------------- Woodcock delta tracking (north-star tracking mode)
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_woodcock_replay_and_results_bit_exact(case):
+    v, xs, dx, mesh, fuel = load_case(case)
+    H = 100_000
+    with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=3, histories=H, skip=0, tracking_mode="woodcock") as ctx:
+        rec = ctx.trace(2, 0, H)
+        tally, counters = ctx.read_tally()
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=3, histories=H, skip=0, threads=8, trace_gen=2, want_tally=True,
+                           tracking_mode="woodcock")
+    assert np.array_equal(rec, want.trace)
+    assert np.array_equal(tally, want.tally_fixed[2])
+    got, want = _both(case, generations=4, histories=80_000, tracking_mode="woodcock")
+    _assert_identical(got, want)
+
+
+def test_woodcock_variants_bit_exact():
+    for kw in (dict(stale_xs=False), dict(scatter_mode="rust_pre182"), dict(source_mode="fission_bank")):
+        got, want = _both("c", generations=3, histories=50_000, tracking_mode="woodcock", **kw)
+        _assert_identical(got, want)
+        assert np.array_equal(got.bank_sizes, want.bank_sizes)
+    args = _with_bounds("a", 0.0, 0.5)
+    got = nb.monte_carlo(*args, 1.0, generations=2, histories=50_000, skip=1, want_tally=True, tracking_mode="woodcock")
+    deck, m = oracle_inputs(*args)
+    want = orc.monte_carlo(deck, m, generations=2, histories=50_000, skip=1, threads=8, want_tally=True, tracking_mode="woodcock")
+    _assert_identical(got, want)
+    assert got.counters["leaks"] > 0 and got.counters["reflections"] == want.counters["reflections"] > 0
+    v, xs, dx, mesh, fuel = load_case("c", mpfr=80, mpwr=40)  # fine mesh: cost independent of N
+    got = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=50_000, skip=1, want_tally=True, tracking_mode="woodcock")
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=2, histories=50_000, skip=1, threads=8, want_tally=True, tracking_mode="woodcock")
+    _assert_identical(got, want)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_woodcock_agrees_with_reference_tracking_statistically(case):
+    """north-star criterion: k within 3 sigma combined and per-bin chi-square against the surface-tracking
+    (reference-semantics) solver, independent estimators on the same physics."""
+    v, xs, dx, mesh, fuel = load_case(case)
+    gens, H = 16, 200_000
+    w = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1, want_tally=True, tracking_mode="woodcock")
+    s = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1, want_tally=True, seed=9, stream=9, stride=152917)
+    kw, ks = w.k.astype(np.float64), s.k.astype(np.float64)
+    sigma = np.hypot(kw.std(ddof=1), ks.std(ddof=1)) / np.sqrt(gens)
+    assert abs(kw.mean() - ks.mean()) < 3 * sigma, (kw.mean(), ks.mean(), sigma)
+    tw = w.tally_fixed.astype(np.float64).reshape(gens, -1)
+    ts = s.tally_fixed.astype(np.float64).reshape(gens, -1)
+    var = (tw.var(axis=0, ddof=1) + ts.var(axis=0, ddof=1)) / gens
+    z2 = (tw.mean(axis=0) - ts.mean(axis=0)) ** 2 / var
+    assert abs(z2.sum() - z2.size) < 6 * np.sqrt(2 * z2.size) * 1.2, (z2.sum(), z2.size)

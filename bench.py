@@ -66,7 +66,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -105,6 +105,15 @@ def peaks():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s; MEASURED_PEAKS.json absent)"
+
+
+def measured_traffic(kernel: str):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)[kernel]["bytes"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def cpu_sample(args, histories: int, generations: int, threads: int, faithful: bool = True):
@@ -181,56 +190,68 @@ def run_ours(a):
     K, W = a.steps, a.warmup
     gens_total = W + K
 
-    opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode,
-                tracking_mode=a.tracking)
-    ctx = nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens_total, histories=H, skip=1, **opts)
-    tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{local}")
-    ctx.use_tally_tensor(tally)
+    base_opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode)
+    opts = dict(base_opts, tracking_mode=a.tracking)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
     begin, count = shard_range(H, rank, world)
     from nraps_b200.dist import make_bank_callback
-
-    bank = make_bank_callback(ctx, world, local, stream) if source_mode == "fission_bank" else None
-
-    def step(gen, ev=None):
-        flush.zero_()
-        if ev:
-            ev[0].record()
-        ctx.transport(gen, begin, count, stream)
-        if ev:
-            ev[1].record()
-        if world > 1:
-            dist.all_reduce(tally)
-        ctx.finalize_generation(gen, stream)
-        if bank is not None:
-            bank(gen)
 
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for g in range(W):
-        step(g)
-    fence()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_begin.record()
-    for i in range(K):
-        step(W + i, k_events[i])
-    t_end.record()
-    fence()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = t_begin.elapsed_time(t_end)
-    ms_kernel = sum(e0.elapsed_time(e1) for e0, e1 in k_events) / K  # memsets + transport kernel of one step
-    res = ctx.fetch(stream)
+    def device_run(run_opts, sample_clocks):
+        """W warm-up + K timed generations with everything resident on the device."""
+        ctx = nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens_total, histories=H, skip=1, **run_opts)
+        tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{local}")
+        ctx.use_tally_tensor(tally)
+        bank = make_bank_callback(ctx, world, local, stream) if source_mode == "fission_bank" else None
+
+        def step(gen, ev=None):
+            flush.zero_()
+            if ev:
+                ev[0].record()
+            ctx.transport(gen, begin, count, stream)
+            if ev:
+                ev[1].record()
+            if world > 1:
+                dist.all_reduce(tally)
+            ctx.finalize_generation(gen, stream)
+            if bank is not None:
+                bank(gen)
+
+        for g in range(W):
+            step(g)
+        fence()
+        sampler = ClockSampler(local)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin.record()
+        for i in range(K):
+            step(W + i, k_events[i])
+        t_end.record()
+        fence()
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        out = dict(ms_total=t_begin.elapsed_time(t_end), ms_kernel=sum(e0.elapsed_time(e1) for e0, e1 in k_events) / K,
+                   res=ctx.fetch(stream), info=ctx.launch_info(), clocks=clocks, has_bank=bank is not None)
+        ctx.close()
+        if world > 1:
+            t = torch.tensor([out["ms_total"], out["ms_kernel"]], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out["ms_total"], out["ms_kernel"] = (float(x) for x in t.tolist())
+        return out
+
+    main_run = device_run(opts, True)
+    ms_total, ms_kernel, res, info, clocks = (main_run[k] for k in ("ms_total", "ms_kernel", "res", "info", "clocks"))
+    has_bank = main_run["has_bank"]
     coll_per_hist = res.counters["collisions"] / max(1, res.counters["histories"])
-    info = ctx.launch_info()
-    ctx.close()
+    # the other tracking mode on the same workload, reported beside the headline (not instead of it)
+    other = "woodcock" if a.tracking == "surface" else "surface"
+    other_run = None if a.no_variants else device_run(dict(base_opts, tracking_mode=other), False)
 
     # end to end through the public call: host arrays in, SolutionResults out (create + H2D + K generations + D2H)
     fence()
@@ -243,16 +264,16 @@ def run_ours(a):
     e2e_s = time.perf_counter() - t0
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_kernel, e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_kernel, e2e_s = (float(x) for x in t.tolist())
+        e2e_s = float(t.item())
     if rank == 0:
         G, M, N, NF = v.energygroups, v.mattypes, len(mesh), len(fuel)
         h2d = 4 * (8 * M * G + M * G * G + 3 * N) + N + 8 * NF  # tables the call uploads, once per run
         d2h = 4 * (G * N + N + K) + 64                           # flux, fission source, k, counters
         peak, peak_src = peaks()
         b_hist = RECORD_BYTES + 2 * RECORD_BYTES * coll_per_hist
-        if bank is not None:
+        if has_bank:
             b_hist += 12 + 12 * res.counters["banked"] / max(1, res.counters["histories"])  # source read + bank write, SURVEY 8d
         hist_per_launch = count
         achieved = b_hist * hist_per_launch / (ms_kernel * 1e-3) / 1e9
@@ -266,14 +287,24 @@ def run_ours(a):
             "clocks": clocks,
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "note": "one monte_carlo() call: context create + table upload + K generations + result download; bytes are per run / K"},
-            "gpu_launches": (2 + (5 if bank is not None else 0)) * K,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if bank is not None else "false"), "kernel_ms": ms_kernel,
+            "gpu_launches": (2 + (5 if has_bank else 0)) * K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel"),
+                         "peak_source": peak_src, "kernel": ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if has_bank else "false"), "kernel_ms": ms_kernel,
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
                          "note": "algorithmic bytes = 24 + 48*collisions/history (SURVEY 8d bank model); the fused kernel keeps "
                                  "particles in registers so real DRAM traffic is far lower: the kernel is issue/shared-memory bound"},
             "k_mean": float(res.k[W:].mean()), "k_e2e_mean": float(e2e_res.k[1:].mean()) if K > 1 else float(e2e_res.k[0]),
         }
+        if other_run is not None:
+            o_coll = other_run["res"].counters["collisions"] / max(1, other_run["res"].counters["histories"])
+            line["variants"] = {other: {
+                "value": H * K / (other_run["ms_total"] * 1e-3), "unit": UNIT, "ms_per_step": other_run["ms_total"] / K,
+                "k_mean": float(other_run["res"].k[W:].mean()), "collisions_per_history": o_coll,
+                "roofline_frac": (RECORD_BYTES + 2 * RECORD_BYTES * o_coll) * count / (other_run["ms_kernel"] * 1e-3) / 1e9 / peak,
+                "note": "same workload, same timing rules, other tracking mode: 'surface' follows the reference cell by cell "
+                        "(bit-comparable with the CPU restatement); 'woodcock' is delta tracking with a collision-estimator tally "
+                        "(statistically equivalent, 3 sigma / chi-square tested)"}}
         if world == 1 and not a.no_cpu:
             cores = os.cpu_count() or 2
             threads = max(1, cores - 1)
@@ -303,6 +334,7 @@ def main():
     ap.add_argument("--tracking", default="surface", choices=["surface", "woodcock"],
                     help="surface = the reference's cell-by-cell tracking (headline, bit-comparable); woodcock = delta tracking")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other-tracking-mode measurement")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

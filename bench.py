@@ -191,7 +191,7 @@ def run_ours(a):
     gens_total = W + K
 
     base_opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode)
-    opts = dict(base_opts, tracking_mode=a.tracking)
+    opts = dict(base_opts, tracking_mode=a.tracking, kernel_variant=a.variant)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
     begin, count = shard_range(H, rank, world)
@@ -333,6 +333,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--tracking", default="surface", choices=["surface", "woodcock"],
                     help="surface = the reference's cell-by-cell tracking (headline, bit-comparable); woodcock = delta tracking")
+    ap.add_argument("--variant", default="fused", choices=["fused", "event"], help="kernel variant (event = SoA-bank pipeline, woodcock only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other-tracking-mode measurement")
     a = ap.parse_args()

@@ -123,6 +123,11 @@ struct nraps_mc_ctx {
     const unsigned long long *src_bank = nullptr, *src_count_ptr = nullptr;
     uint64_t ext_count_host = 0;
     uint64_t last_shard = 0;
+
+    // event-based pipeline (kernel_variant = NRAPS_KERNEL_EVENT)
+    EventBank ev{};
+    uint64_t ev_cap = 0;
+    uint32_t ev_iterations = 0; // advance/collide/compact rounds of the last generation
 };
 
 namespace {
@@ -140,7 +145,11 @@ int validate(const nraps_problem *p, const nraps_options *o)
     if ((uint64_t)p->M * p->G * p->G * p->G > 8192) return NRAPS_ERR_TOO_LARGE;
     if (o->scatter_mode < 0 || o->scatter_mode > NRAPS_SCATTER_RUST_182) return NRAPS_ERR_OPTION;
     if (o->source_mode < 0 || o->source_mode > NRAPS_SOURCE_FISSION_BANK || o->tracking_mode < 0 || o->tracking_mode > NRAPS_TRACK_WOODCOCK ||
-        o->kernel_variant != NRAPS_KERNEL_FUSED || o->bank_cap < 0 || o->bank_cap > 255)
+        o->kernel_variant < 0 || o->kernel_variant > NRAPS_KERNEL_EVENT || o->bank_cap < 0 || o->bank_cap > 255)
+        return NRAPS_ERR_OPTION;
+    // the event pipeline is built for Woodcock tracking with the uniform source (one event = one tentative collision)
+    if (o->kernel_variant == NRAPS_KERNEL_EVENT &&
+        (o->tracking_mode != NRAPS_TRACK_WOODCOCK || o->source_mode != NRAPS_SOURCE_UNIFORM_FUEL))
         return NRAPS_ERR_OPTION;
     for (uint32_t i = 0; i < p->N; ++i) {
         if (p->matid[i] >= p->M) return NRAPS_ERR_MESH;
@@ -166,8 +175,31 @@ void free_ctx(nraps_mc_ctx *c)
     cudaFree(c->d_terms); cudaFree(c->d_res_flux); cudaFree(c->d_res_fission); cudaFree(c->d_k_hist); cudaFree(c->d_k_cur);
     cudaFree(c->d_trace);
     cudaFree(c->d_slots); cudaFree(c->d_block_sums); cudaFree(c->d_dense[0]); cudaFree(c->d_dense[1]);
+    for (EventHalf &h : c->ev.half) { cudaFree(h.x); cudaFree(h.mu); cudaFree(h.pack); cudaFree(h.cnt); cudaFree(h.ccnt); cudaFree(h.rng); }
+    cudaFree(c->ev.n_alive);
     cudaFree(c->d_bank_count); cudaFree(c->d_bank_sizes); cudaFree(c->d_entropy); cudaFree(c->d_counts); cudaFree(c->d_hist);
     delete c;
+}
+
+int ensure_event_bank(nraps_mc_ctx *c, uint64_t count)
+{
+    if (count <= c->ev_cap) return NRAPS_OK;
+    for (EventHalf &h : c->ev.half) {
+        cudaFree(h.x); cudaFree(h.mu); cudaFree(h.pack); cudaFree(h.cnt); cudaFree(h.ccnt); cudaFree(h.rng);
+        h = EventHalf{};
+        CU(cudaMalloc((void **)&h.x, count * sizeof(float)));
+        CU(cudaMalloc((void **)&h.mu, count * sizeof(float)));
+        CU(cudaMalloc((void **)&h.pack, count * sizeof(uint32_t)));
+        CU(cudaMalloc((void **)&h.cnt, count * sizeof(uint32_t)));
+        CU(cudaMalloc((void **)&h.ccnt, count * sizeof(uint32_t)));
+        CU(cudaMalloc((void **)&h.rng, count * sizeof(unsigned long long)));
+    }
+    if (!c->ev.n_alive) {
+        CU(cudaMalloc((void **)&c->ev.n_alive, 2 * sizeof(unsigned long long)));
+        c->ev.n_next = c->ev.n_alive + 1;
+    }
+    c->ev_cap = count;
+    return NRAPS_OK;
 }
 
 // (re)size the per-history slot rows and the dense banks for a shard of `count` histories
@@ -220,6 +252,13 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
     P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
+    if (c->opt.kernel_variant == NRAPS_KERNEL_EVENT) {
+        if (trace) return NRAPS_ERR_OPTION;
+        int rc = ensure_event_bank(c, count);
+        if (rc != NRAPS_OK) return rc;
+        CU(run_event_generation(P, c->ev, c->layout.total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
+        return NRAPS_OK;
+    }
     if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
     else CU(launch_transport(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
     return NRAPS_OK;
@@ -589,7 +628,7 @@ extern "C" int nraps_mc_launch_info(nraps_mc_ctx *c, uint32_t out[6])
 {
     if (!c || !out) return NRAPS_ERR_NULL;
     out[0] = c->grid; out[1] = c->block; out[2] = c->layout.total; out[3] = c->blocks_per_sm;
-    out[4] = (uint32_t)c->sm_count; out[5] = c->chunk;
+    out[4] = (uint32_t)c->sm_count; out[5] = c->opt.kernel_variant == NRAPS_KERNEL_EVENT ? c->ev_iterations : c->chunk;
     return NRAPS_OK;
 }
 

@@ -77,6 +77,17 @@ struct TransportParams {
     uint32_t bank_cap;
 };
 
+// SoA particle bank of the event-based pipeline, two halves for ping-pong compaction (28 B per record)
+struct EventHalf {
+    float *x, *mu;
+    uint32_t *pack, *cnt, *ccnt;
+    unsigned long long *rng;
+};
+struct EventBank {
+    EventHalf half[2];
+    unsigned long long *n_alive, *n_next; // device scalars
+};
+
 struct BankParams {
     const uint8_t *counts;            // [n_hist padded to kBankTile]
     const unsigned long long *slots;  // [n_hist][cap]
@@ -108,6 +119,7 @@ struct FinalizeParams {
 cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
 cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
 cudaError_t prepare_woodcock(uint32_t smem_bytes);
+cudaError_t run_event_generation(const TransportParams &p, const EventBank &b, uint32_t smem, int sm_count, cudaStream_t s, uint32_t *iters);
 cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s);
 cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
                                 double *entropy_out, unsigned long long *size_out, cudaStream_t s);

@@ -392,3 +392,15 @@ def test_woodcock_agrees_with_reference_tracking_statistically(case):
     var = (tw.var(axis=0, ddof=1) + ts.var(axis=0, ddof=1)) / gens
     z2 = (tw.mean(axis=0) - ts.mean(axis=0)) ** 2 / var
     assert abs(z2.sum() - z2.size) < 6 * np.sqrt(2 * z2.size) * 1.2, (z2.sum(), z2.size)
+
+
+# ---------------------------------------------------------------- event-based SoA-bank pipeline (alternative kernel variant)
+@pytest.mark.parametrize("case", ["a", "c"])
+def test_event_pipeline_equals_fused_woodcock_and_oracle(case):
+    """source -> {advance, collide, compact}* over an HBM particle bank gives the same bins as the fused kernel."""
+    got, want = _both(case, generations=3, histories=70_000, tracking_mode="woodcock", gpu_kw=dict(kernel_variant="event"))
+    _assert_identical(got, want)
+    v, xs, dx, mesh, fuel = load_case(case)
+    with pytest.raises(_lib.NrapsError) as e:  # the event variant exists for Woodcock tracking only
+        nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1, kernel_variant="event")
+    assert e.value.code == 7

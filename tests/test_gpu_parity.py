@@ -404,3 +404,12 @@ def test_event_pipeline_equals_fused_woodcock_and_oracle(case):
     with pytest.raises(_lib.NrapsError) as e:  # the event variant exists for Woodcock tracking only
         nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1, kernel_variant="event")
     assert e.value.code == 7
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(tracking_mode="woodcock"), dict(tracking_mode="woodcock", source_mode="fission_bank")])
+def test_analytic_k_infinity_deck_a_on_gpu(kw):
+    """k = nu*Sigma_f / Sigma_a = 1.26 exactly for deck A once the stale-index quirk is off (see the CPU twin)."""
+    v, xs, dx, mesh, fuel = load_case("a")
+    r = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=12, histories=1_000_000, skip=1, stale_xs=False, **kw)
+    k = r.k[1:].astype(np.float64)
+    assert abs(k.mean() - 1.26) < 4 * k.std(ddof=1) / np.sqrt(len(k)) + 2e-5, (kw, k.mean(), k.std(ddof=1))

@@ -155,3 +155,16 @@ def test_oracle_faithful_f32_tallies_close_to_exact():
     faithful = orc.monte_carlo(deck, mesh, tally_mode="f32_per_worker", **kw)
     assert np.allclose(exact.k, faithful.k, rtol=2e-5)
     assert exact.counters == faithful.counters
+
+
+def test_analytic_k_infinity_deck_a():
+    """Physics anchor independent of any restatement: in deck A (mu_bar = 0, reflective walls) the only absorber
+    is thermal UO2 (Sigma_a = 0.2, nu*Sigma_f = 1.4*0.18), so with the stale-index quirk switched off every
+    neutron is absorbed there exactly once and k = nu*Sigma_f / Sigma_a = 1.26, whatever the flux shape."""
+    from tests.util import load_case, oracle_inputs
+
+    deck, mesh = oracle_inputs(*load_case("a"))
+    for kw in (dict(), dict(tracking_mode="woodcock"), dict(source_mode="fission_bank")):
+        r = orc.monte_carlo(deck, mesh, generations=8, histories=60000, skip=1, threads=4, stale_xs=False, **kw)
+        k = r.k[1:].astype(np.float64)
+        assert abs(k.mean() - 1.26) < 4 * k.std(ddof=1) / np.sqrt(len(k)) + 1e-4, (kw, k.mean())

@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-from nraps_b200.dist import run_generations, shard_range  # noqa: E402
+from nraps_b200.dist import gather_bank, run_generations, shard_range  # noqa: E402
 
 
 def test_shard_ranges_tile_the_generation():
@@ -22,6 +22,32 @@ def test_shard_ranges_tile_the_generation():
             for (b0, c0), (b1, _) in zip(spans, spans[1:]):
                 assert b0 + c0 == b1
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_gather_bank_concatenates_in_rank_order():
+    """Variable-length site lists -> one bank in rank (= history) order; simulated 3-rank all-gather."""
+    import torch
+
+    locals_ = [torch.arange(5, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), torch.arange(100, 103, dtype=torch.int64)]
+    counts = [t.numel() for t in locals_]
+    pads = {}
+
+    def counts_fn(n):
+        return counts
+
+    def make_padded_fn(rank):
+        def fn(padded, max_n):
+            pads[rank] = padded
+            rows = [torch.zeros(max_n, dtype=torch.int64) for _ in range(3)]
+            for r, t in enumerate(locals_):
+                rows[r][: t.numel()] = t
+            return torch.stack(rows)
+        return fn
+
+    for rank in range(3):
+        full, got_counts = gather_bank(locals_[rank], 3, counts_fn, make_padded_fn(rank))
+        assert got_counts == counts and full.tolist() == [0, 1, 2, 3, 4, 100, 101, 102]
+        assert pads[rank].numel() == 5 and pads[rank][: counts[rank]].tolist() == locals_[rank].tolist()
 
 
 class OracleEngine:

@@ -168,3 +168,33 @@ def test_analytic_k_infinity_deck_a():
         r = orc.monte_carlo(deck, mesh, generations=8, histories=60000, skip=1, threads=4, stale_xs=False, **kw)
         k = r.k[1:].astype(np.float64)
         assert abs(k.mean() - 1.26) < 4 * k.std(ddof=1) / np.sqrt(len(k)) + 1e-4, (kw, k.mean())
+
+
+def test_oracle_fission_bank_is_thread_invariant_and_shifts_k():
+    """fission_bank mode (new capability): canonical (history, site) bank order makes it independent of the worker
+    count; k_B rises ~1.9 % over the flat-source value (SURVEY section 0 probe: 1.777 -> 1.811)."""
+    from tests.util import load_case, oracle_inputs
+
+    deck, mesh = oracle_inputs(*load_case("b"))
+    kw = dict(generations=8, histories=40000, skip=1, source_mode="fission_bank", bank_gen=4)
+    a = orc.monte_carlo(deck, mesh, threads=1, **kw)
+    b = orc.monte_carlo(deck, mesh, threads=5, **kw)
+    assert np.array_equal(a.bank_sizes, b.bank_sizes) and np.array_equal(a.bank_sites, b.bank_sites)
+    assert np.array_equal(a.k.view(np.uint32), b.k.view(np.uint32))
+    assert abs(a.bank_sizes[1:].astype(float).mean() / 40000 - 1) < 0.02  # population control by 1/k_prev
+    flat = orc.monte_carlo(deck, mesh, threads=5, generations=8, histories=40000, skip=1)
+    assert 1.010 < a.k[3:].mean() / flat.k[3:].mean() < 1.030
+    assert a.entropy[0] > a.entropy[-1] > 7.0
+
+
+def test_oracle_woodcock_matches_surface_tracking_statistically():
+    from tests.util import load_case, oracle_inputs
+
+    deck, mesh = oracle_inputs(*load_case("b"))
+    w = orc.monte_carlo(deck, mesh, generations=10, histories=40000, skip=0, threads=4, tracking_mode="woodcock")
+    s = orc.monte_carlo(deck, mesh, generations=10, histories=40000, skip=0, threads=4, seed=5, seq=6)
+    kw_, ks = w.k.astype(np.float64), s.k.astype(np.float64)
+    sigma = np.hypot(kw_.std(ddof=1), ks.std(ddof=1)) / np.sqrt(10)
+    assert abs(kw_.mean() - ks.mean()) < 4 * sigma
+    assert abs(w.counters["collisions"] / w.counters["histories"] - s.counters["collisions"] / s.counters["histories"]) < 0.3
+    assert w.counters["crossings"] == 0 and w.counters["flights"] < 1.4 * w.counters["collisions"]

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
         __syncwarp();
         // ---------------- SPAWN: hand fresh history indices to dead lanes
         const unsigned need = __ballot_sync(kFull, !alive);
-        if (need) {
+        if (need && ((uint32_t)__popc(need) >= P.spawn_batch || need == kFull)) {
             if (w_next == w_end && !exhausted) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(P.work, (unsigned long long)P.chunk);

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
         __syncwarp();
         // ---------------- SPAWN (identical to the surface kernel)
         const unsigned need = __ballot_sync(kFull, !alive);
-        if (need) {
+        if (need && ((uint32_t)__popc(need) >= P.spawn_batch || need == kFull)) {
             if (w_next == w_end && !exhausted) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(P.work, (unsigned long long)P.chunk);
@@ -108,40 +108,47 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
 
         // ---------------- FLIGHT to the next tentative collision
         uint32_t fate = 0;
-        bool accepted = false;
+        bool accepted = false, moved = false;
         int mat = 0, g_eff = 0;
+        float xn = 0.f, inv_maj = 0.f;
         if (alive) {
             if (h_flight >= P.max_flights) {
                 fate = NRAPS_FATE_TRUNCATED;
             } else {
-                const float inv_maj = s_inv_maj[xsg * G + g];
-                float xn = fadd(x, fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), inv_maj));
+                inv_maj = s_inv_maj[xsg * G + g];
+                xn = fadd(x, fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), inv_maj));
                 ++h_flight;
-                while (xn < 0.0f || xn > len) { // albedo walls; rare
+                moved = true;
+                while (xn < 0.0f || xn > len) { // albedo walls; ~0.9 per history
                     const bool lo_wall = xn < 0.0f;
                     const float wall = lo_wall ? 0.0f : len, b = lo_wall ? P.boundl : P.boundr;
-                    if (!(b > 0.0f)) { fate = NRAPS_FATE_LEAKED; break; }
+                    if (!(b > 0.0f)) { fate = NRAPS_FATE_LEAKED; moved = false; break; }
                     const float rem = fsub(xn, wall);
                     mu = fmul(mu, -b);
                     xn = fadd(wall, fmul(rem, -b));
                     if (lo_wall ? (home_lo != 0) : (home_hi != N)) left = true;
                     ++h_refl;
                 }
-                if (!fate) {
-                    // cell containing xn: bucket guess, then exact correction against the edges
-                    int c = __float2int_rz(fmul(xn, P.inv_h));
-                    c = s_bucket[c < NB - 1 ? c : NB - 1];
-                    while (c < N - 1 && s_edges[c + 1] <= xn) ++c;
-                    while (c > 0 && s_edges[c] > xn) --c;
-                    cell = c;
-                    x = xn;
-                    left = left || cell < home_lo || cell >= home_hi;
-                    mat = s_matid[cell];
-                    g_eff = left ? g : xsg;
-                    score(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, inv_maj);
-                    accepted = pcg32_unit(rng, inc) < fmul(s_sigtr[mat + M * g_eff], inv_maj);
-                }
             }
+        }
+        __syncwarp(); // the lane that bounced off a wall rejoins before the common part (profiles/r1d: it ran twice)
+        if (moved) {
+            // cell containing xn: bucket guess (a bucket is no wider than a cell, so at most one step right),
+            // then an exact check against the edges with a rarely-taken repair path
+            int c = __float2int_rz(fmul(xn, P.inv_h));
+            c = s_bucket[c < NB - 1 ? c : NB - 1];
+            c += (c < N - 1 && s_edges[c + 1] <= xn) ? 1 : 0;
+            if (xn < s_edges[c] || (xn >= s_edges[c + 1] && c < N - 1)) {
+                while (c < N - 1 && s_edges[c + 1] <= xn) ++c;
+                while (c > 0 && s_edges[c] > xn) --c;
+            }
+            cell = c;
+            x = xn;
+            left = left || cell < home_lo || cell >= home_hi;
+            mat = s_matid[cell];
+            g_eff = left ? g : xsg;
+            score(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, inv_maj);
+            accepted = pcg32_unit(rng, inc) < fmul(s_sigtr[mat + M * g_eff], inv_maj);
         }
         __syncwarp();
 

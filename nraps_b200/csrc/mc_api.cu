@@ -103,6 +103,7 @@ struct nraps_mc_ctx {
     uint32_t NB = 0;
     float inv_h = 0.0f;
     bool woodcock = false;
+    uint32_t prepared = 0;
     ulonglong2 *d_jump = nullptr;
     unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
@@ -259,6 +260,11 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         if (rc != NRAPS_OK) return rc;
         CU(run_event_generation(P, c->ev, c->layout.total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
         return NRAPS_OK;
+    }
+    if (!(c->prepared & (1u << (trace ? 1 : 0)))) { // shared-memory opt-in, once per (kernel, trace) instantiation
+        CU(c->woodcock ? prepare_woodcock(c->layout.total, c->G, trace, c->bank_mode)
+                       : prepare_transport(c->layout.total, c->G, trace, c->bank_mode));
+        c->prepared |= 1u << (trace ? 1 : 0);
     }
     if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
     else CU(launch_transport(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
@@ -425,7 +431,6 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     ok(cudaMalloc((void **)&c->d_bank_sizes, c->generations * sizeof(unsigned long long)));
     ok(cudaMalloc((void **)&c->d_entropy, c->generations * sizeof(double)));
     ok(cudaMalloc((void **)&c->d_hist, N * sizeof(uint32_t)));
-    ok(woodcock ? prepare_woodcock(L.total) : prepare_transport(L.total));
     c->NB = NB; c->woodcock = woodcock;
     c->inv_h = NB ? (float)((double)NB / (double)p->right[N - 1]) : 0.0f;
     if (e != cudaSuccess) {

@@ -119,12 +119,12 @@ struct FinalizeParams {
 
 cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
 cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
-cudaError_t prepare_woodcock(uint32_t smem_bytes);
+cudaError_t prepare_woodcock(uint32_t smem_bytes, uint32_t G, bool trace, bool bank);
 cudaError_t run_event_generation(const TransportParams &p, const EventBank &b, uint32_t smem, int sm_count, cudaStream_t s, uint32_t *iters);
 cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s);
 cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
                                 double *entropy_out, unsigned long long *size_out, cudaStream_t s);
-cudaError_t prepare_transport(uint32_t smem_bytes);
+cudaError_t prepare_transport(uint32_t smem_bytes, uint32_t G, bool trace, bool bank);
 cudaError_t launch_finalize(const FinalizeParams &p, cudaStream_t s);
 cudaError_t launch_probe_logf(const float *x, float *out, uint32_t n, cudaStream_t s);
 cudaError_t launch_probe_div(const float *t, const float *mu, float *out_fast, float *out_ieee, uint32_t n, cudaStream_t s);

@@ -230,24 +230,25 @@ cudaError_t launch_g(const TransportParams &p, bool trace, bool bank, dim3 grid,
     return cudaGetLastError();
 }
 
-template <int TG> cudaError_t set_smem(uint32_t bytes)
+template <int TG> cudaError_t set_smem(uint32_t bytes, bool trace, bool bank)
 {
-    cudaError_t e;
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if ((e = cudaFuncSetAttribute(woodcock_kernel<TG, false, false>, attr, (int)bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(woodcock_kernel<TG, true, false>, attr, (int)bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(woodcock_kernel<TG, false, true>, attr, (int)bytes)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(woodcock_kernel<TG, true, true>, attr, (int)bytes);
+    if (bank) return trace ? cudaFuncSetAttribute(woodcock_kernel<TG, true, true>, attr, (int)bytes)
+                           : cudaFuncSetAttribute(woodcock_kernel<TG, false, true>, attr, (int)bytes);
+    return trace ? cudaFuncSetAttribute(woodcock_kernel<TG, true, false>, attr, (int)bytes)
+                 : cudaFuncSetAttribute(woodcock_kernel<TG, false, false>, attr, (int)bytes);
 }
 
 } // namespace
 
-cudaError_t prepare_woodcock(uint32_t smem_bytes)
+// opt in to > 48 KB dynamic shared memory for the one instantiation about to be launched
+cudaError_t prepare_woodcock(uint32_t smem_bytes, uint32_t G, bool trace, bool bank)
 {
-    cudaError_t e;
-    if ((e = set_smem<2>(smem_bytes)) != cudaSuccess) return e;
-    if ((e = set_smem<4>(smem_bytes)) != cudaSuccess) return e;
-    return set_smem<0>(smem_bytes);
+    switch (G) {
+    case 2: return set_smem<2>(smem_bytes, trace, bank);
+    case 4: return set_smem<4>(smem_bytes, trace, bank);
+    default: return set_smem<0>(smem_bytes, trace, bank);
+    }
 }
 
 cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)

@@ -413,3 +413,22 @@ def test_analytic_k_infinity_deck_a_on_gpu(kw):
     r = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=12, histories=1_000_000, skip=1, stale_xs=False, **kw)
     k = r.k[1:].astype(np.float64)
     assert abs(k.mean() - 1.26) < 4 * k.std(ddof=1) / np.sqrt(len(k)) + 2e-5, (kw, k.mean(), k.std(ddof=1))
+
+
+def test_nraps_driver_binary_writes_reference_csv_files(tmp_path):
+    """The C++ `nraps` driver (deck in, three CSV files out) is the drop-in for the reference binary's pipeline."""
+    import subprocess
+
+    from tests.util import DECKS, ROOT
+
+    exe = os.path.join(ROOT, "nraps_b200", "lib", "nraps")
+    out = subprocess.run([exe, DECKS["a"], "--out", str(tmp_path), "--generations", "5", "--histories", "30000", "--skip", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.startswith("running MC code\n")  # src/mc_code.rs:292
+    v, xs, dx, mesh, fuel = load_case("a")
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=5, histories=30000, skip=2, threads=8)
+    files = ho.csv_files(want.flux, want.assembly_average, want.fission_source, want.k, want.k_fund, mesh.mesh_right[-1], len(mesh), 5)
+    for name, text in files.items():
+        assert (tmp_path / name).read_text() == text, name

@@ -432,3 +432,28 @@ def test_nraps_driver_binary_writes_reference_csv_files(tmp_path):
     files = ho.csv_files(want.flux, want.assembly_average, want.fission_source, want.k, want.k_fund, mesh.mesh_right[-1], len(mesh), 5)
     for name, text in files.items():
         assert (tmp_path / name).read_text() == text, name
+
+
+# ---------------------------------------------------------------- shapes the shipped decks do not exercise
+@pytest.mark.parametrize("M,G,pins,mpfr,mpwr,bl,br", [
+    (2, 3, [1, 0, 1], 3, 2, 1.0, 1.0),              # generic-G kernel, fuel touching both walls, no moderator material
+    (3, 5, [2, 0, 2, 1, 2, 0, 2], 5, 4, 1.0, 0.0),  # five groups, vacuum on the right
+    (5, 8, [4, 0, 3, 1, 2, 0, 4], 4, 6, 0.7, 1.0),  # maximum G, five materials, albedo 0.7 on the left
+    (2, 2, [0], 1, 0, 1.0, 1.0),                    # one single cell: N = 1 (no water cells at all)
+    (3, 4, [2, 1, 2], 64, 2, 0.0, 0.0),             # one long fuel run (64 cells) between vacuum walls
+])
+@pytest.mark.parametrize("tracking", ["surface", "woodcock"])
+def test_synthetic_shapes_bit_exact(M, G, pins, mpfr, mpwr, bl, br, tracking):
+    from tests.util import synthetic_case
+
+    args = synthetic_case(M, G, pins, mpfr, mpwr, seed=M * 10 + G, boundl=bl, boundr=br)
+    for source in ("uniform_fuel", "fission_bank"):
+        got = nb.monte_carlo(*args, 1.0, generations=3, histories=30_000, skip=1, want_tally=True, tracking_mode=tracking,
+                             source_mode=source)
+        deck, m = oracle_inputs(*args)
+        want = orc.monte_carlo(deck, m, generations=3, histories=30_000, skip=1, threads=8, want_tally=True,
+                               tracking_mode=tracking, source_mode=source)
+        _assert_identical(got, want)
+        assert np.array_equal(got.bank_sizes, want.bank_sizes)
+        assert got.counters["reflections"] == want.counters["reflections"] or tracking == "surface"
+        assert got.counters["truncated"] == 0 and np.isfinite(got.k).all() and got.k[-1] > 0

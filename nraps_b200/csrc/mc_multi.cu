@@ -1,0 +1,138 @@
+// Single-process multi-GPU driver over the generation-level C ABI (include/nraps_multi.h).
+// One host thread per device; NCCL over NVLink for the per-generation exchange:
+//   tally:  ncclAllReduce(sum) on uint64[G*N + 8]   (mirrors the ordered thread join, src/mc_code.rs:331-338)
+//   bank :  ncclAllGather of counts, then of the padded local banks, compacted in rank order
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/nraps_multi.h"
+
+namespace {
+
+struct Rank {
+    int device = 0;
+    nraps_mc_ctx *ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    int rc = NRAPS_OK;
+};
+
+#define RK(call)                                  \
+    do {                                          \
+        const int rc_ = (call);                   \
+        if (rc_ != NRAPS_OK) { me.rc = rc_; return; } \
+    } while (0)
+#define RCU(call)                                                  \
+    do {                                                           \
+        if ((call) != cudaSuccess) { me.rc = NRAPS_ERR_CUDA; return; } \
+    } while (0)
+#define RNC(call)                                                   \
+    do {                                                            \
+        if ((call) != ncclSuccess) { me.rc = NRAPS_ERR_CUDA; return; } \
+    } while (0)
+
+void rank_main(Rank &me, int rank, int world, const nraps_problem *p, const nraps_options *o, nraps_results *r)
+{
+    RCU(cudaSetDevice(me.device));
+    cudaStream_t s = nullptr;
+    RCU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    void *tally = nullptr;
+    uint64_t words = 0;
+    RK(nraps_mc_tally_buffer(me.ctx, &tally, &words));
+    const uint64_t H = p->histories;
+    const uint64_t begin = H * (uint64_t)rank / (uint64_t)world, end = H * (uint64_t)(rank + 1) / (uint64_t)world;
+    const bool bank = o->source_mode == NRAPS_SOURCE_FISSION_BANK;
+
+    unsigned long long *d_counts = nullptr, *d_stage = nullptr, *d_gathered = nullptr, *d_global[2] = {nullptr, nullptr};
+    uint64_t stage_cap = 0, global_cap[2] = {0, 0};
+    std::vector<unsigned long long> counts((size_t)world);
+    if (bank) RCU(cudaMalloc((void **)&d_counts, (size_t)(world + 1) * sizeof(unsigned long long)));
+
+    for (uint64_t gen = 0; gen < p->generations; ++gen) {
+        RK(nraps_mc_transport(me.ctx, gen, begin, end - begin, s));
+        RNC(ncclAllReduce(tally, tally, words, ncclUint64, ncclSum, me.comm, s));
+        RK(nraps_mc_finalize_generation(me.ctx, gen, s));
+        if (!bank) continue;
+        RK(nraps_mc_bank_compact(me.ctx, gen, s));
+        void *local = nullptr;
+        uint64_t n_local = 0;
+        RK(nraps_mc_bank_local(me.ctx, &local, &n_local, s));
+        RCU(cudaMemcpyAsync(d_counts + world, &n_local, sizeof(n_local), cudaMemcpyHostToDevice, s));
+        RNC(ncclAllGather(d_counts + world, d_counts, 1, ncclUint64, me.comm, s));
+        RCU(cudaMemcpyAsync(counts.data(), d_counts, (size_t)world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        RCU(cudaStreamSynchronize(s));
+        unsigned long long max_n = 0, total = 0;
+        for (unsigned long long c : counts) { max_n = std::max(max_n, c); total += c; }
+        if (total == 0) { RK(nraps_mc_bank_set_source(me.ctx, gen, nullptr, 0, s)); continue; }
+        if (max_n > stage_cap) { // padded staging: NCCL all-gather wants equal contributions
+            cudaFree(d_stage); cudaFree(d_gathered);
+            RCU(cudaMalloc((void **)&d_stage, max_n * sizeof(unsigned long long)));
+            RCU(cudaMalloc((void **)&d_gathered, max_n * (size_t)world * sizeof(unsigned long long)));
+            stage_cap = max_n;
+        }
+        const int w = (int)(gen & 1u); // the bank read by generation gen+1 must outlive the next gather
+        if (total > global_cap[w]) {
+            cudaFree(d_global[w]);
+            RCU(cudaMalloc((void **)&d_global[w], total * sizeof(unsigned long long)));
+            global_cap[w] = total;
+        }
+        if (n_local) RCU(cudaMemcpyAsync(d_stage, local, n_local * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        RNC(ncclAllGather(d_stage, d_gathered, max_n, ncclUint64, me.comm, s));
+        unsigned long long off = 0;
+        for (int q = 0; q < world; ++q) { // rank order == canonical history order
+            if (counts[(size_t)q])
+                RCU(cudaMemcpyAsync(d_global[w] + off, d_gathered + (size_t)q * max_n, counts[(size_t)q] * sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToDevice, s));
+            off += counts[(size_t)q];
+        }
+        RK(nraps_mc_bank_set_source(me.ctx, gen, d_global[w], total, s));
+    }
+    if (rank == 0) RK(nraps_mc_fetch(me.ctx, r, s));
+    RCU(cudaStreamSynchronize(s));
+    cudaFree(d_counts); cudaFree(d_stage); cudaFree(d_gathered); cudaFree(d_global[0]); cudaFree(d_global[1]);
+    cudaStreamDestroy(s);
+}
+
+} // namespace
+
+extern "C" int nraps_mc_run_multi(const nraps_problem *p, const nraps_options *o, nraps_results *r, int32_t num_gpus,
+                                  const int32_t *devices)
+{
+    if (!p || !o || !r) return NRAPS_ERR_NULL;
+    if (num_gpus < 1) return NRAPS_ERR_OPTION;
+    if (num_gpus == 1 && !devices) return nraps_mc_run(p, o, r);
+    if (r->tally_fixed) return NRAPS_ERR_OPTION; // per-generation tally dumps are a single-GPU debugging aid
+
+    std::vector<Rank> ranks((size_t)num_gpus);
+    std::vector<int> devs((size_t)num_gpus);
+    for (int i = 0; i < num_gpus; ++i) devs[(size_t)i] = devices ? devices[i] : i;
+    int rc = NRAPS_OK;
+    for (int i = 0; i < num_gpus && rc == NRAPS_OK; ++i) {
+        nraps_options oo = *o;
+        oo.device = devs[(size_t)i];
+        oo.quiet = 1;
+        ranks[(size_t)i].device = devs[(size_t)i];
+        rc = nraps_mc_create(p, &oo, &ranks[(size_t)i].ctx);
+    }
+    std::vector<ncclComm_t> comms((size_t)num_gpus, nullptr);
+    if (rc == NRAPS_OK && ncclCommInitAll(comms.data(), num_gpus, devs.data()) != ncclSuccess) rc = NRAPS_ERR_CUDA;
+    if (rc == NRAPS_OK) {
+        if (!o->quiet) { std::printf("running MC code\n"); std::fflush(stdout); }
+        for (int i = 0; i < num_gpus; ++i) ranks[(size_t)i].comm = comms[(size_t)i];
+        std::vector<std::thread> threads;
+        for (int i = 0; i < num_gpus; ++i)
+            threads.emplace_back(rank_main, std::ref(ranks[(size_t)i]), i, num_gpus, p, o, r);
+        for (std::thread &t : threads) t.join();
+        for (const Rank &k : ranks)
+            if (k.rc != NRAPS_OK) rc = k.rc;
+    }
+    for (int i = 0; i < num_gpus; ++i) {
+        if (comms[(size_t)i]) ncclCommDestroy(comms[(size_t)i]);
+        if (ranks[(size_t)i].ctx) nraps_mc_destroy(ranks[(size_t)i].ctx);
+    }
+    return rc;
+}

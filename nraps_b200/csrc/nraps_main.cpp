@@ -3,7 +3,7 @@
 //   process_input -> mesh_gen -> monte_carlo -> plot_solution (three CSV files)
 // Usage: nraps [deck] [--out DIR] [--generations N] [--histories N] [--skip N]
 //              [--seed S --stream Q --stride T] [--device D] [--scatter single_xi|rust_pre182|rust_182]
-//              [--fix-stale-xs] [--quiet]
+//              [--fix-stale-xs] [--quiet] [--gpus N] [--tracking surface|woodcock] [--source uniform_fuel|fission_bank]
 // The deck defaults to ./TestCaseC.txt like the reference (src/process_input.rs:86).
 #include <chrono>
 #include <cstdio>
@@ -12,7 +12,10 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/nraps_host.h"
+#include "../../include/nraps_multi.h"
 
 int main(int argc, char **argv)
 {
@@ -20,6 +23,7 @@ int main(int argc, char **argv)
     nraps_options opt{};
     opt.stale_xs = 1;
     long long gens = -1, hist = -1, skip = -1;
+    int gpus = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&](const char *what) -> const char * {
@@ -36,6 +40,9 @@ int main(int argc, char **argv)
         else if (a == "--device") opt.device = std::atoi(next("--device"));
         else if (a == "--fix-stale-xs") opt.stale_xs = 0;
         else if (a == "--quiet") opt.quiet = 1;
+        else if (a == "--gpus") gpus = std::atoi(next("--gpus"));
+        else if (a == "--tracking") opt.tracking_mode = std::string(next("--tracking")) == "woodcock" ? NRAPS_TRACK_WOODCOCK : NRAPS_TRACK_SURFACE;
+        else if (a == "--source") opt.source_mode = std::string(next("--source")) == "fission_bank" ? NRAPS_SOURCE_FISSION_BANK : NRAPS_SOURCE_UNIFORM_FUEL;
         else if (a == "--scatter") {
             const std::string m = next("--scatter");
             opt.scatter_mode = m == "rust_pre182" ? NRAPS_SCATTER_RUST_PRE182 : m == "rust_182" ? NRAPS_SCATTER_RUST_182 : NRAPS_SCATTER_SINGLE_XI;
@@ -64,7 +71,14 @@ int main(int argc, char **argv)
     nraps_results res{};
     res.flux = flux.data(); res.assembly_average = avg.data(); res.fission_source = fis.data();
     res.k = k.data(); res.k_fund = kf.data();
-    rc = nraps_mc_run(&prob, &opt, &res);
+    if (gpus > 1) { // all GPUs of the box through libnraps_b200_nccl.so (loaded on demand: the core has no NCCL dependency)
+        void *h = dlopen("libnraps_b200_nccl.so", RTLD_NOW);
+        auto fn = h ? reinterpret_cast<decltype(&nraps_mc_run_multi)>(dlsym(h, "nraps_mc_run_multi")) : nullptr;
+        if (!fn) { std::fprintf(stderr, "--gpus %d needs libnraps_b200_nccl.so: %s\n", gpus, dlerror()); return 1; }
+        rc = fn(&prob, &opt, &res, gpus, nullptr);
+    } else {
+        rc = nraps_mc_run(&prob, &opt, &res);
+    }
     if (rc != NRAPS_OK) {
         std::fprintf(stderr, "monte_carlo: %s %s\n", nraps_strerror(rc), rc == NRAPS_ERR_CUDA ? nraps_last_cuda_error() : "");
         return 1;
@@ -76,7 +90,7 @@ int main(int argc, char **argv)
     const double total = (double)prob.histories * (double)prob.generations;
     std::printf("Run was completed in %lld milliseconds \n", (long long)(wall * 1e3)); // src/main.rs:366-369
     std::fprintf(stderr, "{\"k_fund\": %.7g, \"histories_per_s\": %.6g, \"device_s\": %.6g, \"collisions_per_history\": %.6g}\n",
-                 (double)kf[prob.generations - 1], total / res.seconds_device, res.seconds_device,
+                 (double)kf[prob.generations - 1], total / (res.seconds_device > 0 ? res.seconds_device : wall), res.seconds_device,
                  (double)res.counters[NRAPS_CT_COLLISIONS] / total);
     nraps_mesh_free(&mesh);
     nraps_deck_free(&deck);

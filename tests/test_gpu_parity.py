@@ -457,3 +457,27 @@ def test_synthetic_shapes_bit_exact(M, G, pins, mpfr, mpwr, bl, br, tracking):
         assert np.array_equal(got.bank_sizes, want.bank_sizes)
         assert got.counters["reflections"] == want.counters["reflections"] or tracking == "surface"
         assert got.counters["truncated"] == 0 and np.isfinite(got.k).all() and got.k[-1] > 0
+
+
+@pytest.mark.parametrize("extra", [[], ["--source", "fission_bank"], ["--tracking", "woodcock", "--source", "fission_bank"]])
+def test_native_nccl_driver_two_gpus_equals_one(tmp_path, extra):
+    """`nraps --gpus 2` (single process, one host thread per GPU, ncclAllReduce / ncclAllGather inside the C ABI
+    library) writes byte-identical CSV files to the single-GPU run."""
+    import subprocess
+
+    import torch
+
+    from tests.util import DECKS, ROOT
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    exe = os.path.join(ROOT, "nraps_b200", "lib", "nraps")
+    outs = []
+    for gpus in (1, 2):
+        d = tmp_path / f"g{gpus}"
+        d.mkdir()
+        run = subprocess.run([exe, DECKS["c"], "--out", str(d), "--generations", "4", "--histories", "60001", "--gpus", str(gpus)] + extra,
+                             capture_output=True, text=True, timeout=300)
+        assert run.returncode == 0, run.stderr
+        outs.append({n: (d / n).read_bytes() for n in ("k_eff.csv", "interface.csv", "vars.csv")})
+    assert outs[0] == outs[1]

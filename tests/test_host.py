@@ -172,3 +172,16 @@ def test_average_assembly_and_k_fund_match_oracle():
         orc.lib().oracle_k_fund(k.ctypes.data_as(fp), gens, skip, b.ctypes.data_as(fp))
         assert np.array_equal(bits(a), bits(b))
         assert np.all(a[:skip] == 0) and a[skip] == k[skip]
+
+
+def test_nccl_driver_library_exports_its_entry_point():
+    import ctypes
+
+    src = open(os.path.join(ROOT, "include", "nraps_multi.h")).read()
+    assert "nraps_mc_run_multi" in src
+    path = os.path.join(ROOT, "nraps_b200", "lib", "libnraps_b200_nccl.so")
+    try:
+        L = ctypes.CDLL(path)
+    except OSError as e:  # libnccl.so.2 not installed on this host
+        pytest.skip(str(e))
+    assert L.nraps_mc_run_multi(None, None, None, 2, None) == 1  # NRAPS_ERR_NULL before any CUDA / NCCL call

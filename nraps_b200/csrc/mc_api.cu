@@ -103,7 +103,7 @@ struct nraps_mc_ctx {
     uint32_t NB = 0;
     float inv_h = 0.0f;
     bool woodcock = false;
-    uint32_t prepared = 0;
+    uint32_t prepared = 0, big = 0;
     ulonglong2 *d_jump = nullptr;
     unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
@@ -239,7 +239,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
 
     TransportParams P{};
     P.edges = c->d_edges; P.runb = c->d_runb; P.matid = c->d_matid; P.fuel = c->d_fuel; P.xs = c->d_xs; P.jump = c->d_jump;
-    P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF; P.NB = c->NB; P.bucket = c->d_bucket; P.inv_h = c->inv_h;
+    P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF; P.NB = c->NB; P.bucket = c->d_bucket; P.inv_h = c->inv_h; P.big = c->big;
     P.boundl = c->boundl; P.boundr = c->boundr; P.dx_fuel = c->dx_fuel;
     // history (gen, y) owns the stream position (gen*H + y)*stride; the kernel adds the y part
     uint64_t jm, jp;
@@ -261,7 +261,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         CU(run_event_generation(P, c->ev, c->layout.total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
         return NRAPS_OK;
     }
-    if (!(c->prepared & (1u << (trace ? 1 : 0)))) { // shared-memory opt-in, once per (kernel, trace) instantiation
+    if (!c->big && !(c->prepared & (1u << (trace ? 1 : 0)))) { // shared-memory opt-in, once per (kernel, trace) instantiation
         CU(c->woodcock ? prepare_woodcock(c->layout.total, c->G, trace, c->bank_mode)
                        : prepare_transport(c->layout.total, c->G, trace, c->bank_mode));
         c->prepared |= 1u << (trace ? 1 : 0);
@@ -309,8 +309,11 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
         for (uint32_t i = 0; i < N; ++i) min_dx = std::min(min_dx, p->right[i] - p->left[i]);
         NB = (uint32_t)std::min(16384.0, std::max(1.0, std::ceil((double)p->right[N - 1] / (double)min_dx)));
     }
-    const SmemLayout L = make_layout(M, G, N, NF, NB);
-    if (L.total > kMaxSmem) return NRAPS_ERR_TOO_LARGE;
+    // a mesh too large for one SM's shared memory runs in BIG mode: tables through L1/L2, tally in global memory
+    SmemLayout L = make_layout(M, G, N, NF, NB, 0);
+    const uint32_t big = L.total > kMaxSmem ? 1u : 0u;
+    if (big) L = make_layout(M, G, N, NF, NB, 1);
+    if (L.total > kMaxSmem || (big && o->kernel_variant == NRAPS_KERNEL_EVENT)) return NRAPS_ERR_TOO_LARGE;
 
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -431,7 +434,7 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     ok(cudaMalloc((void **)&c->d_bank_sizes, c->generations * sizeof(unsigned long long)));
     ok(cudaMalloc((void **)&c->d_entropy, c->generations * sizeof(double)));
     ok(cudaMalloc((void **)&c->d_hist, N * sizeof(uint32_t)));
-    c->NB = NB; c->woodcock = woodcock;
+    c->NB = NB; c->woodcock = woodcock; c->big = big;
     c->inv_h = NB ? (float)((double)NB / (double)p->right[N - 1]) : 0.0f;
     if (e != cudaSuccess) {
         free_ctx(c);

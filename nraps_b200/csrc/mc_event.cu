@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(512) ev_advance(const TransportParams P, const
                 left = left || c < home_lo || c >= home_hi;
                 cell = c;
                 x = xn;
-                score(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, inv_maj);
+                score<false>(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, inv_maj, nullptr);
                 const int g_eff = left ? g : xsg;
                 accepted = pcg32_unit(rng, P.rng_inc) < fmul(T.sigtr[T.matid[cell] + M * g_eff], inv_maj);
             }

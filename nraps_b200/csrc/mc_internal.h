@@ -30,8 +30,11 @@ __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v
 // floats in the XS block: inv_sigtr | p_abs | chi_cdf | nusigf | sigtr [MG each] | scat_cdf [M*G^3] | inv_maj [G*G]
 __host__ __device__ inline uint32_t xs_floats(uint32_t M, uint32_t G) { return 5 * M * G + M * G * G * G + G * G; }
 
-__host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t NF, uint32_t NB)
+// big = 1: the mesh does not fit one SM's shared memory; only the jump table and the XS block are staged, the mesh
+// tables are read through L1/L2 and the tally goes straight to the global 64-bit bins (slower, any N <= 65535)
+__host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t NF, uint32_t NB, uint32_t big = 0)
 {
+    if (big) { N = 0; NF = 0; NB = 0; }
     SmemLayout L;
     uint32_t off = 0;
     L.jump = off;     off += 64 * 16;
@@ -57,7 +60,7 @@ struct TransportParams {
     const float *xs;
     const ulonglong2 *jump;
     const uint16_t *bucket;  // [NB] Woodcock position buckets (NB = 0 in surface mode)
-    uint32_t M, G, N, NF, NB;
+    uint32_t M, G, N, NF, NB, big;
     float boundl, boundr, dx_fuel, inv_h;
     uint64_t rng_state; // master stream advanced to history 0 of this generation
     uint64_t rng_inc;

@@ -28,15 +28,26 @@ static __device__ __forceinline__ float lds_f32(uint32_t saddr)
     return v;
 }
 
-// 64-bit fixed-point bin += score, as two u32 words with an explicit carry;
-// `a` is the shared address of the low word, the high word sits hi_off bytes above
-static __device__ __forceinline__ void score(uint32_t a, uint32_t hi_off, float v)
+// 64-bit fixed-point bin += score.  Shared-memory mode: two u32 words with an explicit carry, `ref` is the shared
+// address of the low word and the high word sits hi_off bytes above.  BIG mode (mesh too large for shared
+// memory): `ref` is the bin index and the add goes to the global 64-bit bin directly.
+template <bool BIG>
+static __device__ __forceinline__ void score(uint32_t ref, uint32_t hi_off, float v, unsigned long long *global_bins)
 {
     const unsigned long long fx = __float2ull_rz(fmul(v, kTallyScale));
+    if (BIG) {
+        atomicAdd(global_bins + ref, fx);
+        return;
+    }
     const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
-    const uint32_t old = atoms_add(a, l);
+    const uint32_t old = atoms_add(ref, l);
     const bool carry = (uint32_t)(old + l) < l;
-    if (carry | (h != 0u)) reds_add(a + hi_off, h + (carry ? 1u : 0u));
+    if (carry | (h != 0u)) reds_add(ref + hi_off, h + (carry ? 1u : 0u));
+}
+// tally reference of bin `bin`: shared byte address or plain index
+template <bool BIG> static __device__ __forceinline__ uint32_t tally_ref(uint32_t lo_base, int bin)
+{
+    return BIG ? (uint32_t)bin : lo_base + 4u * (uint32_t)bin;
 }
 
 template <int TG> static __device__ __forceinline__ int search_cdf(const float *cdf, int G, float v)
@@ -105,6 +116,18 @@ struct SmemView {
 static __device__ __forceinline__ SmemView load_block_tables(unsigned char *smem_raw, const TransportParams &P, const SmemLayout &L)
 {
     SmemView S;
+    if (P.big) { // mesh tables stay in global memory (read-only, L1/L2 cached); stage only the small tables
+        S.lo = S.hi = nullptr;
+        S.edges = const_cast<float *>(P.edges); S.runb = const_cast<uint32_t *>(P.runb);
+        S.fuel = const_cast<uint16_t *>(P.fuel); S.matid = const_cast<uint8_t *>(P.matid);
+        S.bucket = const_cast<uint16_t *>(P.bucket);
+        S.jump = reinterpret_cast<ulonglong2 *>(smem_raw + L.jump);
+        S.xs = reinterpret_cast<float *>(smem_raw + L.xs);
+        for (int i = threadIdx.x; i < (int)xs_floats(P.M, P.G); i += blockDim.x) S.xs[i] = P.xs[i];
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) S.jump[i] = P.jump[i];
+        __syncthreads();
+        return S;
+    }
     S.lo = reinterpret_cast<uint32_t *>(smem_raw + L.tally_lo);
     S.hi = reinterpret_cast<uint32_t *>(smem_raw + L.tally_hi);
     S.edges = reinterpret_cast<float *>(smem_raw + L.edges);
@@ -132,7 +155,7 @@ static __device__ __forceinline__ void flush_block(const SmemView &S, const Tran
 {
     const int tid = threadIdx.x, nthr = blockDim.x, GN = (int)(P.G * P.N);
     __syncthreads();
-    for (int i = tid; i < GN; i += nthr) {
+    for (int i = tid; i < GN && !P.big; i += nthr) {
         const unsigned long long v = ((unsigned long long)S.hi[i] << 32) + S.lo[i];
         if (v) atomicAdd(&P.tally[i], v);
     }

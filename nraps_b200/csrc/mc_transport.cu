@@ -30,13 +30,13 @@ namespace {
 
 enum { EV_NONE = 0, EV_COLLIDE = 1, EV_MATCHANGE = 2 };
 
-template <int TG, bool TRACE, bool BANK>
+template <int TG, bool TRACE, bool BANK, bool BIG>
 __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G;
     const int M = (int)P.M, N = (int)P.N;
-    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB);
+    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG);
 
     const SmemView S = load_block_tables(smem_raw, P, L);
     uint32_t *s_lo = S.lo;
@@ -52,9 +52,11 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     // fission_bank mode: sites are banked with weight nu*Sigma_f * inv_sigtr / k_prev; an empty bank => uniform source
     const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
     const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
-    const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(s_lo);
+    const uint32_t lo_base = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(s_lo);
     const uint32_t hi_off = L.tally_hi - L.tally_lo;
-    const uint32_t edges_base = (uint32_t)__cvta_generic_to_shared(s_edges);
+    // edge reference: shared byte address (running pointer of the walk) or, in BIG mode, the edge index
+    const uint32_t edges_base = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(s_edges);
+    constexpr int kStep = BIG ? 1 : 4;
 
     const unsigned lane = tid & 31;
     const uint64_t inc = P.rng_inc;
@@ -151,19 +153,19 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 int dir = 2 * fwd - 1;
                 int wall = fwd ? N - 1 : 0;
                 int run_exit = fwd ? run_hi : run_lo - 1;
-                uint32_t e_addr = edges_base + 4u * (uint32_t)(cell + fwd); // edge ahead of the neutron
-                uint32_t t_addr = lo_base + 4u * (uint32_t)(g * N + cell);  // low word of tally[g][cell]
+                uint32_t e_addr = edges_base + (uint32_t)(kStep * (cell + fwd)); // edge ahead of the neutron
+                uint32_t t_addr = tally_ref<BIG>(lo_base, g * N + cell);         // tally[g][cell]
                 bool cont;
                 do {
                     end = fadd(x, ds);
-                    const float edge = lds_f32(e_addr);
+                    const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
                     const float t = fsub(x, edge);
                     crossed = fabsf(fsub(end, x)) > fabsf(t); // |edge - x| == |x - edge| exactly
                     cont = false;
                     if (cell == wall) { // domain boundary cell: src/mc_code.rs:159-170
                         const bool beyond = fwd ? (end > edge) : (edge > end);
                         if (beyond) {
-                            score(t_addr, hi_off, fabsf(fdiv(t, mu)));
+                            score<BIG>(t_addr, hi_off, fabsf(fdiv(t, mu)), P.tally);
                             const float b = fwd ? P.boundr : P.boundl;
                             crossed = false;
                             if (b > 0.0f) { // hit_boundary
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                                 dir = 2 * fwd - 1;
                                 wall = fwd ? N - 1 : 0;
                                 run_exit = fwd ? run_hi : run_lo - 1;
-                                e_addr = edges_base + 4u * (uint32_t)(cell + fwd);
+                                e_addr = edges_base + (uint32_t)(kStep * (cell + fwd));
                                 if (TRACE) ++h_refl;
                                 cont = true;
                             } else {
@@ -184,12 +186,12 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                         }
                     }
                     if (crossed) { // cross_mesh, src/mc_code.rs:171-181
-                        score(t_addr, hi_off, fabsf(fast_div(t, rc)));
+                        score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
                         ds = fadd(ds, t);
                         x = edge;
                         cell += dir;
-                        e_addr += 4 * dir;
-                        t_addr += 4 * dir;
+                        e_addr += kStep * dir;
+                        t_addr += kStep * dir;
                         if (TRACE) ++h_cross;
                         cont = cell != run_exit;
                     }
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
 
         // ---------------- COLLIDE / material change
         if (ev == EV_COLLIDE) {
-            score(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, fabsf(fast_div(fsub(x, end), rc)));
+            score<BIG>(tally_ref<BIG>(lo_base, g * N + cell), hi_off, fabsf(fast_div(fsub(x, end), rc)), P.tally);
             ++h_coll;
             const int xs = mat + M * xsg; // stale group index, src/mc_code.rs:147
             const float xi_int = pcg32_unit(rng, inc);
@@ -275,31 +277,37 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     flush_block(S, P, vals);
 }
 
+template <int TG, bool BIG>
+cudaError_t launch_gb(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
+{
+    if (bank) {
+        if (trace) transport_kernel<TG, true, true, BIG><<<grid, block, smem, s>>>(p);
+        else transport_kernel<TG, false, true, BIG><<<grid, block, smem, s>>>(p);
+    } else {
+        if (trace) transport_kernel<TG, true, false, BIG><<<grid, block, smem, s>>>(p);
+        else transport_kernel<TG, false, false, BIG><<<grid, block, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
 template <int TG>
 cudaError_t launch_g(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
 {
-    if (bank) {
-        if (trace) transport_kernel<TG, true, true><<<grid, block, smem, s>>>(p);
-        else transport_kernel<TG, false, true><<<grid, block, smem, s>>>(p);
-    } else {
-        if (trace) transport_kernel<TG, true, false><<<grid, block, smem, s>>>(p);
-        else transport_kernel<TG, false, false><<<grid, block, smem, s>>>(p);
-    }
-    return cudaGetLastError();
+    return p.big ? launch_gb<TG, true>(p, trace, bank, grid, block, smem, s) : launch_gb<TG, false>(p, trace, bank, grid, block, smem, s);
 }
 
 template <int TG> cudaError_t set_smem(uint32_t bytes, bool trace, bool bank)
 {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (bank) return trace ? cudaFuncSetAttribute(transport_kernel<TG, true, true>, attr, (int)bytes)
-                           : cudaFuncSetAttribute(transport_kernel<TG, false, true>, attr, (int)bytes);
-    return trace ? cudaFuncSetAttribute(transport_kernel<TG, true, false>, attr, (int)bytes)
-                 : cudaFuncSetAttribute(transport_kernel<TG, false, false>, attr, (int)bytes);
+    if (bank) return trace ? cudaFuncSetAttribute(transport_kernel<TG, true, true, false>, attr, (int)bytes)
+                           : cudaFuncSetAttribute(transport_kernel<TG, false, true, false>, attr, (int)bytes);
+    return trace ? cudaFuncSetAttribute(transport_kernel<TG, true, false, false>, attr, (int)bytes)
+                 : cudaFuncSetAttribute(transport_kernel<TG, false, false, false>, attr, (int)bytes);
 }
 
 } // namespace
 
-// opt in to > 48 KB dynamic shared memory for the one instantiation about to be launched
+// opt in to > 48 KB dynamic shared memory for the one instantiation about to be launched (BIG mode needs < 48 KB)
 cudaError_t prepare_transport(uint32_t smem_bytes, uint32_t G, bool trace, bool bank)
 {
     switch (G) {

@@ -18,13 +18,13 @@ namespace nraps {
 
 namespace {
 
-template <int TG, bool TRACE, bool BANK>
+template <int TG, bool TRACE, bool BANK, bool BIG>
 __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G;
     const int M = (int)P.M, N = (int)P.N, NB = (int)P.NB;
-    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB);
+    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG);
     const SmemView S = load_block_tables(smem_raw, P, L);
     const float *s_edges = S.edges, *s_xs = S.xs;
     const uint32_t *s_runb = S.runb;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
                 *s_sigtr = s_xs + 4 * MG, *s_scat = s_xs + 5 * MG, *s_inv_maj = s_xs + 5 * MG + MG * G * G;
     const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
     const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
-    const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(S.lo);
+    const uint32_t lo_base = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(S.lo);
     const uint32_t hi_off = L.tally_hi - L.tally_lo;
     const float len = s_edges[N];
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
             left = left || cell < home_lo || cell >= home_hi;
             mat = s_matid[cell];
             g_eff = left ? g : xsg;
-            score(lo_base + 4u * (uint32_t)(g * N + cell), hi_off, inv_maj);
+            score<BIG>(tally_ref<BIG>(lo_base, g * N + cell), hi_off, inv_maj, P.tally);
             accepted = pcg32_unit(rng, inc) < fmul(s_sigtr[mat + M * g_eff], inv_maj);
         }
         __syncwarp();
@@ -217,31 +217,36 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
     flush_block(S, P, vals);
 }
 
+template <int TG, bool BIG>
+cudaError_t launch_gb(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
+{
+    if (bank) {
+        if (trace) woodcock_kernel<TG, true, true, BIG><<<grid, block, smem, s>>>(p);
+        else woodcock_kernel<TG, false, true, BIG><<<grid, block, smem, s>>>(p);
+    } else {
+        if (trace) woodcock_kernel<TG, true, false, BIG><<<grid, block, smem, s>>>(p);
+        else woodcock_kernel<TG, false, false, BIG><<<grid, block, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
 template <int TG>
 cudaError_t launch_g(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
 {
-    if (bank) {
-        if (trace) woodcock_kernel<TG, true, true><<<grid, block, smem, s>>>(p);
-        else woodcock_kernel<TG, false, true><<<grid, block, smem, s>>>(p);
-    } else {
-        if (trace) woodcock_kernel<TG, true, false><<<grid, block, smem, s>>>(p);
-        else woodcock_kernel<TG, false, false><<<grid, block, smem, s>>>(p);
-    }
-    return cudaGetLastError();
+    return p.big ? launch_gb<TG, true>(p, trace, bank, grid, block, smem, s) : launch_gb<TG, false>(p, trace, bank, grid, block, smem, s);
 }
 
 template <int TG> cudaError_t set_smem(uint32_t bytes, bool trace, bool bank)
 {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (bank) return trace ? cudaFuncSetAttribute(woodcock_kernel<TG, true, true>, attr, (int)bytes)
-                           : cudaFuncSetAttribute(woodcock_kernel<TG, false, true>, attr, (int)bytes);
-    return trace ? cudaFuncSetAttribute(woodcock_kernel<TG, true, false>, attr, (int)bytes)
-                 : cudaFuncSetAttribute(woodcock_kernel<TG, false, false>, attr, (int)bytes);
+    if (bank) return trace ? cudaFuncSetAttribute(woodcock_kernel<TG, true, true, false>, attr, (int)bytes)
+                           : cudaFuncSetAttribute(woodcock_kernel<TG, false, true, false>, attr, (int)bytes);
+    return trace ? cudaFuncSetAttribute(woodcock_kernel<TG, true, false, false>, attr, (int)bytes)
+                 : cudaFuncSetAttribute(woodcock_kernel<TG, false, false, false>, attr, (int)bytes);
 }
 
 } // namespace
 
-// opt in to > 48 KB dynamic shared memory for the one instantiation about to be launched
 cudaError_t prepare_woodcock(uint32_t smem_bytes, uint32_t G, bool trace, bool bank)
 {
     switch (G) {

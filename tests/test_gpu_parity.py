@@ -481,3 +481,23 @@ def test_native_nccl_driver_two_gpus_equals_one(tmp_path, extra):
         assert run.returncode == 0, run.stderr
         outs.append({n: (d / n).read_bytes() for n in ("k_eff.csv", "interface.csv", "vars.csv")})
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("tracking", ["surface", "woodcock"])
+def test_mesh_larger_than_shared_memory_bit_exact(tracking):
+    """N = 8160 cells x 4 groups needs 261 KB of tally bins: more than one SM's shared memory.  The kernels then
+    read the mesh through L1/L2 and score straight into the global 64-bit bins (BIG mode); results are unchanged."""
+    v, xs, dx, mesh, fuel = load_case("c", mpfr=160, mpwr=80)
+    assert len(mesh) == 8160
+    for source in ("uniform_fuel", "fission_bank"):
+        got = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=20_000, skip=1, want_tally=True,
+                             tracking_mode=tracking, source_mode=source)
+        deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+        want = orc.monte_carlo(deck, m, generations=2, histories=20_000, skip=1, threads=8, want_tally=True,
+                               tracking_mode=tracking, source_mode=source)
+        _assert_identical(got, want)
+    with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1, tracking_mode=tracking) as ctx:
+        assert ctx.launch_info()["smem_bytes"] < 48 * 1024
+    with pytest.raises(_lib.NrapsError) as e:  # the event pipeline keeps its tally in shared memory only
+        nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1, tracking_mode="woodcock", kernel_variant="event")
+    assert e.value.code == 5

@@ -41,8 +41,9 @@ static __device__ __forceinline__ void score(uint32_t ref, uint32_t hi_off, floa
     }
     const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
     const uint32_t old = atoms_add(ref, l);
-    const bool carry = (uint32_t)(old + l) < l;
-    if (carry | (h != 0u)) reds_add(ref + hi_off, h + (carry ? 1u : 0u));
+    // high word += h + carry, as one predicated reduction (no branch, so no reconvergence barrier in the walk loop)
+    const uint32_t add_hi = h + ((uint32_t)(old + l) < l ? 1u : 0u);
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], %1; }" ::"r"(ref + hi_off), "r"(add_hi) : "memory");
 }
 // tally reference of bin `bin`: shared byte address or plain index
 template <bool BIG> static __device__ __forceinline__ uint32_t tally_ref(uint32_t lo_base, int bin)

@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
         int ev = EV_NONE;
         float end = 0.f;
         Recip rc{1.f, 1.f};
-        bool crossed = false;
         if (alive) {
             if (h_flight >= P.max_flights) {
                 fate = NRAPS_FATE_TRUNCATED;
@@ -155,48 +154,42 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 int run_exit = fwd ? run_hi : run_lo - 1;
                 uint32_t e_addr = edges_base + (uint32_t)(kStep * (cell + fwd)); // edge ahead of the neutron
                 uint32_t t_addr = tally_ref<BIG>(lo_base, g * N + cell);         // tally[g][cell]
-                bool cont;
-                do {
+                for (;;) {
                     end = fadd(x, ds);
                     const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
                     const float t = fsub(x, edge);
-                    crossed = fabsf(fsub(end, x)) > fabsf(t); // |edge - x| == |x - edge| exactly
-                    cont = false;
                     if (cell == wall) { // domain boundary cell: src/mc_code.rs:159-170
                         const bool beyond = fwd ? (end > edge) : (edge > end);
                         if (beyond) {
                             score<BIG>(t_addr, hi_off, fabsf(fdiv(t, mu)), P.tally);
                             const float b = fwd ? P.boundr : P.boundl;
-                            crossed = false;
-                            if (b > 0.0f) { // hit_boundary
-                                mu = fmul(mu, -b);
-                                ds = fmul(fadd(ds, t), -b);
-                                x = edge;
-                                rc = make_recip(mu);
-                                fwd = mu >= 0.0f ? 1 : 0;
-                                dir = 2 * fwd - 1;
-                                wall = fwd ? N - 1 : 0;
-                                run_exit = fwd ? run_hi : run_lo - 1;
-                                e_addr = edges_base + (uint32_t)(kStep * (cell + fwd));
-                                if (TRACE) ++h_refl;
-                                cont = true;
-                            } else {
-                                fate = NRAPS_FATE_LEAKED;
-                            }
+                            if (!(b > 0.0f)) { fate = NRAPS_FATE_LEAKED; break; }
+                            mu = fmul(mu, -b); // hit_boundary
+                            ds = fmul(fadd(ds, t), -b);
+                            x = edge;
+                            rc = make_recip(mu);
+                            fwd = mu >= 0.0f ? 1 : 0;
+                            dir = 2 * fwd - 1;
+                            wall = fwd ? N - 1 : 0;
+                            run_exit = fwd ? run_hi : run_lo - 1;
+                            e_addr = edges_base + (uint32_t)(kStep * (cell + fwd));
+                            if (TRACE) ++h_refl;
+                            continue;
                         }
                     }
-                    if (crossed) { // cross_mesh, src/mc_code.rs:171-181
-                        score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
-                        ds = fadd(ds, t);
-                        x = edge;
-                        cell += dir;
-                        e_addr += kStep * dir;
-                        t_addr += kStep * dir;
-                        if (TRACE) ++h_cross;
-                        cont = cell != run_exit;
-                    }
-                } while (cont);
-                if (!fate) ev = crossed ? EV_MATCHANGE : EV_COLLIDE;
+                    if (!(fabsf(fsub(end, x)) > fabsf(t))) break; // collision at `end` (|edge - x| == |x - edge| exactly)
+                    // cross_mesh, src/mc_code.rs:171-181
+                    score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
+                    ds = fadd(ds, t);
+                    x = edge;
+                    cell += dir;
+                    e_addr += kStep * dir;
+                    t_addr += kStep * dir;
+                    if (TRACE) ++h_cross;
+                    if (cell == run_exit) break; // left the material run
+                }
+                // a collision always happens strictly inside the run, so the exit cell tells the two ways out apart
+                if (!fate) ev = (cell == run_exit) ? EV_MATCHANGE : EV_COLLIDE;
             }
         }
         __syncwarp();

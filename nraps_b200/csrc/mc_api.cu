@@ -109,6 +109,8 @@ struct nraps_mc_ctx {
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
     uint32_t *d_trace = nullptr;
     uint64_t trace_cap = 0;
+    uint4 *d_source = nullptr; // born neutrons of the current shard (source_kernel -> transport kernels)
+    uint64_t source_cap = 0;
 
     // fission_bank source mode
     bool bank_mode = false;
@@ -254,6 +256,16 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
     P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
+    if (c->opt.kernel_variant != NRAPS_KERNEL_EVENT) { // births first, every lane busy; the transport lanes adopt them
+        if (count > c->source_cap) {
+            CU(cudaFree(c->d_source));
+            c->d_source = nullptr; c->source_cap = 0;
+            CU(cudaMalloc((void **)&c->d_source, count * 2 * sizeof(uint4)));
+            c->source_cap = count;
+        }
+        P.source = c->d_source;
+        CU(launch_source(P, c->bank_mode, c->d_source, s));
+    }
     if (c->opt.kernel_variant == NRAPS_KERNEL_EVENT) {
         if (trace) return NRAPS_ERR_OPTION;
         int rc = ensure_event_bank(c, count);

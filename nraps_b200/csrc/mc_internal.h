@@ -60,6 +60,7 @@ struct TransportParams {
     const float *xs;
     const ulonglong2 *jump;
     const uint16_t *bucket;  // [NB] Woodcock position buckets (NB = 0 in surface mode)
+    const uint4 *source;     // [hist_end-hist_begin][2] born neutrons written by source_kernel
     uint32_t M, G, N, NF, NB, big;
     float boundl, boundr, dx_fuel, inv_h;
     uint64_t rng_state; // master stream advanced to history 0 of this generation
@@ -121,6 +122,7 @@ struct FinalizeParams {
 };
 
 cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
+cudaError_t launch_source(const TransportParams &p, bool bank, uint4 *out, cudaStream_t s);
 cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
 cudaError_t prepare_woodcock(uint32_t smem_bytes, uint32_t G, bool trace, bool bank);
 cudaError_t run_event_generation(const TransportParams &p, const EventBank &b, uint32_t smem, int sm_count, cudaStream_t s, uint32_t *iters);

@@ -64,6 +64,24 @@ template <int TG> static __device__ __forceinline__ int search_cdf(const float *
     return lower_bound_clamped<TG>(cdf, G, v);
 }
 
+template <int TG> static __device__ __forceinline__ int search_cdf_global(const float *cdf, int G, float v)
+{
+    float c[8];
+    const int n = TG ? TG : G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = j < n ? __ldg(cdf + j) : 0.0f;
+    int lo = 0, hi = n; // partition_point(|x| x < v).min(n - 1), same probes as lower_bound_clamped
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        float cm = c[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) cm = (j == mid) ? c[j] : cm;
+        if (cm < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo < n - 1 ? lo : n - 1;
+}
+
 template <int TG>
 static __device__ __forceinline__ int sample_group(const float *cdf, int G, int mode, uint64_t &rng, uint64_t inc)
 {

@@ -1,0 +1,76 @@
+// Source kernel: every history of the shard is born here, with all 32 lanes of a warp busy, instead of inside the
+// persistent transport kernels where a neutron dies on one lane at a time (ncu: the single-lane spawn path was 6 %
+// of the issue slots of the surface kernel and 16 % of the Woodcock kernel, profiles/r1d, r1g).
+//
+// Replaces spawn_neutron + energy (src/mc_code.rs:7-53, 228-230); draw order cell, position, mu, chi (:46-51), or
+// site index, mu, chi in fission_bank mode.  Each thread takes a run of consecutive histories so that only the
+// first needs the full PCG32 jump; the next ones are one affine map (stride draws) further.  Output: one 32-byte
+// record per history {x, mu, cell | g << 16, -, rng state, -}, read back by the lane that adopts the history.
+#include "mc_lane.cuh"
+
+namespace nraps {
+
+namespace {
+
+constexpr int kRun = 8; // consecutive histories per thread
+
+template <int TG, bool BANK>
+__global__ void __launch_bounds__(256) source_kernel(const TransportParams P, uint4 *out)
+{
+    __shared__ ulonglong2 s_jump[64];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_jump[i] = P.jump[i];
+    __syncthreads();
+    const int G = TG ? TG : (int)P.G, MG = (int)P.M * G;
+    const float *chi = P.xs + 2 * MG;
+    const uint64_t n = P.hist_end - P.hist_begin;
+    const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
+    const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRun;
+    if (first >= n) return;
+    uint64_t base = jump_ahead(P.rng_state, P.hist_begin + first, s_jump);
+    const ulonglong2 J1 = s_jump[0];
+    const uint64_t last = first + kRun < n ? first + kRun : n;
+    for (uint64_t i = first; i < last; ++i) {
+        uint64_t rng = base;
+        base = J1.x * base + J1.y; // stream of the next history
+        const uint32_t u = pcg32_next(rng, P.rng_inc);
+        int cell;
+        float x, mu;
+        if (BANK && src_count) {
+            const unsigned long long site = __ldg(P.src_bank + (((unsigned long long)u * src_count) >> 32));
+            cell = (int)(site >> 32);
+            x = __uint_as_float((uint32_t)site);
+            mu = fsub(fmul(2.0f, pcg32_unit(rng, P.rng_inc)), 1.0f);
+        } else {
+            cell = __ldg(P.fuel + __umulhi(u, P.NF));
+            const float xi_pos = pcg32_unit(rng, P.rng_inc);
+            mu = fsub(fmul(2.0f, pcg32_unit(rng, P.rng_inc)), 1.0f);
+            x = fadd(__ldg(P.edges + cell), fmul(xi_pos, P.dx_fuel));
+        }
+        const int g = search_cdf_global<TG>(chi + __ldg(P.matid + cell) * G, G, pcg32_unit(rng, P.rng_inc));
+        out[2 * i] = make_uint4(__float_as_uint(x), __float_as_uint(mu), (uint32_t)cell | ((uint32_t)g << 16), 0u);
+        out[2 * i + 1] = make_uint4((uint32_t)rng, (uint32_t)(rng >> 32), 0u, 0u);
+    }
+}
+
+template <int TG> cudaError_t launch_g(const TransportParams &p, bool bank, uint4 *out, cudaStream_t s)
+{
+    const uint64_t n = p.hist_end - p.hist_begin;
+    const unsigned blocks = (unsigned)((n + 256ull * kRun - 1) / (256ull * kRun));
+    if (!blocks) return cudaSuccess;
+    if (bank) source_kernel<TG, true><<<blocks, 256, 0, s>>>(p, out);
+    else source_kernel<TG, false><<<blocks, 256, 0, s>>>(p, out);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t launch_source(const TransportParams &p, bool bank, uint4 *out, cudaStream_t s)
+{
+    switch (p.G) {
+    case 2: return launch_g<2>(p, bank, out, s);
+    case 4: return launch_g<4>(p, bank, out, s);
+    default: return launch_g<0>(p, bank, out, s);
+    }
+}
+
+} // namespace nraps

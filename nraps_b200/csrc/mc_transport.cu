@@ -42,16 +42,13 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     uint32_t *s_lo = S.lo;
     const float *s_edges = S.edges, *s_xs = S.xs;
     const uint32_t *s_runb = S.runb;
-    const ulonglong2 *s_jump = S.jump;
-    const uint16_t *s_fuel = S.fuel;
     const uint8_t *s_matid = S.matid;
     const int tid = threadIdx.x;
     const int MG = M * G;
-    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_chi = s_xs + 2 * MG, *s_nusigf = s_xs + 3 * MG,
+    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_nusigf = s_xs + 3 * MG,
                 *s_scat = s_xs + 5 * MG;
     // fission_bank mode: sites are banked with weight nu*Sigma_f * inv_sigtr / k_prev; an empty bank => uniform source
     const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
-    const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
     const uint32_t lo_base = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(s_lo);
     const uint32_t hi_off = L.tally_hi - L.tally_lo;
     // edge reference: shared byte address (running pointer of the walk) or, in BIG mode, the edge index
@@ -63,7 +60,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
 
     // warp-uniform cursor over the chunk of history indices this warp owns, and
     // the master stream positioned at history w_next
-    uint64_t w_next = 0, w_end = 0, w_state = 0;
+    uint64_t w_next = 0, w_end = 0;
     bool exhausted = false;
 
     // lane state: one neutron
@@ -88,7 +85,6 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 else {
                     w_next = b;
                     w_end = (b + P.chunk < P.hist_end) ? b + P.chunk : P.hist_end;
-                    w_state = jump_ahead(P.rng_state, b, s_jump); // once per chunk, warp-uniform
                 }
             }
             const uint32_t avail = (uint32_t)(w_end - w_next);
@@ -96,26 +92,15 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 const uint32_t rank = __popc(need & ((1u << lane) - 1u));
                 if (!alive && rank < avail) {
                     y = w_next + rank;
-                    // per-history stream = master advanced by y*stride draws; jump maps commute, so
-                    // start from the chunk cursor and add the (small) rank
-                    rng = jump_ahead(w_state, rank, s_jump);
-                    const uint32_t u = pcg32_next(rng, inc);
-                    if (BANK && src_count) {
-                        // fission_bank source: site index, mu, chi (the site carries position and cell)
-                        const unsigned long long site = __ldg(P.src_bank + (((unsigned long long)u * src_count) >> 32));
-                        cell = (int)(site >> 32);
-                        x = __uint_as_float((uint32_t)site);
-                        mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
-                    } else {
-                        // draw order cell, position, mu, chi (src/mc_code.rs:46-51)
-                        cell = s_fuel[__umulhi(u, P.NF)];
-                        const float xi_pos = pcg32_unit(rng, inc);
-                        mu = fsub(fmul(2.0f, pcg32_unit(rng, inc)), 1.0f);
-                        x = fadd(s_edges[cell], fmul(xi_pos, P.dx_fuel));
-                    }
-                    const float xi_chi = pcg32_unit(rng, inc);
+                    // adopt the neutron source_kernel gave birth to (mc_source.cu)
+                    const uint4 *rec = P.source + 2 * (y - P.hist_begin);
+                    const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+                    x = __uint_as_float(r0.x);
+                    mu = __uint_as_float(r0.y);
+                    cell = (int)(r0.z & 0xffffu);
+                    g = (int)(r0.z >> 16);
+                    rng = (uint64_t)r1.x | ((uint64_t)r1.y << 32);
                     mat = s_matid[cell];
-                    g = search_cdf<TG>(s_chi + mat * G, G, xi_chi);
                     xsg = g;
                     h_bank = 0;
                     const uint32_t rb = s_runb[cell];
@@ -127,7 +112,6 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 const uint32_t want = __popc(need);
                 const uint32_t took = want < avail ? want : avail;
                 w_next += took;
-                w_state = jump_ahead(w_state, took, s_jump);
             } else if (need == kFull) {
                 break; // no work left anywhere and every lane is dead
             }

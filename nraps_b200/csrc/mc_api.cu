@@ -176,7 +176,7 @@ void free_ctx(nraps_mc_ctx *c)
     cudaFree(c->d_runb); cudaFree(c->d_matid); cudaFree(c->d_fuel); cudaFree(c->d_jump); cudaFree(c->d_bucket);
     cudaFree(c->d_tally_own); cudaFree(c->d_work); cudaFree(c->d_counters_total);
     cudaFree(c->d_terms); cudaFree(c->d_res_flux); cudaFree(c->d_res_fission); cudaFree(c->d_k_hist); cudaFree(c->d_k_cur);
-    cudaFree(c->d_trace);
+    cudaFree(c->d_trace); cudaFree(c->d_source);
     cudaFree(c->d_slots); cudaFree(c->d_block_sums); cudaFree(c->d_dense[0]); cudaFree(c->d_dense[1]);
     for (EventHalf &h : c->ev.half) { cudaFree(h.x); cudaFree(h.mu); cudaFree(h.pack); cudaFree(h.cnt); cudaFree(h.ccnt); cudaFree(h.rng); }
     cudaFree(c->ev.n_alive);
@@ -252,7 +252,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.work = c->d_work; P.tally = c->d_tally;
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;
-    P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)std::min(c->opt.spawn_batch, 32) : (c->woodcock ? 4u : 1u);
+    P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)std::min(c->opt.spawn_batch, 32) : (c->woodcock ? 2u : 1u);
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
     P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;

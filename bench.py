@@ -294,7 +294,8 @@ def run_ours(a):
                          "peak_source": peak_src, "kernel": ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if has_bank else "false"), "kernel_ms": ms_kernel,
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
                          "note": "algorithmic bytes = 24 + 48*collisions/history (SURVEY 8d bank model); the fused kernel keeps "
-                                 "particles in registers so real DRAM traffic is far lower: the kernel is issue/shared-memory bound"},
+                                 "particles in registers, so measured DRAM traffic (the 32-byte birth records) is ~2 % of that: "
+                                 "the kernel is instruction-issue bound (profiles/)"},
             "k_mean": float(res.k[W:].mean()), "k_e2e_mean": float(e2e_res.k[1:].mean()) if K > 1 else float(e2e_res.k[0]),
         }
         if other_run is not None:

@@ -288,7 +288,7 @@ def run_ours(a):
             "clocks": clocks,
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "note": "one monte_carlo() call: context create + table upload + K generations + result download; bytes are per run / K"},
-            "gpu_launches": (2 + (5 if has_bank else 0)) * K,
+            "gpu_launches": (3 + (5 if has_bank else 0)) * K,  # source + transport + finalize (+ bank compaction / entropy)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel"),
                          "peak_source": peak_src, "kernel": ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if has_bank else "false"), "kernel_ms": ms_kernel,

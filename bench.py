@@ -191,7 +191,7 @@ def run_ours(a):
     gens_total = W + K
 
     base_opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode,
-                     spawn_batch=a.spawn_batch)
+                     spawn_batch=a.spawn_batch, walk_cap=a.walk_cap)
     opts = dict(base_opts, tracking_mode=a.tracking, kernel_variant=a.variant)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
@@ -334,6 +334,7 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--spawn-batch", type=int, default=0)
+    ap.add_argument("--walk-cap", type=int, default=0)
     ap.add_argument("--tracking", default="surface", choices=["surface", "woodcock"],
                     help="surface = the reference's cell-by-cell tracking (headline, bit-comparable); woodcock = delta tracking")
     ap.add_argument("--variant", default="fused", choices=["fused", "event"], help="kernel variant (event = SoA-bank pipeline, woodcock only)")

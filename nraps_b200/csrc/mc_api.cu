@@ -103,7 +103,7 @@ struct nraps_mc_ctx {
     uint32_t NB = 0;
     float inv_h = 0.0f;
     bool woodcock = false;
-    uint32_t prepared = 0, big = 0;
+    uint32_t prepared = 0, big = 0, walk_cap_auto = 0x7fffffffu;
     ulonglong2 *d_jump = nullptr;
     unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
@@ -253,6 +253,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;
     P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)std::min(c->opt.spawn_batch, 32) : (c->woodcock ? 2u : 1u);
+    P.walk_cap = c->opt.walk_cap > 0 ? (uint32_t)c->opt.walk_cap : (c->opt.walk_cap < 0 ? 0x7fffffffu : c->walk_cap_auto);
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
     P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
@@ -372,6 +373,11 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
         i = j;
     }
     for (uint32_t j = 0; j < NF; ++j) fuel[j] = (uint16_t)p->fuel_indices[j];
+    {   // regroup after half of the longest material run
+        uint32_t longest = 1;
+        for (uint32_t i = 0; i < N; ++i) longest = std::max(longest, (runb[i] >> 16) - (runb[i] & 0xffffu));
+        c->walk_cap_auto = std::max(2u, (longest + 1) / 2);
+    }
 
     std::vector<float> xs(xs_floats(M, G));
     float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *nusigf = chi_cdf + MG, *sigtr = nusigf + MG,

@@ -71,6 +71,7 @@ struct TransportParams {
     uint32_t *trace;               // [hist_end-hist_begin][NRAPS_TR_WORDS] or nullptr
     uint32_t chunk;
     uint32_t max_flights;
+    uint32_t walk_cap;    // surface kernel: crossings a lane walks before the warp regroups (0xffffffff = never)
     uint32_t spawn_batch; // dead lanes a warp waits for before it refills (amortises the divergent spawn path)
     int32_t scatter_mode, stale_xs;
     // fission_bank source mode

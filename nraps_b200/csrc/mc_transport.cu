@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     bool exhausted = false;
 
     // lane state: one neutron
-    bool alive = false;
+    bool alive = false, pending = false;
     uint64_t rng = 0, y = 0;
     float x = 0.f, mu = 1.f, ds = 0.f;
     int cell = 0, g = 0, xsg = 0, mat = 0, run_lo = 0, run_hi = 0;
@@ -123,12 +123,16 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
         float end = 0.f;
         Recip rc{1.f, 1.f};
         if (alive) {
-            if (h_flight >= P.max_flights) {
-                fate = NRAPS_FATE_TRUNCATED;
-            } else {
-                // ------------ FLIGHT: signed x-displacement to the next collision
-                ds = fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), s_inv_sigtr[mat + M * xsg]);
-                ++h_flight;
+            if (!pending) {
+                if (h_flight >= P.max_flights) {
+                    fate = NRAPS_FATE_TRUNCATED;
+                } else {
+                    // ------------ FLIGHT: signed x-displacement to the next collision
+                    ds = fmul(fmul(mu, -mc_logf(pcg32_unit(rng, inc))), s_inv_sigtr[mat + M * xsg]);
+                    ++h_flight;
+                }
+            }
+            if (!fate) {
                 // ------------ WALK: cell by cell inside one material run.  Single-exit loop with
                 // running shared addresses: ~30 SASS instructions per crossing (profiles/r1c_*).
                 rc = make_recip(mu);
@@ -138,6 +142,12 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 int run_exit = fwd ? run_hi : run_lo - 1;
                 uint32_t e_addr = edges_base + (uint32_t)(kStep * (cell + fwd)); // edge ahead of the neutron
                 uint32_t t_addr = tally_ref<BIG>(lo_base, g * N + cell);         // tally[g][cell]
+                // a walk longer than `walk_cap` crossings is suspended (pending) and resumed on the next trip, so
+                // the lanes that finished early are not kept waiting for the longest flight of the warp
+                // (folded into the loop's one exit compare: the walk stops at `stop_cell`, the nearer of the run
+                // exit and walk_cap cells ahead)
+                int stop_cell = cell + dir * min((run_exit - cell) * dir, (int)P.walk_cap);
+                pending = false;
                 for (;;) {
                     end = fadd(x, ds);
                     const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
@@ -156,6 +166,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                             dir = 2 * fwd - 1;
                             wall = fwd ? N - 1 : 0;
                             run_exit = fwd ? run_hi : run_lo - 1;
+                            stop_cell = cell + dir * min((run_exit - cell) * dir, (int)P.walk_cap);
                             e_addr = edges_base + (uint32_t)(kStep * (cell + fwd));
                             if (TRACE) ++h_refl;
                             continue;
@@ -170,10 +181,14 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     e_addr += kStep * dir;
                     t_addr += kStep * dir;
                     if (TRACE) ++h_cross;
-                    if (cell == run_exit) break; // left the material run
+                    if (cell == stop_cell) break; // left the material run, or time to regroup
                 }
                 // a collision always happens strictly inside the run, so the exit cell tells the two ways out apart
-                if (!fate) ev = (cell == run_exit) ? EV_MATCHANGE : EV_COLLIDE;
+                if (!fate) {
+                    if (cell == run_exit) ev = EV_MATCHANGE;
+                    else if (cell == stop_cell) pending = true;
+                    else ev = EV_COLLIDE;
+                }
             }
         }
         __syncwarp();

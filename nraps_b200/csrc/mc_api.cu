@@ -95,6 +95,7 @@ struct nraps_mc_ctx {
     uint64_t stride = 0;
     SmemLayout layout{};
     uint32_t grid = 0, block = 0, blocks_per_sm = 0, chunk = 0, max_flights = 0;
+    uint32_t geo_grid[2] = {0, 0}, geo_block[2] = {0, 0}; // launch geometry of the plain / trace instantiation
 
     float *d_edges = nullptr, *d_xs = nullptr, *d_dx = nullptr, *d_nut = nullptr, *d_sigf = nullptr;
     uint32_t *d_runb = nullptr;
@@ -274,13 +275,27 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         CU(run_event_generation(P, c->ev, c->layout.total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
         return NRAPS_OK;
     }
-    if (!c->big && !(c->prepared & (1u << (trace ? 1 : 0)))) { // shared-memory opt-in, once per (kernel, trace) instantiation
-        CU(c->woodcock ? prepare_woodcock(c->layout.total, c->G, trace, c->bank_mode)
-                       : prepare_transport(c->layout.total, c->G, trace, c->bank_mode));
-        c->prepared |= 1u << (trace ? 1 : 0);
+    const int ti = trace ? 1 : 0;
+    if (!(c->prepared & (1u << ti))) { // once per (kernel, trace) instantiation: shared-memory opt-in and launch geometry
+        if (!c->big)
+            CU(c->woodcock ? prepare_woodcock(c->layout.total, c->G, trace, c->bank_mode)
+                           : prepare_transport(c->layout.total, c->G, trace, c->bank_mode));
+        // auto geometry: 2 x 576 threads per SM (36 warps) when the instantiation's registers allow it, else 2 x 512;
+        // ncu: the kernels are issue bound and the extra warps buy ~3 % (gpurun sweep, profiles/r1_sweeps.txt)
+        uint32_t block = c->block, bps = c->blocks_per_sm;
+        if (c->opt.threads_per_block <= 0 && c->opt.blocks_per_sm <= 0 && bps == 2) {
+            auto occ = [&](int b) {
+                return c->woodcock ? occupancy_woodcock(c->G, c->big, trace, c->bank_mode, b, c->layout.total)
+                                   : occupancy_transport(c->G, c->big, trace, c->bank_mode, b, c->layout.total);
+            };
+            block = occ(576) >= 2 ? 576u : 512u;
+        }
+        c->geo_block[ti] = block;
+        c->geo_grid[ti] = (uint32_t)c->sm_count * bps;
+        c->prepared |= 1u << ti;
     }
-    if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
-    else CU(launch_transport(P, trace, c->bank_mode, dim3(c->grid), dim3(c->block), c->layout.total, s));
+    if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->layout.total, s));
+    else CU(launch_transport(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->layout.total, s));
     return NRAPS_OK;
 }
 
@@ -654,7 +669,7 @@ extern "C" int nraps_mc_bank_set_source(nraps_mc_ctx *c, uint64_t gen, const voi
 extern "C" int nraps_mc_launch_info(nraps_mc_ctx *c, uint32_t out[6])
 {
     if (!c || !out) return NRAPS_ERR_NULL;
-    out[0] = c->grid; out[1] = c->block; out[2] = c->layout.total; out[3] = c->blocks_per_sm;
+    out[0] = c->geo_grid[0] ? c->geo_grid[0] : c->grid; out[1] = c->geo_block[0] ? c->geo_block[0] : c->block; out[2] = c->layout.total; out[3] = c->blocks_per_sm;
     out[4] = (uint32_t)c->sm_count; out[5] = c->opt.kernel_variant == NRAPS_KERNEL_EVENT ? c->ev_iterations : c->chunk;
     return NRAPS_OK;
 }

@@ -123,6 +123,8 @@ struct FinalizeParams {
 };
 
 cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
+int occupancy_transport(uint32_t G, bool big, bool trace, bool bank, int block, uint32_t smem);
+int occupancy_woodcock(uint32_t G, bool big, bool trace, bool bank, int block, uint32_t smem);
 cudaError_t launch_source(const TransportParams &p, bool bank, uint4 *out, cudaStream_t s);
 cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
 cudaError_t prepare_woodcock(uint32_t smem_bytes, uint32_t G, bool trace, bool bank);

@@ -318,4 +318,32 @@ cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, di
     }
 }
 
+
+namespace {
+template <int TG, bool BIG> int occ_gb(bool trace, bool bank, int block, uint32_t smem)
+{
+    int n = 0;
+    cudaError_t e;
+    if (bank) e = trace ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, true, true, BIG>, block, smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, false, true, BIG>, block, smem);
+    else e = trace ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, true, false, BIG>, block, smem)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, false, false, BIG>, block, smem);
+    return e == cudaSuccess ? n : 0;
+}
+template <int TG> int occ_g(bool big, bool trace, bool bank, int block, uint32_t smem)
+{
+    return big ? occ_gb<TG, true>(trace, bank, block, smem) : occ_gb<TG, false>(trace, bank, block, smem);
+}
+} // namespace
+
+// resident blocks per SM of the instantiation that would be launched (registers and shared memory both count)
+int occupancy_transport(uint32_t G, bool big, bool trace, bool bank, int block, uint32_t smem)
+{
+    switch (G) {
+    case 2: return occ_g<2>(big, trace, bank, block, smem);
+    case 4: return occ_g<4>(big, trace, bank, block, smem);
+    default: return occ_g<0>(big, trace, bank, block, smem);
+    }
+}
+
 } // namespace nraps

@@ -1,4 +1,4 @@
-for t in woodcock surface; do for cfg in "512 2" "384 3" "1024 1" "576 2" "288 4"; do
+for t in woodcock surface; do for cfg in "512 3" "384 4" "448 3" "512 2" "256 6"; do
   set -- $cfg
   timeout 60 python bench.py --steps 8 --warmup 3 --no-cpu --no-variants --tracking $t --threads $1 --blocks-per-sm $2 2>/dev/null | python -c "
 import json,sys

@@ -3,6 +3,7 @@
 //   process_input -> mesh_gen -> monte_carlo -> plot_solution (three CSV files)
 // Usage: nraps [deck] [--out DIR] [--generations N] [--histories N] [--skip N]
 //              [--seed S --stream Q --stride T] [--device D] [--scatter single_xi|rust_pre182|rust_182]
+//              [--generation-log]  (one JSON line per generation on stderr: k, k_fund, bank size, source entropy)
 //              [--fix-stale-xs] [--quiet] [--gpus N] [--tracking surface|woodcock] [--source uniform_fuel|fission_bank]
 // The deck defaults to ./TestCaseC.txt like the reference (src/process_input.rs:86).
 #include <chrono>
@@ -24,6 +25,7 @@ int main(int argc, char **argv)
     opt.stale_xs = 1;
     long long gens = -1, hist = -1, skip = -1;
     int gpus = 1;
+    bool gen_log = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&](const char *what) -> const char * {
@@ -40,6 +42,7 @@ int main(int argc, char **argv)
         else if (a == "--device") opt.device = std::atoi(next("--device"));
         else if (a == "--fix-stale-xs") opt.stale_xs = 0;
         else if (a == "--quiet") opt.quiet = 1;
+        else if (a == "--generation-log") gen_log = true;
         else if (a == "--gpus") gpus = std::atoi(next("--gpus"));
         else if (a == "--tracking") opt.tracking_mode = std::string(next("--tracking")) == "woodcock" ? NRAPS_TRACK_WOODCOCK : NRAPS_TRACK_SURFACE;
         else if (a == "--source") opt.source_mode = std::string(next("--source")) == "fission_bank" ? NRAPS_SOURCE_FISSION_BANK : NRAPS_SOURCE_UNIFORM_FUEL;
@@ -71,6 +74,9 @@ int main(int argc, char **argv)
     nraps_results res{};
     res.flux = flux.data(); res.assembly_average = avg.data(); res.fission_source = fis.data();
     res.k = k.data(); res.k_fund = kf.data();
+    std::vector<uint64_t> bank_sizes(prob.generations);
+    std::vector<double> entropy(prob.generations);
+    res.bank_sizes = bank_sizes.data(); res.entropy = entropy.data();
     if (gpus > 1) { // all GPUs of the box through libnraps_b200_nccl.so (loaded on demand: the core has no NCCL dependency)
         void *h = dlopen("libnraps_b200_nccl.so", RTLD_NOW);
         auto fn = h ? reinterpret_cast<decltype(&nraps_mc_run_multi)>(dlsym(h, "nraps_mc_run_multi")) : nullptr;
@@ -86,6 +92,10 @@ int main(int argc, char **argv)
     rc = nraps_plot_solution(&res, prob.G, prob.generations, prob.N, (double)mesh.right[mesh.N - 1], out_dir.c_str());
     if (rc != NRAPS_OK) { std::fprintf(stderr, "plot_solution: %s\n", nraps_strerror(rc)); return 1; }
 
+    if (gen_log)
+        for (uint64_t g = 0; g < prob.generations; ++g)
+            std::fprintf(stderr, "{\"generation\": %llu, \"k\": %.7g, \"k_fund\": %.7g, \"bank\": %llu, \"entropy_bits\": %.6f}\n",
+                         (unsigned long long)g, (double)k[g], (double)kf[g], (unsigned long long)bank_sizes[g], entropy[g]);
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const double total = (double)prob.histories * (double)prob.generations;
     std::printf("Run was completed in %lld milliseconds \n", (long long)(wall * 1e3)); // src/main.rs:366-369

@@ -198,3 +198,28 @@ def test_oracle_woodcock_matches_surface_tracking_statistically():
     assert abs(kw_.mean() - ks.mean()) < 4 * sigma
     assert abs(w.counters["collisions"] / w.counters["histories"] - s.counters["collisions"] / s.counters["histories"]) < 0.3
     assert w.counters["crossings"] == 0 and w.counters["flights"] < 1.4 * w.counters["collisions"]
+
+
+def test_flux_shape_against_the_reference_shipped_output():
+    """The only end-to-end artefact the reference ships (interface.csv, an older build with a different
+    normalisation): scale-free shapes must agree.  The fission-source shape also confirms SURVEY 9-Q7: the
+    shipped run used the flat fuel source, not a fission-bank iteration."""
+    import json
+    import os
+
+    from tests.util import ROOT, load_case, oracle_inputs
+
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_shipped_shape.json")))
+    deck, mesh = oracle_inputs(*load_case("c"))
+    r = orc.monte_carlo(deck, mesh, generations=10, histories=100000, skip=2, threads=4)
+    assert r.flux.shape[1] == ref["n_cells"]
+    fis = r.fission_source / r.fission_source.sum()
+    assert np.corrcoef(fis, ref["fission_source_shape"])[0, 1] > 0.999
+    th = r.flux[3] / r.flux[3].sum()
+    assert np.corrcoef(th, ref["thermal_flux_shape"])[0, 1] > 0.93  # the shipped thermal row is visibly noisier
+    ratio = r.flux.mean(axis=1) / r.flux.mean(axis=1)[0]
+    assert np.allclose(ratio[:3], ref["group_mean_flux_ratio"][:3], rtol=0.03)
+    assert abs(ratio[3] / ref["group_mean_flux_ratio"][3] - 1) < 0.12  # thermal group: older semantics differ by ~9 %
+    bank = orc.monte_carlo(deck, mesh, generations=10, histories=100000, skip=2, threads=4, source_mode="fission_bank")
+    fb = bank.fission_source / bank.fission_source.sum()
+    assert np.corrcoef(fb, ref["fission_source_shape"])[0, 1] < 0.98  # a converged fission source tilts towards the MOX side

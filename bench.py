@@ -107,13 +107,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s; MEASURED_PEAKS.json absent)"
 
 
-def measured_traffic(kernel: str):
+def ncu_facts(kernel: str) -> dict:
+    """Numbers taken from the committed ncu captures of this kernel (profiles/traffic.json), not measured live."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as fh:
-            return json.load(fh)[kernel]["bytes"]
+            return json.load(fh)[kernel]
     except (OSError, KeyError, ValueError):
-        return None
+        return {}
+
+
+def measured_traffic(kernel: str):
+    return ncu_facts(kernel).get("bytes")
 
 
 def cpu_sample(args, histories: int, generations: int, threads: int, faithful: bool = True):
@@ -293,6 +298,8 @@ def run_ours(a):
                          "traffic": measured_traffic("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel"),
                          "peak_source": peak_src, "kernel": ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if has_bank else "false"), "kernel_ms": ms_kernel,
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
+                         "actual_limiter": {"what": "instruction issue (ncu, profiles/)", **{k: v for k, v in ncu_facts(
+                             "woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel").items() if k not in ("bytes", "source")}},
                          "note": "algorithmic bytes = 24 + 48*collisions/history (SURVEY 8d bank model); the fused kernel keeps "
                                  "particles in registers, so measured DRAM traffic (the 32-byte birth records) is ~2 % of that: "
                                  "the kernel is instruction-issue bound (profiles/)"},

@@ -142,23 +142,24 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 int run_exit = fwd ? run_hi : run_lo - 1;
                 uint32_t e_addr = edges_base + (uint32_t)(kStep * (cell + fwd)); // edge ahead of the neutron
                 uint32_t t_addr = tally_ref<BIG>(lo_base, g * N + cell);         // tally[g][cell]
-                // a walk longer than `walk_cap` crossings is suspended (pending) and resumed on the next trip, so
-                // the lanes that finished early are not kept waiting for the longest flight of the warp
-                // (folded into the loop's one exit compare: the walk stops at `stop_cell`, the nearer of the run
-                // exit and walk_cap cells ahead)
-                int stop_cell = cell + dir * min((run_exit - cell) * dir, (int)P.walk_cap);
+                // The hot loop below has two ways out and no wall logic.  The domain-boundary cell in the direction
+                // of travel is handled here, before the loop (src/mc_code.rs:159-170): a lane that reaches it
+                // inside the loop stops there (it is its stop_cell) and comes back through this block next trip.
+                bool in_loop = true;
                 pending = false;
-                for (;;) {
+                if (cell == wall) {
                     end = fadd(x, ds);
                     const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
                     const float t = fsub(x, edge);
-                    if (cell == wall) { // domain boundary cell: src/mc_code.rs:159-170
-                        const bool beyond = fwd ? (end > edge) : (edge > end);
-                        if (beyond) {
-                            score<BIG>(t_addr, hi_off, fabsf(fdiv(t, mu)), P.tally);
-                            const float b = fwd ? P.boundr : P.boundl;
-                            if (!(b > 0.0f)) { fate = NRAPS_FATE_LEAKED; break; }
-                            mu = fmul(mu, -b); // hit_boundary
+                    const bool beyond = fwd ? (end > edge) : (edge > end);
+                    if (beyond) {
+                        score<BIG>(t_addr, hi_off, fabsf(fdiv(t, mu)), P.tally);
+                        const float b = fwd ? P.boundr : P.boundl;
+                        if (!(b > 0.0f)) {
+                            fate = NRAPS_FATE_LEAKED;
+                            in_loop = false;
+                        } else { // hit_boundary; the flight goes on in the other direction
+                            mu = fmul(mu, -b);
                             ds = fmul(fadd(ds, t), -b);
                             x = edge;
                             rc = make_recip(mu);
@@ -166,25 +167,44 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                             dir = 2 * fwd - 1;
                             wall = fwd ? N - 1 : 0;
                             run_exit = fwd ? run_hi : run_lo - 1;
-                            stop_cell = cell + dir * min((run_exit - cell) * dir, (int)P.walk_cap);
                             e_addr = edges_base + (uint32_t)(kStep * (cell + fwd));
                             if (TRACE) ++h_refl;
-                            continue;
+                            // N == 1, or albedo <= 0 after the flip: the other wall is this very cell -> next trip
+                            if (cell == wall) { in_loop = false; pending = true; }
                         }
+                    } else if (!(fabsf(fsub(end, x)) > fabsf(t))) {
+                        ev = EV_COLLIDE; // collision inside the boundary cell
+                        in_loop = false;
+                    } else {
+                        // unreachable for finite positive inv_sigtr (a crossing test that succeeds where the wall
+                        // test failed); keep the reference's order of tests and treat it as a collision at `end`
+                        ev = EV_COLLIDE;
+                        in_loop = false;
                     }
-                    if (!(fabsf(fsub(end, x)) > fabsf(t))) break; // collision at `end` (|edge - x| == |x - edge| exactly)
-                    // cross_mesh, src/mc_code.rs:171-181
-                    score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
-                    ds = fadd(ds, t);
-                    x = edge;
-                    cell += dir;
-                    e_addr += kStep * dir;
-                    t_addr += kStep * dir;
-                    if (TRACE) ++h_cross;
-                    if (cell == stop_cell) break; // left the material run, or time to regroup
                 }
-                // a collision always happens strictly inside the run, so the exit cell tells the two ways out apart
-                if (!fate) {
+                if (in_loop) {
+                    // a walk longer than `walk_cap` crossings is suspended (pending) and resumed on the next trip, so
+                    // the lanes that finished early are not kept waiting for the longest flight of the warp; the cap
+                    // and the boundary cell are folded into the loop's one exit compare (`stop_cell`)
+                    int steps = min((run_exit - cell) * dir, (int)P.walk_cap);
+                    const int to_wall = (wall - cell) * dir; // cells until the boundary cell, if it lies in this run
+                    if (to_wall < steps) steps = to_wall;
+                    const int stop_cell = cell + dir * steps;
+                    for (;;) {
+                        end = fadd(x, ds);
+                        const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
+                        const float t = fsub(x, edge);
+                        if (!(fabsf(fsub(end, x)) > fabsf(t))) break; // collision at `end` (|edge - x| == |x - edge| exactly)
+                        // cross_mesh, src/mc_code.rs:171-181
+                        score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
+                        ds = fadd(ds, t);
+                        x = edge;
+                        cell += dir;
+                        e_addr += kStep * dir;
+                        t_addr += kStep * dir;
+                        if (TRACE) ++h_cross;
+                        if (cell == stop_cell) break; // left the material run, reached the boundary cell, or time to regroup
+                    }
                     if (cell == run_exit) ev = EV_MATCHANGE;
                     else if (cell == stop_cell) pending = true;
                     else ev = EV_COLLIDE;

@@ -34,16 +34,17 @@ static __device__ __forceinline__ float lds_f32(uint32_t saddr)
 template <bool BIG>
 static __device__ __forceinline__ void score(uint32_t ref, uint32_t hi_off, float v, unsigned long long *global_bins)
 {
-    const unsigned long long fx = __float2ull_rz(fmul(v, kTallyScale));
+    const float vs = fmul(v, kTallyScale);
+    const unsigned long long fx = __float2ull_rz(vs);
     if (BIG) {
         atomicAdd(global_bins + ref, fx);
         return;
     }
     const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
     const uint32_t old = atoms_add(ref, l);
-    // high word += h + carry, as one predicated reduction (no branch, so no reconvergence barrier in the walk loop)
-    const uint32_t add_hi = h + ((uint32_t)(old + l) < l ? 1u : 0u);
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], %1; }" ::"r"(ref + hi_off), "r"(add_hi) : "memory");
+    // high word += h + carry; both are rare (a score >= 16 cm, or the low word wrapping), so one test guards the pair
+    const bool carry = old > ~l;
+    if (carry | (vs >= 4294967296.0f)) reds_add(ref + hi_off, h + (carry ? 1u : 0u)); // vs >= 2^32 <=> h != 0, one FSETP
 }
 // tally reference of bin `bin`: shared byte address or plain index
 template <bool BIG> static __device__ __forceinline__ uint32_t tally_ref(uint32_t lo_base, int bin)

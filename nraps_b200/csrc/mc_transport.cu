@@ -190,11 +190,12 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     const int to_wall = (wall - cell) * dir; // cells until the boundary cell, if it lies in this run
                     if (to_wall < steps) steps = to_wall;
                     const int stop_cell = cell + dir * steps;
-                    for (;;) {
+                    // one crossing; false = the walk is over (collision, or stop_cell reached)
+                    auto step = [&]() -> bool {
                         end = fadd(x, ds);
                         const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
                         const float t = fsub(x, edge);
-                        if (!(fabsf(fsub(end, x)) > fabsf(t))) break; // collision at `end` (|edge - x| == |x - edge| exactly)
+                        if (!(fabsf(fsub(end, x)) > fabsf(t))) return false; // collision at `end` (|edge - x| == |x - edge| exactly)
                         // cross_mesh, src/mc_code.rs:171-181
                         score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
                         ds = fadd(ds, t);
@@ -203,8 +204,9 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                         e_addr += kStep * dir;
                         t_addr += kStep * dir;
                         if (TRACE) ++h_cross;
-                        if (cell == stop_cell) break; // left the material run, reached the boundary cell, or time to regroup
-                    }
+                        return cell != stop_cell; // left the material run, reached the boundary cell, or time to regroup
+                    };
+                    while (step() && step() && step() && step()) {} // unrolled by four: no loop-carried moves, one back branch per four crossings
                     if (cell == run_exit) ev = EV_MATCHANGE;
                     else if (cell == stop_cell) pending = true;
                     else ev = EV_COLLIDE;

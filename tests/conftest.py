@@ -18,4 +18,4 @@ def _built():
     """Make sure the oracle and the product library exist (incremental make)."""
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
     if not os.path.exists(os.path.join(ROOT, "nraps_b200", "lib", "libnraps_b200.so")):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "nraps_b200", "csrc")], check=True, capture_output=True)
+        subprocess.run(["make", "-j", "8", "-C", os.path.join(ROOT, "nraps_b200", "csrc")], check=True, capture_output=True)

@@ -105,6 +105,7 @@ struct nraps_mc_ctx {
     float inv_h = 0.0f;
     bool woodcock = false;
     uint32_t prepared = 0, big = 0, walk_cap_auto = 0x7fffffffu;
+    uint32_t batch = 1; // generations one launch may carry (small generations do not fill the GPU on their own)
     ulonglong2 *d_jump = nullptr;
     unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
@@ -225,9 +226,12 @@ int ensure_bank(nraps_mc_ctx *c, uint64_t count)
     return NRAPS_OK;
 }
 
-int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count, bool trace, cudaStream_t s)
+// Transport generations gen .. gen+nb-1 (shard [begin, begin+count) of each) in one launch.  nb > 1 only for the
+// uniform source, where generations are independent; each generation scores into its own G tally rows.
+int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count, bool trace, cudaStream_t s, uint32_t nb = 1)
 {
     if (begin > c->histories || count > c->histories - begin) return NRAPS_ERR_SHAPE;
+    if (nb < 1 || nb > c->batch || gen + nb > c->generations || (nb > 1 && (trace || c->d_tally != c->d_tally_own))) return NRAPS_ERR_STATE;
     c->last_shard = count;
     if (c->bank_mode) {
         int rc = ensure_bank(c, count);
@@ -235,7 +239,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
         if (padded) CU(cudaMemsetAsync(c->d_counts, 0, padded, s));
     }
-    const uint64_t words = (uint64_t)c->G * c->N + NRAPS_CT_WORDS;
+    const uint64_t words = (uint64_t)nb * c->G * c->N + NRAPS_CT_WORDS;
     CU(cudaMemsetAsync(c->d_tally, 0, words * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
     if (count == 0) return NRAPS_OK;
@@ -249,7 +253,8 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     pcg_jump_coeffs(c->master.inc, gen * c->histories * c->stride, &jm, &jp);
     P.rng_state = jm * c->master.state + jp;
     P.rng_inc = c->master.inc;
-    P.hist_begin = begin; P.hist_end = begin + count;
+    P.hist_begin = begin; P.hist_end = begin + (uint64_t)nb * count;
+    P.rows = nb * c->G; P.hist_shard = count; P.hist_total = c->histories;
     P.work = c->d_work; P.tally = c->d_tally;
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;
@@ -259,11 +264,12 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
     if (c->opt.kernel_variant != NRAPS_KERNEL_EVENT) { // births first, every lane busy; the transport lanes adopt them
-        if (count > c->source_cap) {
+        const uint64_t births = (uint64_t)nb * count;
+        if (births > c->source_cap) {
             CU(cudaFree(c->d_source));
             c->d_source = nullptr; c->source_cap = 0;
-            CU(cudaMalloc((void **)&c->d_source, count * 2 * sizeof(uint4)));
-            c->source_cap = count;
+            CU(cudaMalloc((void **)&c->d_source, births * 2 * sizeof(uint4)));
+            c->source_cap = births;
         }
         P.source = c->d_source;
         CU(launch_source(P, c->bank_mode, c->d_source, s));
@@ -321,7 +327,10 @@ extern "C" const char *nraps_strerror(int code)
     }
 }
 
-extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **out)
+namespace {
+
+// allow_batch: the caller runs whole generations back to back (nraps_mc_run) and lets one launch carry several
+int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **out, bool allow_batch)
 {
     if (!out) return NRAPS_ERR_NULL;
     *out = nullptr;
@@ -342,6 +351,18 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     const uint32_t big = L.total > kMaxSmem ? 1u : 0u;
     if (big) L = make_layout(M, G, N, NF, NB, 1);
     if (L.total > kMaxSmem || (big && o->kernel_variant == NRAPS_KERNEL_EVENT)) return NRAPS_ERR_TOO_LARGE;
+    // Generations of the uniform source are independent, and one of the shipped decks' 1e5..1e6 histories leaves most
+    // of the 148 SMs idle: let a launch carry enough generations for ~2^23 histories, each scoring into its own G
+    // tally rows, as long as the block still fits twice on an SM.
+    uint32_t batch = 1;
+    if (allow_batch && !big && o->source_mode == NRAPS_SOURCE_UNIFORM_FUEL && o->kernel_variant != NRAPS_KERNEL_EVENT) {
+        uint64_t want = std::min<uint64_t>(std::min<uint64_t>((1ull << 23) / p->histories, p->generations), 64);
+        while (want > 1 && make_layout(M, G, N, NF, NB, 0, (uint32_t)want * G).total > 100u * 1024u) --want;
+        if (want > 1) {
+            batch = (uint32_t)want;
+            L = make_layout(M, G, N, NF, NB, 0, batch * G);
+        }
+    }
 
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -361,7 +382,7 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     const bool dflt = (o->seed == 0 && o->stream == 0 && o->stride == 0);
     c->master = pcg_seed(dflt ? 42u : o->seed, dflt ? 54u : o->stream);
     c->stride = dflt ? 152917u : o->stride;
-    c->layout = L;
+    c->layout = L; c->batch = batch;
     c->max_flights = (uint32_t)std::min<uint64_t>(o->max_flights ? o->max_flights : (1ull << 24), 0xffffffffull);
     c->chunk = o->chunk > 0 ? (uint32_t)o->chunk : 64u;
     c->bank_mode = (o->source_mode == NRAPS_SOURCE_FISSION_BANK);
@@ -455,7 +476,7 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     ok(upload(&c->d_edges, edges)); ok(upload(&c->d_runb, runb)); ok(upload(&c->d_matid, matid));
     ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump)); ok(upload(&c->d_bucket, bucket));
     ok(upload(&c->d_dx, dx)); ok(upload(&c->d_nut, nut)); ok(upload(&c->d_sigf, sigf));
-    ok(cudaMalloc((void **)&c->d_tally_own, (GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
+    ok(cudaMalloc((void **)&c->d_tally_own, (batch * GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
     ok(cudaMalloc((void **)&c->d_work, sizeof(unsigned long long)));
     ok(cudaMalloc((void **)&c->d_counters_total, NRAPS_CT_WORDS * sizeof(unsigned long long)));
     ok(cudaMalloc((void **)&c->d_terms, GN * sizeof(float)));
@@ -479,6 +500,33 @@ extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, n
     CU(cudaDeviceSynchronize());
     *out = c;
     return NRAPS_OK;
+}
+
+// fold generation `gen`, whose tally is rows [slice*G, slice*G+G) of the launch that carried nb generations
+int finalize_slice(nraps_mc_ctx *c, uint64_t gen, uint32_t slice, uint32_t nb, cudaStream_t s)
+{
+    const uint64_t GN = (uint64_t)c->G * c->N;
+    FinalizeParams F{};
+    F.tally = c->d_tally + slice * GN;
+    F.counters = slice == 0 ? c->d_tally + nb * GN : nullptr; // the launch's counters are accounted once
+    F.dx = c->d_dx; F.matid = c->d_matid; F.nusigf_nut = c->d_nut; F.sigf = c->d_sigf;
+    F.terms = c->d_terms; F.res_flux = c->d_res_flux; F.res_fission = c->d_res_fission;
+    F.k_hist = c->d_k_hist; F.k_cur = c->d_k_cur; F.counters_total = c->d_counters_total;
+    F.M = c->M; F.G = c->G; F.N = c->N;
+    F.histories_f32 = (float)c->histories;
+    F.length = c->length; F.nut_m1 = c->nut_m1;
+    // 1 / (generations - (skip - 1)) in wrapping usize arithmetic, src/mc_code.rs:340 (SURVEY 9-Q5)
+    F.fund = 1.0f / (float)(uint64_t)(c->generations - (c->skip - 1));
+    F.gen = gen; F.skip = c->skip;
+    CU(launch_finalize(F, s));
+    return NRAPS_OK;
+}
+
+} // namespace
+
+extern "C" int nraps_mc_create(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **out)
+{
+    return create_ctx(p, o, out, false);
 }
 
 extern "C" int nraps_mc_destroy(nraps_mc_ctx *ctx)
@@ -520,18 +568,7 @@ extern "C" int nraps_mc_finalize_generation(nraps_mc_ctx *c, uint64_t gen, void 
     if (!c) return NRAPS_ERR_NULL;
     if (gen >= c->generations) return NRAPS_ERR_SHAPE;
     CU(cudaSetDevice(c->device));
-    FinalizeParams F{};
-    F.tally = c->d_tally; F.dx = c->d_dx; F.matid = c->d_matid; F.nusigf_nut = c->d_nut; F.sigf = c->d_sigf;
-    F.terms = c->d_terms; F.res_flux = c->d_res_flux; F.res_fission = c->d_res_fission;
-    F.k_hist = c->d_k_hist; F.k_cur = c->d_k_cur; F.counters_total = c->d_counters_total;
-    F.M = c->M; F.G = c->G; F.N = c->N;
-    F.histories_f32 = (float)c->histories;
-    F.length = c->length; F.nut_m1 = c->nut_m1;
-    // 1 / (generations - (skip - 1)) in wrapping usize arithmetic, src/mc_code.rs:340 (SURVEY 9-Q5)
-    F.fund = 1.0f / (float)(uint64_t)(c->generations - (c->skip - 1));
-    F.gen = gen; F.skip = c->skip;
-    CU(launch_finalize(F, static_cast<cudaStream_t>(stream)));
-    return NRAPS_OK;
+    return finalize_slice(c, gen, 0, 1, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int nraps_mc_tally_buffer(nraps_mc_ctx *c, void **device_ptr, uint64_t *n_words)
@@ -679,7 +716,7 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
     if (!p || !o || !r) return NRAPS_ERR_NULL;
     if (!r->flux || !r->assembly_average || !r->fission_source || !r->k || !r->k_fund) return NRAPS_ERR_NULL;
     nraps_mc_ctx *c = nullptr;
-    int rc = nraps_mc_create(p, o, &c);
+    int rc = create_ctx(p, o, &c, true);
     if (rc != NRAPS_OK) return rc;
     if (!o->quiet) { std::printf("running MC code\n"); std::fflush(stdout); } // src/mc_code.rs:292
 
@@ -697,17 +734,21 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
         return bail(cuda_fail(cudaGetLastError(), "stream/event create"));
     cudaEventRecord(e0, s);
     const uint64_t GN = (uint64_t)p->G * p->N;
-    std::vector<uint64_t> words(r->tally_fixed ? GN + NRAPS_CT_WORDS : 0);
-    for (uint64_t gen = 0; gen < p->generations; ++gen) {
-        if ((rc = nraps_mc_transport(c, gen, 0, p->histories, s)) != NRAPS_OK) return bail(rc);
+    for (uint64_t gen = 0; gen < p->generations;) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(c->batch, p->generations - gen);
+        if ((rc = run_transport(c, gen, 0, p->histories, false, s, nb)) != NRAPS_OK) return bail(rc);
         if (r->tally_fixed) {
-            if ((rc = nraps_mc_read_tally(c, words.data(), s)) != NRAPS_OK) return bail(rc);
-            std::memcpy(r->tally_fixed + gen * GN, words.data(), GN * sizeof(uint64_t));
+            if (cudaMemcpyAsync(r->tally_fixed + gen * GN, c->d_tally, nb * GN * sizeof(uint64_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess)
+                return bail(cuda_fail(cudaGetLastError(), "tally read-back"));
         }
-        if ((rc = nraps_mc_finalize_generation(c, gen, s)) != NRAPS_OK) return bail(rc);
+        // generations fold in order: k and the running flux sums are sequential f32 accumulations
+        for (uint32_t j = 0; j < nb; ++j)
+            if ((rc = finalize_slice(c, gen + j, j, nb, s)) != NRAPS_OK) return bail(rc);
+        gen += nb;
         if (c->bank_mode) {
-            if ((rc = nraps_mc_bank_compact(c, gen, s)) != NRAPS_OK) return bail(rc);
-            if ((rc = nraps_mc_bank_set_source(c, gen, nullptr, 0, s)) != NRAPS_OK) return bail(rc);
+            if ((rc = nraps_mc_bank_compact(c, gen - 1, s)) != NRAPS_OK) return bail(rc);
+            if ((rc = nraps_mc_bank_set_source(c, gen - 1, nullptr, 0, s)) != NRAPS_OK) return bail(rc);
         }
     }
     cudaEventRecord(e1, s);

@@ -46,7 +46,7 @@ __device__ __forceinline__ Tables tables_of(const SmemView &S, int MG, int G)
 __device__ __forceinline__ void count_deaths(const TransportParams &P, uint32_t hist, uint32_t coll, uint32_t flight, uint32_t refl,
                                              uint32_t leak, uint32_t trunc)
 {
-    unsigned long long *ct = P.tally + (size_t)P.G * P.N;
+    unsigned long long *ct = P.tally + (size_t)P.rows * P.N;
     const uint32_t vals[8] = {hist, coll, 0u, flight, refl, leak, trunc, 0u};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(512) ev_source(const TransportParams P, const 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G, MG = (int)P.M * G;
-    const SmemView S = load_block_tables(smem_raw, P, make_layout(P.M, P.G, P.N, P.NF, P.NB));
+    const SmemView S = load_block_tables(smem_raw, P, make_layout(P.M, P.G, P.N, P.NF, P.NB, 0, P.rows));
     const Tables T = tables_of(S, MG, G);
     const uint64_t n = P.hist_end - P.hist_begin;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(512) ev_advance(const TransportParams P, const
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G, M = (int)P.M, N = (int)P.N, NB = (int)P.NB, MG = M * G;
-    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB);
+    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, 0, P.rows);
     const SmemView S = load_block_tables(smem_raw, P, L);
     const Tables T = tables_of(S, MG, G);
     const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(S.lo), hi_off = L.tally_hi - L.tally_lo;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(512) ev_collide(const TransportParams P, const
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G, M = (int)P.M, MG = M * G;
-    const SmemView S = load_block_tables(smem_raw, P, make_layout(P.M, P.G, P.N, P.NF, P.NB));
+    const SmemView S = load_block_tables(smem_raw, P, make_layout(P.M, P.G, P.N, P.NF, P.NB, 0, P.rows));
     const Tables T = tables_of(S, MG, G);
     const uint64_t n = *n_alive;
     uint32_t d_hist = 0, d_coll = 0, d_flight = 0, d_refl = 0;

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
         P.k_hist[P.gen] = k_acc;
         *P.k_cur = k_acc;
     }
-    if (tid < NRAPS_CT_WORDS) P.counters_total[tid] += P.tally[GN + tid];
+    if (tid < NRAPS_CT_WORDS && P.counters) P.counters_total[tid] += P.counters[tid];
 }
 
 __global__ void probe_logf_kernel(const float *x, float *out, uint32_t n)

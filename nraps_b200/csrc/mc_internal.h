@@ -32,14 +32,17 @@ __host__ __device__ inline uint32_t xs_floats(uint32_t M, uint32_t G) { return 5
 
 // big = 1: the mesh does not fit one SM's shared memory; only the jump table and the XS block are staged, the mesh
 // tables are read through L1/L2 and the tally goes straight to the global 64-bit bins (slower, any N <= 65535)
-__host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t NF, uint32_t NB, uint32_t big = 0)
+// rows = tally rows: G, or batch*G when several small generations share one launch (0 = G)
+__host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t NF, uint32_t NB, uint32_t big = 0,
+                                                  uint32_t rows = 0)
 {
     if (big) { N = 0; NF = 0; NB = 0; }
+    if (!rows) rows = G;
     SmemLayout L;
     uint32_t off = 0;
     L.jump = off;     off += 64 * 16;
-    L.tally_lo = off; off += G * N * 4;
-    L.tally_hi = off; off += G * N * 4;
+    L.tally_lo = off; off += rows * N * 4;
+    L.tally_hi = off; off += rows * N * 4;
     L.edges = off;    off += (N + 1) * 4;
     L.runb = off;     off += N * 4;
     off = align_up(off, 16); // float4 rows of the CDF tables
@@ -62,6 +65,9 @@ struct TransportParams {
     const uint16_t *bucket;  // [NB] Woodcock position buckets (NB = 0 in surface mode)
     const uint4 *source;     // [hist_end-hist_begin][2] born neutrons written by source_kernel
     uint32_t M, G, N, NF, NB, big;
+    uint32_t rows;       // tally rows of this launch = batch * G: generations gen .. gen+batch-1 share the launch
+    uint64_t hist_shard; // histories of one generation in this launch (hist_end - hist_begin = batch * hist_shard)
+    uint64_t hist_total; // histories per generation (stream position of generation j starts at j * hist_total)
     float boundl, boundr, dx_fuel, inv_h;
     uint64_t rng_state; // master stream advanced to history 0 of this generation
     uint64_t rng_inc;
@@ -106,7 +112,8 @@ struct BankParams {
 constexpr uint32_t kBankTile = 16384; // histories per block of the compaction kernels (1024 threads x 16)
 
 struct FinalizeParams {
-    const unsigned long long *tally; // [G*N]
+    const unsigned long long *tally; // [G*N] of this generation
+    const unsigned long long *counters; // [NRAPS_CT_WORDS] of the launch, or nullptr if already accounted
     const float *dx;                 // [N]
     const uint8_t *matid;            // [N]
     const float *nusigf_nut;         // nut[MG]

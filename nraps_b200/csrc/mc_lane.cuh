@@ -158,7 +158,7 @@ static __device__ __forceinline__ SmemView load_block_tables(unsigned char *smem
     S.matid = smem_raw + L.matid;
     S.bucket = reinterpret_cast<uint16_t *>(smem_raw + L.bucket);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int G = (int)P.G, M = (int)P.M, N = (int)P.N, GN = G * N, MG = M * G;
+    const int G = (int)P.G, M = (int)P.M, N = (int)P.N, GN = (int)P.rows * N, MG = M * G;
     for (int i = tid; i < GN; i += nthr) { S.lo[i] = 0u; S.hi[i] = 0u; }
     for (int i = tid; i <= N; i += nthr) S.edges[i] = P.edges[i];
     for (int i = tid; i < N; i += nthr) { S.runb[i] = P.runb[i]; S.matid[i] = P.matid[i]; }
@@ -173,7 +173,7 @@ static __device__ __forceinline__ SmemView load_block_tables(unsigned char *smem
 // Block epilogue: shared bins -> global 64-bit bins, lane counters -> global counters.
 static __device__ __forceinline__ void flush_block(const SmemView &S, const TransportParams &P, const uint32_t (&vals)[8])
 {
-    const int tid = threadIdx.x, nthr = blockDim.x, GN = (int)(P.G * P.N);
+    const int tid = threadIdx.x, nthr = blockDim.x, GN = (int)(P.rows * P.N);
     __syncthreads();
     for (int i = tid; i < GN && !P.big; i += nthr) {
         const unsigned long long v = ((unsigned long long)S.hi[i] << 32) + S.lo[i];

@@ -5,7 +5,7 @@
 // Replaces spawn_neutron + energy (src/mc_code.rs:7-53, 228-230); draw order cell, position, mu, chi (:46-51), or
 // site index, mu, chi in fission_bank mode.  Each thread takes a run of consecutive histories so that only the
 // first needs the full PCG32 jump; the next ones are one affine map (stride draws) further.  Output: one 32-byte
-// record per history {x, mu, cell | g << 16, -, rng state, -}, read back by the lane that adopts the history.
+// record per history {x, mu, cell | g << 16, first tally row of its generation, rng state, -}, read back by the lane that adopts the history.
 #include "mc_lane.cuh"
 
 namespace nraps {
@@ -22,14 +22,24 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
     __syncthreads();
     const int G = TG ? TG : (int)P.G, MG = (int)P.M * G;
     const float *chi = P.xs + 2 * MG;
-    const uint64_t n = P.hist_end - P.hist_begin;
+    const uint64_t n = (uint64_t)(P.rows / P.G) * P.hist_shard;
     const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
     const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRun;
     if (first >= n) return;
-    uint64_t base = jump_ahead(P.rng_state, P.hist_begin + first, s_jump);
+    // record i belongs to generation i / hist_shard of the launch and history hist_begin + i % hist_shard of it;
+    // its stream starts (generation * hist_total + history) * stride draws into the master stream
+    uint32_t gen_local = (uint32_t)(first / P.hist_shard);
+    uint64_t in_gen = first % P.hist_shard;
+    uint64_t base = jump_ahead(P.rng_state, (uint64_t)gen_local * P.hist_total + P.hist_begin + in_gen, s_jump);
     const ulonglong2 J1 = s_jump[0];
     const uint64_t last = first + kRun < n ? first + kRun : n;
     for (uint64_t i = first; i < last; ++i) {
+        if (in_gen == P.hist_shard) { // the run crosses into the next generation of the batch
+            in_gen = 0;
+            ++gen_local;
+            base = jump_ahead(P.rng_state, (uint64_t)gen_local * P.hist_total + P.hist_begin, s_jump);
+        }
+        ++in_gen;
         uint64_t rng = base;
         base = J1.x * base + J1.y; // stream of the next history
         const uint32_t u = pcg32_next(rng, P.rng_inc);
@@ -47,14 +57,14 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
             x = fadd(__ldg(P.edges + cell), fmul(xi_pos, P.dx_fuel));
         }
         const int g = search_cdf_global<TG>(chi + __ldg(P.matid + cell) * G, G, pcg32_unit(rng, P.rng_inc));
-        out[2 * i] = make_uint4(__float_as_uint(x), __float_as_uint(mu), (uint32_t)cell | ((uint32_t)g << 16), 0u);
+        out[2 * i] = make_uint4(__float_as_uint(x), __float_as_uint(mu), (uint32_t)cell | ((uint32_t)g << 16), gen_local * P.G);
         out[2 * i + 1] = make_uint4((uint32_t)rng, (uint32_t)(rng >> 32), 0u, 0u);
     }
 }
 
 template <int TG> cudaError_t launch_g(const TransportParams &p, bool bank, uint4 *out, cudaStream_t s)
 {
-    const uint64_t n = p.hist_end - p.hist_begin;
+    const uint64_t n = (uint64_t)(p.rows / p.G) * p.hist_shard;
     const unsigned blocks = (unsigned)((n + 256ull * kRun - 1) / (256ull * kRun));
     if (!blocks) return cudaSuccess;
     if (bank) source_kernel<TG, true><<<blocks, 256, 0, s>>>(p, out);

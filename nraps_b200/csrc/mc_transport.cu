@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G;
     const int M = (int)P.M, N = (int)P.N;
-    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG);
+    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG, P.rows);
 
     const SmemView S = load_block_tables(smem_raw, P, L);
     uint32_t *s_lo = S.lo;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     bool alive = false, pending = false;
     uint64_t rng = 0, y = 0;
     float x = 0.f, mu = 1.f, ds = 0.f;
-    int cell = 0, g = 0, xsg = 0, mat = 0, run_lo = 0, run_hi = 0;
+    int cell = 0, g = 0, xsg = 0, mat = 0, run_lo = 0, run_hi = 0, row0 = 0;
     uint32_t h_coll = 0, h_cross = 0, h_flight = 0, h_refl = 0, h_bank = 0; // this history
     uint32_t c_hist = 0, c_coll = 0, c_cross = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0, c_bank = 0;
 
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     mu = __uint_as_float(r0.y);
                     cell = (int)(r0.z & 0xffffu);
                     g = (int)(r0.z >> 16);
+                    row0 = (int)r0.w; // first tally row of this history's generation (0 unless generations are batched)
                     rng = (uint64_t)r1.x | ((uint64_t)r1.y << 32);
                     mat = s_matid[cell];
                     xsg = g;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 int wall = fwd ? N - 1 : 0;
                 int run_exit = fwd ? run_hi : run_lo - 1;
                 uint32_t e_addr = edges_base + (uint32_t)(kStep * (cell + fwd)); // edge ahead of the neutron
-                uint32_t t_addr = tally_ref<BIG>(lo_base, g * N + cell);         // tally[g][cell]
+                uint32_t t_addr = tally_ref<BIG>(lo_base, (row0 + g) * N + cell);         // tally[g][cell]
                 // The hot loop below has two ways out and no wall logic.  The domain-boundary cell in the direction
                 // of travel is handled here, before the loop (src/mc_code.rs:159-170): a lane that reaches it
                 // inside the loop stops there (it is its stop_cell) and comes back through this block next trip.
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
 
         // ---------------- COLLIDE / material change
         if (ev == EV_COLLIDE) {
-            score<BIG>(tally_ref<BIG>(lo_base, g * N + cell), hi_off, fabsf(fast_div(fsub(x, end), rc)), P.tally);
+            score<BIG>(tally_ref<BIG>(lo_base, (row0 + g) * N + cell), hi_off, fabsf(fast_div(fsub(x, end), rc)), P.tally);
             ++h_coll;
             const int xs = mat + M * xsg; // stale group index, src/mc_code.rs:147
             const float xi_int = pcg32_unit(rng, inc);

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G;
     const int M = (int)P.M, N = (int)P.N, NB = (int)P.NB;
-    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG);
+    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG, P.rows);
     const SmemView S = load_block_tables(smem_raw, P, L);
     const float *s_edges = S.edges, *s_xs = S.xs;
     const uint32_t *s_runb = S.runb;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
     bool alive = false, left = false;
     uint64_t rng = 0, y = 0;
     float x = 0.f, mu = 1.f;
-    int cell = 0, g = 0, xsg = 0, home_lo = 0, home_hi = 0;
+    int cell = 0, g = 0, xsg = 0, home_lo = 0, home_hi = 0, row0 = 0;
     uint32_t h_coll = 0, h_flight = 0, h_refl = 0, h_bank = 0;
     uint32_t c_hist = 0, c_coll = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0, c_bank = 0;
 
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
                     mu = __uint_as_float(r0.y);
                     cell = (int)(r0.z & 0xffffu);
                     g = (int)(r0.z >> 16);
+                    row0 = (int)r0.w; // first tally row of this history's generation (0 unless generations are batched)
                     rng = (uint64_t)r1.x | ((uint64_t)r1.y << 32);
                     xsg = g;
                     const uint32_t rb = s_runb[cell];
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
             left = left || cell < home_lo || cell >= home_hi;
             mat = s_matid[cell];
             g_eff = left ? g : xsg;
-            score<BIG>(tally_ref<BIG>(lo_base, g * N + cell), hi_off, inv_maj, P.tally);
+            score<BIG>(tally_ref<BIG>(lo_base, (row0 + g) * N + cell), hi_off, inv_maj, P.tally);
             accepted = pcg32_unit(rng, inc) < fmul(s_sigtr[mat + M * g_eff], inv_maj);
         }
         __syncwarp();

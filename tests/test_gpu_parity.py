@@ -108,6 +108,22 @@ def test_replay_every_history_bit_exact(case, gen):
     assert rec[:, 0].max() > 100 and rec[:, 8].min() == 1  # long tails exist; every history was absorbed
 
 
+@pytest.mark.parametrize("case,tracking,H,gens", [("a", "surface", 501, 70), ("c", "surface", 3001, 9),
+                                                  ("b", "woodcock", 2000, 11)])
+def test_batched_generations_bit_exact(case, tracking, H, gens):
+    """nraps_mc_run lets one launch carry several small uniform-source generations (each into its own tally rows);
+    every per-generation tally, k and the folded results must equal the oracle's one-generation-at-a-time run, and
+    the generation-level API (one generation per launch) must give the same tallies."""
+    got, want = _both(case, generations=gens, histories=H, skip=2, tracking_mode=tracking)
+    _assert_identical(got, want)
+    v, xs, dx, mesh, fuel = load_case(case)
+    with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=2, tracking_mode=tracking) as ctx:
+        for gen in (0, gens // 2, gens - 1):
+            ctx.transport(gen)
+            tally, _ = ctx.read_tally()
+            assert np.array_equal(tally, got.tally_fixed[gen])
+
+
 @pytest.mark.parametrize("case,H,gens,skip", [("a", 100_000, 6, 4), ("b", 150_000, 3, 1), ("c", 150_000, 3, 1)])
 def test_results_bit_exact(case, H, gens, skip):
     got, want = _both(case, generations=gens, histories=H, skip=skip)

@@ -7,6 +7,7 @@
  *   nraps_plot_solution ... src/plot_solution.rs:7-58 (without spawning plot.py)
  *   nraps_average_assembly  src/mc_code.rs:259-274
  *   nraps_k_fund .......... src/mc_code.rs:368-376
+ *   nraps_diffusion_run ... src/discrete.rs:181-356 (nalgebra_method, the reference's other solver; cross-check only)
  */
 #ifndef NRAPS_HOST_H
 #define NRAPS_HOST_H
@@ -54,12 +55,21 @@ int nraps_problem_from(const nraps_deck *d, const nraps_mesh *m, float k0, nraps
 /* Rust `f32::to_string()` / `f64::to_string()`: shortest round-trip digits, positional notation. */
 size_t nraps_format_f32(float v, char *buf, size_t cap);
 size_t nraps_format_f64(double v, char *buf, size_t cap);
-/* writes <dir>/vars.csv, interface.csv, k_eff.csv */
+/* writes <dir>/vars.csv, interface.csv, k_eff.csv; with r->fission_source or r->k_fund NULL (diffusion results) only
+ * vars.csv and the 2G flux rows of interface.csv, which is what the reference's writer leaves behind in that case */
 int nraps_plot_solution(const nraps_results *r, uint32_t G, uint64_t generations, uint32_t N,
                         double assembly_length, const char *dir);
 
 void nraps_average_assembly(const float *flux, uint32_t G, uint32_t N, uint32_t numass, float *out);
 void nraps_k_fund(const float *k, uint64_t generations, uint64_t skip, float *out);
+
+/* Finite-difference diffusion eigenvalue solve of the same problem (src/discrete.rs:181-356): fills r->flux[G*N],
+ * r->assembly_average[G*N] and r->k[0]; fission_source and k_fund are not produced (the reference returns empty
+ * vectors, :351-353).  generations / histories / skip of the problem are ignored.  max_iterations = 0 means 100000
+ * (the reference loops without bound); *iterations (optional) receives the number of power iterations.  The dense
+ * f32 inverse of the reference is replaced by an f64 tridiagonal elimination: equal to the rounding noise of that
+ * inverse, not bit for bit. */
+int nraps_diffusion_run(const nraps_problem *p, nraps_results *r, uint64_t max_iterations, uint64_t *iterations);
 
 #ifdef __cplusplus
 }

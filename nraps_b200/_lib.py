@@ -84,6 +84,7 @@ EXPORTS = [
     "nraps_strerror", "nraps_last_cuda_error", "nraps_abi_version",
     "nraps_process_input", "nraps_deck_free", "nraps_mesh_gen", "nraps_mesh_free", "nraps_problem_from",
     "nraps_format_f32", "nraps_format_f64", "nraps_plot_solution", "nraps_average_assembly", "nraps_k_fund",
+    "nraps_diffusion_run",
 ]
 
 _lib = None
@@ -137,6 +138,7 @@ def lib() -> C.CDLL:
     L.nraps_average_assembly.restype = None
     L.nraps_k_fund.argtypes = [_fp, C.c_uint64, C.c_uint64, _fp]
     L.nraps_k_fund.restype = None
+    L.nraps_diffusion_run.argtypes = [C.POINTER(Problem), C.POINTER(Results), C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 

@@ -219,6 +219,21 @@ def monte_carlo(variables, xsdata, delta_x, meshid, fuel_indices, k_new: float =
     return rb.solution()
 
 
+def nalgebra_method(xsdata, meshid, energygroups: int, mattypes: int, boundl: float, boundr: float, numass: int,
+                    *, max_iterations: int = 0) -> SolutionResults:
+    """src/discrete.rs:181-356: the reference's finite-difference diffusion solver (host code), kept as a physics
+    cross-check of the Monte Carlo path.  Returns flux, assembly_average and k = [k]; fission_source and k_fund are
+    empty like the reference's.  ``counters["iterations"]`` holds the number of power iterations."""
+    v = Variables(analk=0, mattypes=mattypes, energygroups=energygroups, generations=1, histories=1, skip=0,
+                  numass=numass, numrods=0, roddia=0.0, rodpitch=0.0, mpfr=0, mpwr=0, boundl=boundl, boundr=boundr)
+    m = _Marshalled(v, xsdata, DeltaX(0.0, 0.0), meshid, np.zeros(0, np.uint64), 1.0, None, None, None)
+    rb = _ResultBuffers(m.G, m.N, 1)
+    it = C.c_uint64(0)
+    check(lib().nraps_diffusion_run(C.byref(m.problem), C.byref(rb.c), max_iterations, C.byref(it)), "nalgebra_method")
+    return SolutionResults(flux=rb.flux, assembly_average=rb.avg, fission_source=np.zeros(0, np.float32), k=rb.k,
+                           k_fund=np.zeros(0, np.float32), counters={"iterations": int(it.value)})
+
+
 class MonteCarloContext:
     """Generation-level control of one GPU: transport -> (all-reduce) -> finalize."""
 
@@ -326,10 +341,11 @@ class MonteCarloContext:
 
 def plot_solution(results: SolutionResults, energygroups: int, generations: int, number_meshes: int,
                   assembly_length: float, out_dir: str = ".") -> None:
-    """src/plot_solution.rs:7-58: writes vars.csv, interface.csv, k_eff.csv (plot.py is not spawned)."""
+    """src/plot_solution.rs:7-58: writes vars.csv, interface.csv, k_eff.csv (plot.py is not spawned).  Diffusion
+    results (empty fission_source / k_fund) leave vars.csv and the 2G flux rows of interface.csv, like the reference."""
     f = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
     keep = [f(results.flux), f(results.assembly_average), f(results.fission_source), f(results.k), f(results.k_fund)]
-    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_float)) if a.size else None  # noqa: E731
     r = Results(flux=p(keep[0]), assembly_average=p(keep[1]), fission_source=p(keep[2]), k=p(keep[3]), k_fund=p(keep[4]))
     check(lib().nraps_plot_solution(C.byref(r), energygroups, generations, number_meshes, C.c_double(assembly_length),
                                     os.fsencode(out_dir)), "plot_solution")

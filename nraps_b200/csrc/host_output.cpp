@@ -80,7 +80,11 @@ extern "C" size_t nraps_format_f64(double v, char *buf, size_t cap) { return emi
 extern "C" int nraps_plot_solution(const nraps_results *r, uint32_t G, uint64_t generations, uint32_t N,
                                    double assembly_length, const char *dir)
 {
-    if (!r || !r->flux || !r->assembly_average || !r->fission_source || !r->k || !r->k_fund) return NRAPS_ERR_NULL;
+    if (!r || !r->flux || !r->assembly_average || !r->k) return NRAPS_ERR_NULL;
+    // Diffusion results carry no fission source and no k_fund (src/discrete.rs:351-353).  The reference's writer then
+    // fails on the empty fission record (csv UnequalLengths) after the 2G flux rows and never opens k_eff.csv; the
+    // caller discards the error (`let _ =`, src/main.rs:358).  NULL fission_source / k_fund reproduce those files.
+    const bool diffusion = !r->fission_source || !r->k_fund;
     const std::string base = (dir && *dir) ? std::string(dir) + "/" : std::string("./");
 
     std::FILE *fh = std::fopen((base + "vars.csv").c_str(), "wb");
@@ -93,9 +97,10 @@ extern "C" int nraps_plot_solution(const nraps_results *r, uint32_t G, uint64_t 
     bool ok = true;
     for (uint32_t g = 0; g < G; ++g) ok = ok && write_row(fh, r->flux + (size_t)g * N, N);
     for (uint32_t g = 0; g < G; ++g) ok = ok && write_row(fh, r->assembly_average + (size_t)g * N, N);
-    ok = ok && write_row(fh, r->fission_source, N);
+    if (!diffusion) ok = ok && write_row(fh, r->fission_source, N);
     std::fclose(fh);
     if (!ok) return NRAPS_ERR_IO;
+    if (diffusion) return NRAPS_OK;
 
     fh = std::fopen((base + "k_eff.csv").c_str(), "wb");
     if (!fh) return NRAPS_ERR_IO;

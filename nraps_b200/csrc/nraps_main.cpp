@@ -5,6 +5,7 @@
 //              [--seed S --stream Q --stride T] [--device D] [--scatter single_xi|rust_pre182|rust_182]
 //              [--generation-log]  (one JSON line per generation on stderr: k, k_fund, bank size, source entropy)
 //              [--fix-stale-xs] [--quiet] [--gpus N] [--tracking surface|woodcock] [--source uniform_fuel|fission_bank]
+//              [--solution mc|diffusion]  (diffusion = the reference's finite-difference solver, host code, cross-check only)
 // The deck defaults to ./TestCaseC.txt like the reference (src/process_input.rs:86).
 #include <chrono>
 #include <cstdio>
@@ -25,7 +26,7 @@ int main(int argc, char **argv)
     opt.stale_xs = 1;
     long long gens = -1, hist = -1, skip = -1;
     int gpus = 1;
-    bool gen_log = false;
+    bool gen_log = false, diffusion = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&](const char *what) -> const char * {
@@ -46,6 +47,7 @@ int main(int argc, char **argv)
         else if (a == "--gpus") gpus = std::atoi(next("--gpus"));
         else if (a == "--tracking") opt.tracking_mode = std::string(next("--tracking")) == "woodcock" ? NRAPS_TRACK_WOODCOCK : NRAPS_TRACK_SURFACE;
         else if (a == "--source") opt.source_mode = std::string(next("--source")) == "fission_bank" ? NRAPS_SOURCE_FISSION_BANK : NRAPS_SOURCE_UNIFORM_FUEL;
+        else if (a == "--solution") diffusion = std::string(next("--solution")) == "diffusion";
         else if (a == "--scatter") {
             const std::string m = next("--scatter");
             opt.scatter_mode = m == "rust_pre182" ? NRAPS_SCATTER_RUST_PRE182 : m == "rust_182" ? NRAPS_SCATTER_RUST_182 : NRAPS_SCATTER_SINGLE_XI;
@@ -77,6 +79,21 @@ int main(int argc, char **argv)
     std::vector<uint64_t> bank_sizes(prob.generations);
     std::vector<double> entropy(prob.generations);
     res.bank_sizes = bank_sizes.data(); res.entropy = entropy.data();
+    if (diffusion) { // the reference's other solver (src/main.rs:338-346, src/discrete.rs), host code, cross-check only
+        uint64_t iterations = 0;
+        rc = nraps_diffusion_run(&prob, &res, 0, &iterations);
+        if (rc != NRAPS_OK) { std::fprintf(stderr, "nalgebra_method: %s\n", nraps_strerror(rc)); return 1; }
+        std::printf("%.10f\n", (double)k[0]); // src/discrete.rs:347
+        res.fission_source = nullptr; res.k_fund = nullptr;
+        rc = nraps_plot_solution(&res, prob.G, prob.generations, prob.N, (double)mesh.right[mesh.N - 1], out_dir.c_str());
+        if (rc != NRAPS_OK) { std::fprintf(stderr, "plot_solution: %s\n", nraps_strerror(rc)); return 1; }
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("Run was completed in %lld milliseconds \n", (long long)(wall * 1e3));
+        std::fprintf(stderr, "{\"k\": %.7g, \"iterations\": %llu}\n", (double)k[0], (unsigned long long)iterations);
+        nraps_mesh_free(&mesh);
+        nraps_deck_free(&deck);
+        return 0;
+    }
     if (gpus > 1) { // all GPUs of the box through libnraps_b200_nccl.so (loaded on demand: the core has no NCCL dependency)
         void *h = dlopen("libnraps_b200_nccl.so", RTLD_NOW);
         auto fn = h ? reinterpret_cast<decltype(&nraps_mc_run_multi)>(dlsym(h, "nraps_mc_run_multi")) : nullptr;

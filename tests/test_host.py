@@ -12,7 +12,7 @@ import nraps_b200 as nb
 from nraps_b200 import _lib
 from oracle import host_oracle as ho
 from oracle import oracle as orc
-from tests.util import DECKS, ROOT, bits, load_case
+from tests.util import DECKS, ROOT, bits, load_case, oracle_inputs
 
 f32 = np.float32
 
@@ -185,3 +185,51 @@ def test_nccl_driver_library_exports_its_entry_point():
     except OSError as e:  # libnccl.so.2 not installed on this host
         pytest.skip(str(e))
     assert L.nraps_mc_run_multi(None, None, None, 2, None) == 1  # NRAPS_ERR_NULL before any CUDA / NCCL call
+
+
+# ---- diffusion solver (src/discrete.rs), SURVEY 8(f) rank 4: cross-check of the Monte Carlo path -------------------
+# parity unpinned: the reference holds no test for this solver and inverts with nalgebra (f32 LU); the oracle inverts
+# with LAPACK and the library eliminates the tridiagonal system in f64, so agreement is to the rounding noise of an f32
+# dense inverse, stated below, not bit for bit.
+DIFFUSION_FLUX_RTOL = 2e-4
+DIFFUSION_K_RTOL = 5e-6
+
+
+@pytest.mark.parametrize("case,bl,br", [("a", None, None), ("b", None, None), ("c", None, None), ("c", 0.0, 1.0),
+                                        ("b", 0.5, 0.0), ("a", 0.3, 0.7)])
+def test_diffusion_solver_matches_the_restatement(case, bl, br):
+    import dataclasses
+
+    from oracle import diffusion_oracle as dif
+    v, xs, dx, mesh, fuel = load_case(case)
+    if bl is not None:
+        v = dataclasses.replace(v, boundl=bl, boundr=br)
+    got = nb.nalgebra_method(xs, mesh, v.energygroups, v.mattypes, v.boundl, v.boundr, v.numass)
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = dif.nalgebra_method(deck, m)
+    # the stop test compares f32 noise with 1e-5 / 1e-6: the last iteration may fall on either side
+    assert abs(got.counters["iterations"] - want.iterations) <= 1
+    assert abs(got.k[0] / want.k - 1) < DIFFUSION_K_RTOL
+    assert np.abs(got.flux / want.flux - 1).max() < DIFFUSION_FLUX_RTOL
+    assert np.abs(got.assembly_average / want.assembly_average - 1).max() < DIFFUSION_FLUX_RTOL
+    assert got.fission_source.size == 0 and got.k_fund.size == 0 and got.k.size == 1  # src/discrete.rs:349-355
+    if case == "a" and bl is None:
+        # deck A is one fuel material between reflecting walls with mu = 0: k = nu*Sigma_f / Sigma_a = 1.26 for any
+        # flux shape -- the same analytic anchor the Monte Carlo path meets with the stale-index quirk off
+        assert abs(got.k[0] - 1.26) < 5e-5
+
+
+def test_diffusion_driver_and_csv(tmp_path):
+    import subprocess
+
+    exe = os.path.join(ROOT, "nraps_b200", "lib", "nraps")
+    out = subprocess.run([exe, DECKS["c"], "--out", str(tmp_path), "--solution", "diffusion"],
+                         check=True, capture_output=True, text=True)
+    v, xs, dx, mesh, fuel = load_case("c")
+    got = nb.nalgebra_method(xs, mesh, v.energygroups, v.mattypes, v.boundl, v.boundr, v.numass)
+    assert out.stdout.splitlines()[0] == f"{got.k[0]:.10f}"  # println!("{:.10}", k), src/discrete.rs:347
+    rows = open(tmp_path / "interface.csv").read().splitlines()
+    assert len(rows) == 2 * v.energygroups and not (tmp_path / "k_eff.csv").exists()
+    assert rows[0].split(",")[0] == nb.format_f32(float(got.flux[0, 0]))
+    nb.plot_solution(got, v.energygroups, v.generations, len(mesh), float(mesh.mesh_right[-1]), str(tmp_path))
+    assert open(tmp_path / "interface.csv").read().splitlines() == rows

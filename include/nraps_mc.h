@@ -110,7 +110,10 @@ typedef struct nraps_results {
 
 typedef struct nraps_mc_ctx nraps_mc_ctx;
 
-/* Whole job on one GPU: the monte_carlo() replacement. */
+/* Whole job on one GPU: the monte_carlo() replacement (src/mc_code.rs:276-380).  With the uniform source, generations
+ * are independent, so one launch carries several small generations (up to ~2^23 histories, each generation scoring
+ * into its own tally rows) and they are folded in order afterwards: results are bit-identical to one launch per
+ * generation, which is what the generation-level API below always does. */
 int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nraps_results *r);
 
 /*

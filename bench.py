@@ -292,6 +292,7 @@ def run_ours(a):
                        "launch": info, "l2": "256 MiB device memset between steps inside the timed region (kernel inputs are ~12 KB of tables)"},
             "clocks": clocks,
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                    "wall_s": e2e_s, "device_s": float(getattr(e2e_res, "seconds_device", 0.0)),
                     "note": "one monte_carlo() call: context create + table upload + K generations + result download; bytes are per run / K"},
             "gpu_launches": (3 + (5 if has_bank else 0)) * K,  # source + transport + finalize (+ bank compaction / entropy)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

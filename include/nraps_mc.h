@@ -125,6 +125,10 @@ int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nraps_results *
  */
 int nraps_mc_create(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **out);
 int nraps_mc_destroy(nraps_mc_ctx *ctx);
+/* Device buffers come from a library-owned memory pool per device that keeps up to 2 GiB mapped after
+ * nraps_mc_destroy / nraps_mc_run, so that the next context does not pay the driver's allocation cost again
+ * (50-300 ms per context, measured).  nraps_mc_trim hands that memory back to the driver. */
+int nraps_mc_trim(int32_t device);
 int nraps_mc_reset(nraps_mc_ctx *ctx, float k0, void *stream);
 int nraps_mc_transport(nraps_mc_ctx *ctx, uint64_t gen, uint64_t hist_begin, uint64_t hist_count, void *stream);
 int nraps_mc_finalize_generation(nraps_mc_ctx *ctx, uint64_t gen, void *stream);

@@ -8,7 +8,7 @@ fails on first use.
 """
 from .api import (  # noqa: F401
     DeltaX, Mesh, MonteCarloContext, SolutionResults, Variables, XSData, dev_div, dev_logf, dev_pcg32, format_f32, format_f64,
-    make_options, mesh_gen, monte_carlo, nalgebra_method, plot_solution, process_input,
+    make_options, mesh_gen, monte_carlo, nalgebra_method, plot_solution, process_input, trim,
 )
 from .dist import monte_carlo_distributed, shard_range  # noqa: F401
 

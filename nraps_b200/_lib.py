@@ -77,7 +77,7 @@ class Mesh(C.Structure):
 
 # every symbol include/nraps_mc.h and include/nraps_host.h declare
 EXPORTS = [
-    "nraps_mc_run", "nraps_mc_create", "nraps_mc_destroy", "nraps_mc_reset", "nraps_mc_transport",
+    "nraps_mc_run", "nraps_mc_create", "nraps_mc_destroy", "nraps_mc_trim", "nraps_mc_reset", "nraps_mc_transport",
     "nraps_mc_finalize_generation", "nraps_mc_tally_buffer", "nraps_mc_set_tally_buffer", "nraps_mc_read_tally",
     "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_mc_bank_compact", "nraps_mc_bank_local",
     "nraps_mc_bank_set_source", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     L.nraps_mc_run.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(Results)]
     L.nraps_mc_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(vp)]
     L.nraps_mc_destroy.argtypes = [vp]
+    L.nraps_mc_trim.argtypes = [C.c_int32]
     L.nraps_mc_reset.argtypes = [vp, C.c_float, vp]
     L.nraps_mc_transport.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
     L.nraps_mc_finalize_generation.argtypes = [vp, C.c_uint64, vp]

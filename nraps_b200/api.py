@@ -351,6 +351,11 @@ def plot_solution(results: SolutionResults, energygroups: int, generations: int,
                                     os.fsencode(out_dir)), "plot_solution")
 
 
+def trim(device: int = 0) -> None:
+    """Hand the device memory the library keeps cached between contexts back to the driver (nraps_mc_trim)."""
+    check(lib().nraps_mc_trim(device), "trim")
+
+
 def format_f32(v: float) -> str:
     buf = C.create_string_buffer(96)
     lib().nraps_format_f32(C.c_float(v), buf, 96)

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -75,9 +76,60 @@ void pcg_jump_coeffs(uint64_t inc, uint64_t delta, uint64_t *mult, uint64_t *plu
     *plus = ap;
 }
 
+// Device buffers come from a library-owned stream-ordered pool per device instead of cudaMalloc / cudaFree: driver
+// allocation calls cost 50-300 ms per context on the gpurun boxes (a 320 MB birth-record buffer mapped and unmapped
+// per monte_carlo() call), which made the end-to-end time of a 0.3 s run vary by 2x.  The pool keeps up to 2 GiB
+// mapped between contexts (nraps_mc_trim releases it); both wrappers keep cudaMalloc's / cudaFree's synchronous
+// contract, so callers need no stream ordering.
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {};
+
+cudaError_t device_pool(cudaMemPool_t *out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if ((e = cudaMemPoolCreate(&pool, &props)) != cudaSuccess) return e;
+        uint64_t keep = 2ull << 30;
+        if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) {
+            cudaMemPoolDestroy(pool);
+            return e;
+        }
+        g_pools[dev] = pool;
+    }
+    *out = g_pools[dev];
+    return cudaSuccess;
+}
+
+cudaError_t dev_malloc(void **p, size_t bytes)
+{
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = device_pool(&pool);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMallocFromPoolAsync(p, bytes, pool, nullptr)) != cudaSuccess) return e;
+    return cudaStreamSynchronize(nullptr); // from here on the buffer may be used on any stream
+}
+
+cudaError_t dev_free(void *p)
+{
+    if (!p) return cudaSuccess;
+    cudaError_t e = cudaDeviceSynchronize(); // like cudaFree: nothing in flight may still use the buffer
+    if (e != cudaSuccess) return e;
+    return cudaFreeAsync(p, nullptr);
+}
+
 template <typename T> cudaError_t upload(T **dst, const std::vector<T> &src)
 {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), std::max<size_t>(1, src.size()) * sizeof(T));
+    cudaError_t e = dev_malloc(reinterpret_cast<void **>(dst), std::max<size_t>(1, src.size()) * sizeof(T));
     if (e != cudaSuccess) return e;
     if (src.empty()) return cudaSuccess;
     return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
@@ -174,15 +226,15 @@ int validate(const nraps_problem *p, const nraps_options *o)
 void free_ctx(nraps_mc_ctx *c)
 {
     if (!c) return;
-    cudaFree(c->d_edges); cudaFree(c->d_xs); cudaFree(c->d_dx); cudaFree(c->d_nut); cudaFree(c->d_sigf);
-    cudaFree(c->d_runb); cudaFree(c->d_matid); cudaFree(c->d_fuel); cudaFree(c->d_jump); cudaFree(c->d_bucket);
-    cudaFree(c->d_tally_own); cudaFree(c->d_work); cudaFree(c->d_counters_total);
-    cudaFree(c->d_terms); cudaFree(c->d_res_flux); cudaFree(c->d_res_fission); cudaFree(c->d_k_hist); cudaFree(c->d_k_cur);
-    cudaFree(c->d_trace); cudaFree(c->d_source);
-    cudaFree(c->d_slots); cudaFree(c->d_block_sums); cudaFree(c->d_dense[0]); cudaFree(c->d_dense[1]);
-    for (EventHalf &h : c->ev.half) { cudaFree(h.x); cudaFree(h.mu); cudaFree(h.pack); cudaFree(h.cnt); cudaFree(h.ccnt); cudaFree(h.rng); }
-    cudaFree(c->ev.n_alive);
-    cudaFree(c->d_bank_count); cudaFree(c->d_bank_sizes); cudaFree(c->d_entropy); cudaFree(c->d_counts); cudaFree(c->d_hist);
+    dev_free(c->d_edges); dev_free(c->d_xs); dev_free(c->d_dx); dev_free(c->d_nut); dev_free(c->d_sigf);
+    dev_free(c->d_runb); dev_free(c->d_matid); dev_free(c->d_fuel); dev_free(c->d_jump); dev_free(c->d_bucket);
+    dev_free(c->d_tally_own); dev_free(c->d_work); dev_free(c->d_counters_total);
+    dev_free(c->d_terms); dev_free(c->d_res_flux); dev_free(c->d_res_fission); dev_free(c->d_k_hist); dev_free(c->d_k_cur);
+    dev_free(c->d_trace); dev_free(c->d_source);
+    dev_free(c->d_slots); dev_free(c->d_block_sums); dev_free(c->d_dense[0]); dev_free(c->d_dense[1]);
+    for (EventHalf &h : c->ev.half) { dev_free(h.x); dev_free(h.mu); dev_free(h.pack); dev_free(h.cnt); dev_free(h.ccnt); dev_free(h.rng); }
+    dev_free(c->ev.n_alive);
+    dev_free(c->d_bank_count); dev_free(c->d_bank_sizes); dev_free(c->d_entropy); dev_free(c->d_counts); dev_free(c->d_hist);
     delete c;
 }
 
@@ -190,17 +242,17 @@ int ensure_event_bank(nraps_mc_ctx *c, uint64_t count)
 {
     if (count <= c->ev_cap) return NRAPS_OK;
     for (EventHalf &h : c->ev.half) {
-        cudaFree(h.x); cudaFree(h.mu); cudaFree(h.pack); cudaFree(h.cnt); cudaFree(h.ccnt); cudaFree(h.rng);
+        dev_free(h.x); dev_free(h.mu); dev_free(h.pack); dev_free(h.cnt); dev_free(h.ccnt); dev_free(h.rng);
         h = EventHalf{};
-        CU(cudaMalloc((void **)&h.x, count * sizeof(float)));
-        CU(cudaMalloc((void **)&h.mu, count * sizeof(float)));
-        CU(cudaMalloc((void **)&h.pack, count * sizeof(uint32_t)));
-        CU(cudaMalloc((void **)&h.cnt, count * sizeof(uint32_t)));
-        CU(cudaMalloc((void **)&h.ccnt, count * sizeof(uint32_t)));
-        CU(cudaMalloc((void **)&h.rng, count * sizeof(unsigned long long)));
+        CU(dev_malloc((void **)&h.x, count * sizeof(float)));
+        CU(dev_malloc((void **)&h.mu, count * sizeof(float)));
+        CU(dev_malloc((void **)&h.pack, count * sizeof(uint32_t)));
+        CU(dev_malloc((void **)&h.cnt, count * sizeof(uint32_t)));
+        CU(dev_malloc((void **)&h.ccnt, count * sizeof(uint32_t)));
+        CU(dev_malloc((void **)&h.rng, count * sizeof(unsigned long long)));
     }
     if (!c->ev.n_alive) {
-        CU(cudaMalloc((void **)&c->ev.n_alive, 2 * sizeof(unsigned long long)));
+        CU(dev_malloc((void **)&c->ev.n_alive, 2 * sizeof(unsigned long long)));
         c->ev.n_next = c->ev.n_alive + 1;
     }
     c->ev_cap = count;
@@ -211,17 +263,17 @@ int ensure_event_bank(nraps_mc_ctx *c, uint64_t count)
 int ensure_bank(nraps_mc_ctx *c, uint64_t count)
 {
     if (count <= c->bank_hist_cap) return NRAPS_OK;
-    cudaFree(c->d_slots); cudaFree(c->d_counts); cudaFree(c->d_block_sums); cudaFree(c->d_dense[0]); cudaFree(c->d_dense[1]);
+    dev_free(c->d_slots); dev_free(c->d_counts); dev_free(c->d_block_sums); dev_free(c->d_dense[0]); dev_free(c->d_dense[1]);
     c->d_slots = c->d_block_sums = c->d_dense[0] = c->d_dense[1] = nullptr;
     c->d_counts = nullptr;
     c->bank_hist_cap = 0;
     const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
     c->dense_cap = 3 * count + 1024; // a bank larger than 3 sites per history is truncated (k / k_prev > 3)
-    CU(cudaMalloc((void **)&c->d_slots, padded * c->bank_cap * sizeof(unsigned long long)));
-    CU(cudaMalloc((void **)&c->d_counts, padded));
-    CU(cudaMalloc((void **)&c->d_block_sums, (padded / kBankTile) * sizeof(unsigned long long)));
-    CU(cudaMalloc((void **)&c->d_dense[0], c->dense_cap * sizeof(unsigned long long)));
-    CU(cudaMalloc((void **)&c->d_dense[1], c->dense_cap * sizeof(unsigned long long)));
+    CU(dev_malloc((void **)&c->d_slots, padded * c->bank_cap * sizeof(unsigned long long)));
+    CU(dev_malloc((void **)&c->d_counts, padded));
+    CU(dev_malloc((void **)&c->d_block_sums, (padded / kBankTile) * sizeof(unsigned long long)));
+    CU(dev_malloc((void **)&c->d_dense[0], c->dense_cap * sizeof(unsigned long long)));
+    CU(dev_malloc((void **)&c->d_dense[1], c->dense_cap * sizeof(unsigned long long)));
     c->bank_hist_cap = count;
     return NRAPS_OK;
 }
@@ -266,9 +318,9 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     if (c->opt.kernel_variant != NRAPS_KERNEL_EVENT) { // births first, every lane busy; the transport lanes adopt them
         const uint64_t births = (uint64_t)nb * count;
         if (births > c->source_cap) {
-            CU(cudaFree(c->d_source));
+            CU(dev_free(c->d_source));
             c->d_source = nullptr; c->source_cap = 0;
-            CU(cudaMalloc((void **)&c->d_source, births * 2 * sizeof(uint4)));
+            CU(dev_malloc((void **)&c->d_source, births * 2 * sizeof(uint4)));
             c->source_cap = births;
         }
         P.source = c->d_source;
@@ -306,6 +358,16 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
 }
 
 } // namespace
+
+extern "C" int nraps_mc_trim(int32_t device)
+{
+    CU(cudaSetDevice(device));
+    cudaMemPool_t pool = nullptr;
+    CU(device_pool(&pool));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return NRAPS_OK;
+}
 
 extern "C" int nraps_abi_version(void) { return NRAPS_ABI_VERSION; }
 extern "C" const char *nraps_last_cuda_error(void) { return g_cuda_error.c_str(); }
@@ -368,9 +430,10 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     CU(cudaGetDeviceCount(&ndev));
     if (o->device < 0 || o->device >= ndev) return cuda_fail(cudaErrorInvalidDevice, "nraps_options.device");
     CU(cudaSetDevice(o->device));
-    cudaDeviceProp prop{};
-    CU(cudaGetDeviceProperties(&prop, o->device));
-    if (prop.major != 10) return cuda_fail(cudaErrorNoKernelImageForDevice, "this library is built for sm_100a only");
+    int cc_major = 0, sm_count = 0; // two attribute reads, not cudaGetDeviceProperties (tens of ms per call)
+    CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, o->device));
+    CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, o->device));
+    if (cc_major != 10) return cuda_fail(cudaErrorNoKernelImageForDevice, "this library is built for sm_100a only");
 
     nraps_mc_ctx *c = new nraps_mc_ctx();
     c->opt = *o;
@@ -378,7 +441,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     c->generations = p->generations; c->histories = p->histories; c->skip = p->skip;
     c->boundl = p->boundl; c->boundr = p->boundr; c->dx_fuel = p->dx_fuel;
     c->length = p->right[N - 1]; c->nut_m1 = p->nut[0 + M * 1]; c->k0 = p->k0;
-    c->device = o->device; c->sm_count = prop.multiProcessorCount;
+    c->device = o->device; c->sm_count = sm_count;
     const bool dflt = (o->seed == 0 && o->stream == 0 && o->stride == 0);
     c->master = pcg_seed(dflt ? 42u : o->seed, dflt ? 54u : o->stream);
     c->stride = dflt ? 152917u : o->stride;
@@ -409,10 +472,21 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
         i = j;
     }
     for (uint32_t j = 0; j < NF; ++j) fuel[j] = (uint16_t)p->fuel_indices[j];
-    {   // regroup after half of the longest material run
-        uint32_t longest = 1;
-        for (uint32_t i = 0; i < N; ++i) longest = std::max(longest, (runb[i] >> 16) - (runb[i] & 0xffffu));
-        c->walk_cap_auto = std::max(2u, (longest + 1) / 2);
+    {   // Walk cap (crossings before a warp regroups).  Lanes cross run after run roughly in step; a cap that divides
+        // every run longer than itself keeps them in step (all reach the run boundary on the same trip), any other
+        // cap leaves a short odd trip per run and the lanes drift apart.  Measured (profiles/r1_sweeps.txt): runs of
+        // 8 and 4 cells -> any cap >= 8; runs of 80 and 40 -> 20 (1.76e8 histories/s against 1.55e8 at 16 or 24).
+        // Pick the largest cap <= 24 that divides the runs longer than it (runs covering < 5 % of the cells ignored).
+        std::vector<uint32_t> cells_in_runs_of(N + 1, 0);
+        for (uint32_t i = 0; i < N; i = runb[i] >> 16) cells_in_runs_of[(runb[i] >> 16) - i] += (runb[i] >> 16) - i;
+        uint32_t cap = 0;
+        for (uint32_t cand = 24; cand >= 4 && !cap; --cand) {
+            uint32_t misfit = 0;
+            for (uint32_t len = cand + 1; len <= N; ++len)
+                if (len % cand) misfit += cells_in_runs_of[len];
+            if ((uint64_t)misfit * 20 <= N) cap = cand;
+        }
+        c->walk_cap_auto = cap ? cap : 8u;
     }
 
     std::vector<float> xs(xs_floats(M, G));
@@ -476,18 +550,18 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     ok(upload(&c->d_edges, edges)); ok(upload(&c->d_runb, runb)); ok(upload(&c->d_matid, matid));
     ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump)); ok(upload(&c->d_bucket, bucket));
     ok(upload(&c->d_dx, dx)); ok(upload(&c->d_nut, nut)); ok(upload(&c->d_sigf, sigf));
-    ok(cudaMalloc((void **)&c->d_tally_own, (batch * GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
-    ok(cudaMalloc((void **)&c->d_work, sizeof(unsigned long long)));
-    ok(cudaMalloc((void **)&c->d_counters_total, NRAPS_CT_WORDS * sizeof(unsigned long long)));
-    ok(cudaMalloc((void **)&c->d_terms, GN * sizeof(float)));
-    ok(cudaMalloc((void **)&c->d_res_flux, GN * sizeof(float)));
-    ok(cudaMalloc((void **)&c->d_res_fission, N * sizeof(float)));
-    ok(cudaMalloc((void **)&c->d_k_hist, c->generations * sizeof(float)));
-    ok(cudaMalloc((void **)&c->d_k_cur, sizeof(float)));
-    ok(cudaMalloc((void **)&c->d_bank_count, 3 * sizeof(unsigned long long)));
-    ok(cudaMalloc((void **)&c->d_bank_sizes, c->generations * sizeof(unsigned long long)));
-    ok(cudaMalloc((void **)&c->d_entropy, c->generations * sizeof(double)));
-    ok(cudaMalloc((void **)&c->d_hist, N * sizeof(uint32_t)));
+    ok(dev_malloc((void **)&c->d_tally_own, (batch * GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
+    ok(dev_malloc((void **)&c->d_work, sizeof(unsigned long long)));
+    ok(dev_malloc((void **)&c->d_counters_total, NRAPS_CT_WORDS * sizeof(unsigned long long)));
+    ok(dev_malloc((void **)&c->d_terms, GN * sizeof(float)));
+    ok(dev_malloc((void **)&c->d_res_flux, GN * sizeof(float)));
+    ok(dev_malloc((void **)&c->d_res_fission, N * sizeof(float)));
+    ok(dev_malloc((void **)&c->d_k_hist, c->generations * sizeof(float)));
+    ok(dev_malloc((void **)&c->d_k_cur, sizeof(float)));
+    ok(dev_malloc((void **)&c->d_bank_count, 3 * sizeof(unsigned long long)));
+    ok(dev_malloc((void **)&c->d_bank_sizes, c->generations * sizeof(unsigned long long)));
+    ok(dev_malloc((void **)&c->d_entropy, c->generations * sizeof(double)));
+    ok(dev_malloc((void **)&c->d_hist, N * sizeof(uint32_t)));
     c->NB = NB; c->woodcock = woodcock; c->big = big;
     c->inv_h = NB ? (float)((double)NB / (double)p->right[N - 1]) : 0.0f;
     if (e != cudaSuccess) {
@@ -497,7 +571,10 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     c->d_tally = c->d_tally_own;
     rc = nraps_mc_reset(c, c->k0, nullptr);
     if (rc != NRAPS_OK) { free_ctx(c); return rc; }
-    CU(cudaDeviceSynchronize());
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
+        free_ctx(c);
+        return cuda_fail(e, "nraps_mc_create");
+    }
     *out = c;
     return NRAPS_OK;
 }
@@ -640,9 +717,9 @@ extern "C" int nraps_mc_trace(nraps_mc_ctx *c, uint64_t gen, uint64_t hist_begin
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU(cudaSetDevice(c->device));
     if (hist_count > c->trace_cap) {
-        CU(cudaFree(c->d_trace));
+        CU(dev_free(c->d_trace));
         c->d_trace = nullptr; c->trace_cap = 0;
-        CU(cudaMalloc((void **)&c->d_trace, hist_count * NRAPS_TR_WORDS * sizeof(uint32_t)));
+        CU(dev_malloc((void **)&c->d_trace, hist_count * NRAPS_TR_WORDS * sizeof(uint32_t)));
         c->trace_cap = hist_count;
     }
     if (hist_count) CU(cudaMemsetAsync(c->d_trace, 0, hist_count * NRAPS_TR_WORDS * sizeof(uint32_t), s));
@@ -764,12 +841,12 @@ extern "C" int nraps_dev_logf(const float *x, float *out, uint32_t n, int32_t de
     if (!x || !out) return NRAPS_ERR_NULL;
     CU(cudaSetDevice(device));
     float *dx = nullptr, *dout = nullptr;
-    CU(cudaMalloc((void **)&dx, std::max<size_t>(1, n) * sizeof(float)));
-    CU(cudaMalloc((void **)&dout, std::max<size_t>(1, n) * sizeof(float)));
+    CU(dev_malloc((void **)&dx, std::max<size_t>(1, n) * sizeof(float)));
+    CU(dev_malloc((void **)&dout, std::max<size_t>(1, n) * sizeof(float)));
     CU(cudaMemcpy(dx, x, n * sizeof(float), cudaMemcpyHostToDevice));
     CU(launch_probe_logf(dx, dout, n, nullptr));
     CU(cudaMemcpy(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(dout);
+    dev_free(dx); dev_free(dout);
     return NRAPS_OK;
 }
 
@@ -778,13 +855,13 @@ extern "C" int nraps_dev_div(const float *t, const float *mu, float *out_fast, f
     if (!t || !mu || !out_fast || !out_ieee) return NRAPS_ERR_NULL;
     CU(cudaSetDevice(device));
     float *d[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (auto &p : d) CU(cudaMalloc((void **)&p, std::max<size_t>(1, n) * sizeof(float)));
+    for (auto &p : d) CU(dev_malloc((void **)&p, std::max<size_t>(1, n) * sizeof(float)));
     CU(cudaMemcpy(d[0], t, n * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d[1], mu, n * sizeof(float), cudaMemcpyHostToDevice));
     CU(launch_probe_div(d[0], d[1], d[2], d[3], n, nullptr));
     CU(cudaMemcpy(out_fast, d[2], n * sizeof(float), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(out_ieee, d[3], n * sizeof(float), cudaMemcpyDeviceToHost));
-    for (auto &p : d) cudaFree(p);
+    for (auto &p : d) dev_free(p);
     return NRAPS_OK;
 }
 
@@ -798,11 +875,11 @@ extern "C" int nraps_dev_pcg32(uint64_t seed, uint64_t stream, uint64_t stride, 
     pcg_jump_coeffs(m.inc, hid * stride, &jm, &jp);
     uint32_t *du = nullptr;
     float *df = nullptr;
-    CU(cudaMalloc((void **)&du, std::max<size_t>(1, n) * sizeof(uint32_t)));
-    CU(cudaMalloc((void **)&df, std::max<size_t>(1, n) * sizeof(float)));
+    CU(dev_malloc((void **)&du, std::max<size_t>(1, n) * sizeof(uint32_t)));
+    CU(dev_malloc((void **)&df, std::max<size_t>(1, n) * sizeof(float)));
     CU(launch_probe_pcg(jm * m.state + jp, m.inc, n, du, df, nullptr));
     CU(cudaMemcpy(out_u32, du, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(out_unit, df, n * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(du); cudaFree(df);
+    dev_free(du); dev_free(df);
     return NRAPS_OK;
 }

@@ -179,7 +179,8 @@ def test_launch_geometry_and_sharding_do_not_change_a_bit():
     H = 70_001
     ref = None
     for kw in [dict(), dict(threads_per_block=256, blocks_per_sm=4, chunk=32), dict(threads_per_block=1024, blocks_per_sm=1, chunk=1000),
-               dict(threads_per_block=64, blocks_per_sm=1, chunk=1)]:
+               dict(threads_per_block=64, blocks_per_sm=1, chunk=1), dict(walk_cap=3), dict(walk_cap=-1),
+               dict(walk_cap=5, spawn_batch=8)]:
         with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=H, skip=1, **kw) as ctx:
             ctx.transport(1)
             tally, counters = ctx.read_tally()
@@ -252,6 +253,25 @@ def test_config3_size_properties():
         nusigf = (xs.nut * xs.sigf).reshape(v.energygroups, v.mattypes)[:, mesh.matid]
         k64 = float((tally.astype(np.float64) * 2.0 ** -28 * nusigf).sum() / H)
         assert abs(k64 - float(k)) < 2e-5 * k64
+
+
+def test_memory_pool_reuse_and_trim():
+    """Contexts draw their device buffers from a library-owned pool that stays mapped between contexts; results do not
+    depend on whether a buffer is fresh or recycled, and nraps_mc_trim gives the memory back."""
+    import torch
+    v, xs, dx, mesh, fuel = load_case("b")
+    first = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=3, histories=200_000, skip=1, want_tally=True)
+    nb.trim(0)
+    free_after_trim = torch.cuda.mem_get_info(0)[0]
+    again = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=3, histories=200_000, skip=1, want_tally=True)
+    cached = free_after_trim - torch.cuda.mem_get_info(0)[0]
+    assert cached >= 200_000 * 32  # the birth-record buffer of the last run is still mapped ...
+    third = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=3, histories=200_000, skip=1, want_tally=True,
+                           tracking_mode="surface", threads_per_block=256, blocks_per_sm=4)
+    nb.trim(0)
+    assert torch.cuda.mem_get_info(0)[0] >= free_after_trim - (8 << 20)  # ... until it is trimmed
+    for other in (again, third):
+        assert np.array_equal(first.tally_fixed, other.tally_fixed) and np.array_equal(bits(first.k), bits(other.k))
 
 
 def test_error_codes():

@@ -4,7 +4,7 @@ import time, torch, nraps_b200 as nb
 from tests.util import load_case
 args = load_case("c")
 torch.cuda.init(); torch.zeros(1, device="cuda"); torch.cuda.synchronize()
-for rep in range(3):
+for rep in range(6):
     t0=time.perf_counter()
     ctx = nb.MonteCarloContext(*args, 1.0, generations=20, histories=10_000_000, skip=1)
     t1=time.perf_counter()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NRAPS_ABI_VERSION 2
+#define NRAPS_ABI_VERSION 3
 #define NRAPS_TALLY_FRAC_BITS 28 /* tallies are exact integers in 2^-28 cm */
 
 enum {
@@ -106,6 +106,9 @@ typedef struct nraps_results {
     double seconds_device;          /* CUDA-event time of the generation loop */
     uint64_t *bank_sizes;           /* optional [generations]: sites banked by each generation (fission_bank mode) */
     double *entropy;                /* optional [generations]: Shannon entropy (bits) of that bank over mesh cells */
+    double *flux_moments;           /* optional [2][G][N] extension: over the generations >= skip, the sum and the sum of
+                                     * squares of the per-generation term flux * conversion that src/mc_code.rs:358
+                                     * accumulates (flux[] = fund * sum); gives the per-bin variance between generations */
 } nraps_results;
 
 typedef struct nraps_mc_ctx nraps_mc_ctx;

@@ -49,7 +49,7 @@ class Results(C.Structure):
     _fields_ = [
         ("flux", _fp), ("assembly_average", _fp), ("fission_source", _fp), ("k", _fp), ("k_fund", _fp),
         ("tally_fixed", _u64p), ("counters", C.c_uint64 * CT_WORDS), ("seconds_device", C.c_double),
-        ("bank_sizes", _u64p), ("entropy", C.POINTER(C.c_double)),
+        ("bank_sizes", _u64p), ("entropy", C.POINTER(C.c_double)), ("flux_moments", C.POINTER(C.c_double)),
     ]
 
 

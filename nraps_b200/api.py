@@ -88,6 +88,21 @@ class SolutionResults:  # src/main.rs:77-83
     tally_fixed: np.ndarray | None = None
     bank_sizes: np.ndarray | None = None  # fission_bank mode: sites banked per generation
     entropy: np.ndarray | None = None     # fission_bank mode: Shannon entropy (bits) of each bank over cells
+    flux_moments: np.ndarray | None = None  # extension, f64 [2][G][N]: sum and sum of squares over generations >= skip
+                                            # of the per-generation term flux * conversion (src/mc_code.rs:358)
+
+    def flux_std_error(self, generations: int, skip: int) -> np.ndarray:
+        """Standard error of ``flux`` per bin from the spread between the accumulated generations, in the units and
+        normalisation of ``flux`` (fund * sum of the per-generation terms, src/mc_code.rs:340,358)."""
+        if self.flux_moments is None:
+            raise ValueError("these results carry no flux_moments")
+        n = generations - skip
+        if n < 2:
+            return np.full(self.flux.shape, np.nan)
+        fund = 1.0 / float(np.uint64(generations - (skip - 1)))  # the reference's fund (SURVEY 9-Q5), not 1/n
+        s1, s2 = self.flux_moments
+        var = np.maximum(s2 - s1 * s1 / n, 0.0) / (n - 1)  # between generations
+        return fund * np.sqrt(var * n)
 
 
 def _np(ptr, n, dtype):
@@ -195,17 +210,19 @@ class _ResultBuffers:
         self.tally = np.zeros((gens, G, N), np.uint64) if want_tally else None
         self.bank_sizes = np.zeros(gens, np.uint64)
         self.entropy = np.zeros(gens, np.float64)
+        self.moments = np.zeros((2, G, N), np.float64)
         p = lambda a, t=C.c_float: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
         self.c = Results(flux=p(self.flux), assembly_average=p(self.avg), fission_source=p(self.fis), k=p(self.k),
                          k_fund=p(self.kf), tally_fixed=p(self.tally, C.c_uint64) if want_tally else None,
-                         bank_sizes=p(self.bank_sizes, C.c_uint64), entropy=p(self.entropy, C.c_double))
+                         bank_sizes=p(self.bank_sizes, C.c_uint64), entropy=p(self.entropy, C.c_double),
+                         flux_moments=p(self.moments, C.c_double))
 
     def solution(self) -> SolutionResults:
         return SolutionResults(
             flux=self.flux, assembly_average=self.avg, fission_source=self.fis, k=self.k, k_fund=self.kf,
             counters={n: int(self.c.counters[i]) for i, n in enumerate(CT_NAMES)},
             seconds_device=float(self.c.seconds_device), tally_fixed=self.tally, bank_sizes=self.bank_sizes,
-            entropy=self.entropy,
+            entropy=self.entropy, flux_moments=self.moments,
         )
 
 

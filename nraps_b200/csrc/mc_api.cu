@@ -160,6 +160,7 @@ struct nraps_mc_ctx {
     uint32_t batch = 1; // generations one launch may carry (small generations do not fill the GPU on their own)
     ulonglong2 *d_jump = nullptr;
     unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
+    double *d_res_moments = nullptr;
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
     uint32_t *d_trace = nullptr;
     uint64_t trace_cap = 0;
@@ -229,7 +230,7 @@ void free_ctx(nraps_mc_ctx *c)
     dev_free(c->d_edges); dev_free(c->d_xs); dev_free(c->d_dx); dev_free(c->d_nut); dev_free(c->d_sigf);
     dev_free(c->d_runb); dev_free(c->d_matid); dev_free(c->d_fuel); dev_free(c->d_jump); dev_free(c->d_bucket);
     dev_free(c->d_tally_own); dev_free(c->d_work); dev_free(c->d_counters_total);
-    dev_free(c->d_terms); dev_free(c->d_res_flux); dev_free(c->d_res_fission); dev_free(c->d_k_hist); dev_free(c->d_k_cur);
+    dev_free(c->d_res_moments); dev_free(c->d_terms); dev_free(c->d_res_flux); dev_free(c->d_res_fission); dev_free(c->d_k_hist); dev_free(c->d_k_cur);
     dev_free(c->d_trace); dev_free(c->d_source);
     dev_free(c->d_slots); dev_free(c->d_block_sums); dev_free(c->d_dense[0]); dev_free(c->d_dense[1]);
     for (EventHalf &h : c->ev.half) { dev_free(h.x); dev_free(h.mu); dev_free(h.pack); dev_free(h.cnt); dev_free(h.ccnt); dev_free(h.rng); }
@@ -555,6 +556,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     ok(dev_malloc((void **)&c->d_counters_total, NRAPS_CT_WORDS * sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_terms, GN * sizeof(float)));
     ok(dev_malloc((void **)&c->d_res_flux, GN * sizeof(float)));
+    ok(dev_malloc((void **)&c->d_res_moments, 2 * GN * sizeof(double)));
     ok(dev_malloc((void **)&c->d_res_fission, N * sizeof(float)));
     ok(dev_malloc((void **)&c->d_k_hist, c->generations * sizeof(float)));
     ok(dev_malloc((void **)&c->d_k_cur, sizeof(float)));
@@ -587,6 +589,7 @@ int finalize_slice(nraps_mc_ctx *c, uint64_t gen, uint32_t slice, uint32_t nb, c
     F.tally = c->d_tally + slice * GN;
     F.counters = slice == 0 ? c->d_tally + nb * GN : nullptr; // the launch's counters are accounted once
     F.dx = c->d_dx; F.matid = c->d_matid; F.nusigf_nut = c->d_nut; F.sigf = c->d_sigf;
+    F.res_moments = c->d_res_moments;
     F.terms = c->d_terms; F.res_flux = c->d_res_flux; F.res_fission = c->d_res_fission;
     F.k_hist = c->d_k_hist; F.k_cur = c->d_k_cur; F.counters_total = c->d_counters_total;
     F.M = c->M; F.G = c->G; F.N = c->N;
@@ -621,6 +624,7 @@ extern "C" int nraps_mc_reset(nraps_mc_ctx *c, float k0, void *stream)
     CU(cudaSetDevice(c->device));
     const uint64_t GN = (uint64_t)c->G * c->N;
     CU(cudaMemsetAsync(c->d_res_flux, 0, GN * sizeof(float), s));
+    CU(cudaMemsetAsync(c->d_res_moments, 0, 2 * GN * sizeof(double), s));
     CU(cudaMemsetAsync(c->d_res_fission, 0, c->N * sizeof(float), s));
     CU(cudaMemsetAsync(c->d_k_hist, 0, c->generations * sizeof(float), s));
     CU(cudaMemsetAsync(c->d_counters_total, 0, NRAPS_CT_WORDS * sizeof(unsigned long long), s));
@@ -681,6 +685,7 @@ extern "C" int nraps_mc_fetch(nraps_mc_ctx *c, nraps_results *r, void *stream)
     CU(cudaSetDevice(c->device));
     const uint64_t GN = (uint64_t)c->G * c->N;
     CU(cudaMemcpyAsync(r->flux, c->d_res_flux, GN * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (r->flux_moments) CU(cudaMemcpyAsync(r->flux_moments, c->d_res_moments, 2 * GN * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(r->fission_source, c->d_res_fission, c->N * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(r->k, c->d_k_hist, c->generations * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(r->counters, c->d_counters_total, NRAPS_CT_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));

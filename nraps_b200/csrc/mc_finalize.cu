@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
             const float fs = fmul(fmul(P.nusigf_nut[mat + M * g], P.sigf[mat + M * g]), flux);
             P.terms[bin] = fmul(fmul(k, dx), fs);
             if (accumulate) {
-                P.res_flux[bin] = fadd(P.res_flux[bin], fmul(fmul(flux, conversion), P.fund));
+                const float term = fmul(flux, conversion);
+                P.res_flux[bin] = fadd(P.res_flux[bin], fmul(term, P.fund));
+                P.res_moments[bin] += (double)term; // extension outputs in f64: term^2 ~ 1e38 overflows f32
+                P.res_moments[GN + bin] += (double)term * (double)term;
                 fis_acc = fadd(fis_acc, fmul(fs, P.fund));
             }
         }

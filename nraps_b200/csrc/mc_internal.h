@@ -114,6 +114,7 @@ constexpr uint32_t kBankTile = 16384; // histories per block of the compaction k
 struct FinalizeParams {
     const unsigned long long *tally; // [G*N] of this generation
     const unsigned long long *counters; // [NRAPS_CT_WORDS] of the launch, or nullptr if already accounted
+    double *res_moments;                // [2][G*N] running sum and sum of squares of flux * conversion over the accumulated generations
     const float *dx;                 // [N]
     const uint8_t *matid;            // [N]
     const float *nusigf_nut;         // nut[MG]

@@ -30,7 +30,7 @@ struct NrapsOptions {
 struct NrapsResults {
     flux: *mut f32, assembly_average: *mut f32, fission_source: *mut f32, k: *mut f32, k_fund: *mut f32,
     tally_fixed: *mut u64, counters: [u64; 8], seconds_device: f64,
-    bank_sizes: *mut u64, entropy: *mut f64,
+    bank_sizes: *mut u64, entropy: *mut f64, flux_moments: *mut f64,
 }
 
 extern "C" {
@@ -74,7 +74,7 @@ pub fn monte_carlo(
     let mut r = NrapsResults {
         flux: flux.as_mut_ptr(), assembly_average: avg.as_mut_ptr(), fission_source: fission.as_mut_ptr(),
         k: k.as_mut_ptr(), k_fund: k_fund.as_mut_ptr(), tally_fixed: std::ptr::null_mut(), counters: [0; 8],
-        seconds_device: 0.0, bank_sizes: std::ptr::null_mut(), entropy: std::ptr::null_mut(),
+        seconds_device: 0.0, bank_sizes: std::ptr::null_mut(), entropy: std::ptr::null_mut(), flux_moments: std::ptr::null_mut(),
     };
     let rc = unsafe { nraps_mc_run(&p, &o, &mut r) };
     if rc != 0 {

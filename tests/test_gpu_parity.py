@@ -255,6 +255,36 @@ def test_config3_size_properties():
         assert abs(k64 - float(k)) < 2e-5 * k64
 
 
+def test_flux_moments_extension_matches_the_per_generation_tallies():
+    """nraps_results.flux_moments (extension): sum and sum of squares over generations >= skip of flux * conversion, checked
+    in f64 against the per-generation tallies (which are bit-identical to the oracle's); tolerance = f32 rounding of
+    the per-generation term, 2e-6 relative."""
+    v, xs, dx, mesh, fuel = load_case("c")
+    gens, skip, H = 12, 3, 40_000
+    got = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=skip, want_tally=True)
+    M = v.mattypes
+    L = float(mesh.mesh_right[-1])
+    scale = 3565e6 * 36.2 / (200e6 * 1.602176634e-19 * float(xs.nut[0 + M * 1]) * L)  # conversion / k, src/mc_code.rs:353-357
+    term = got.tally_fixed[skip:].astype(np.float64) * 2.0 ** -28 / (H * mesh.delta_x.astype(np.float64)) * scale
+    assert np.allclose(got.flux_moments[0], term.sum(axis=0), rtol=2e-6, atol=0)
+    assert np.allclose(got.flux_moments[1], (term ** 2).sum(axis=0), rtol=2e-6, atol=0)
+    fund = 1.0 / (gens - skip + 1)
+    assert np.allclose(got.flux, term.sum(axis=0) * fund, rtol=2e-6)
+    err = got.flux_std_error(gens, skip)
+    n = gens - skip
+    want_err = fund * n * term.std(axis=0, ddof=1) / np.sqrt(n)
+    ok = want_err > 0
+    assert np.allclose(err[ok], want_err[ok], rtol=2e-3)  # f32 rounding of each term against a few-percent spread
+    assert 0.002 < np.median(err[ok] / got.flux[ok]) < 0.1  # percent-level noise at 4e4 histories x 9 generations
+    # the generation-level API accumulates the same sums
+    with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=skip) as ctx:
+        for g in range(gens):
+            ctx.transport(g)
+            ctx.finalize_generation(g)
+        again = ctx.fetch()
+    assert np.array_equal(again.flux_moments, got.flux_moments)
+
+
 def test_memory_pool_reuse_and_trim():
     """Contexts draw their device buffers from a library-owned pool that stays mapped between contexts; results do not
     depend on whether a buffer is fresh or recycled, and nraps_mc_trim gives the memory back."""

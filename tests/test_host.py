@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.nraps_abi_version() == 2
+    assert L.nraps_abi_version() == 3
 
 
 def test_mc_entry_points_fail_loudly_without_arguments_or_gpu():

@@ -19,6 +19,7 @@ for name, kw in [("config3_surface", dict(generations=200, histories=10_000_000)
                      sigma_generation=float(k.std(ddof=1)), device_s=r.seconds_device, wall_s=time.time() - t0,
                      histories_per_s=kw["generations"] * kw["histories"] / r.seconds_device,
                      collisions_per_history=r.counters["collisions"] / r.counters["histories"],
-                     entropy_first_last=[float(r.entropy[0]), float(r.entropy[-1])], bank_last=int(r.bank_sizes[-1]))
+                     entropy_first_last=[float(r.entropy[0]), float(r.entropy[-1])], bank_last=int(r.bank_sizes[-1]),
+                     flux_rel_std_error_median=float(np.median(r.flux_std_error(kw["generations"], sk) / r.flux)))
     print(name, json.dumps(out[name]), flush=True)
 json.dump(out, open("gpurun_out/full_configs.json", "w"), indent=1)

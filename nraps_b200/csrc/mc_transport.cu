@@ -190,27 +190,42 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     int steps = min((run_exit - cell) * dir, (int)P.walk_cap);
                     const int to_wall = (wall - cell) * dir; // cells until the boundary cell, if it lies in this run
                     if (to_wall < steps) steps = to_wall;
-                    const int stop_cell = cell + dir * steps;
-                    // one crossing; false = the walk is over (collision, or stop_cell reached)
+                    const int stride = kStep * dir;
+                    const uint32_t e_first = e_addr;
+                    // the loop tests the tally address, which nothing reads afterwards: testing e_addr lets the compiler
+                    // substitute the stop value on that exit and brings the per-crossing moves back
+                    const uint32_t t_stop = t_addr + (uint32_t)(stride * steps);
+                    // The loop carries the two running addresses, ds and the position `xc` only.  x and cell are NOT
+                    // kept up to date inside it: an unrolled loop with an exit per crossing otherwise pays four
+                    // register moves per crossing to hold them in place for those exits (r1o SASS); both are rebuilt
+                    // from the edge address afterwards.
+                    float xc = x;
+                    // one crossing; false = the walk is over (collision, or the stop edge reached)
                     auto step = [&]() -> bool {
-                        end = fadd(x, ds);
+                        end = fadd(xc, ds);
                         const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
-                        const float t = fsub(x, edge);
-                        if (!(fabsf(fsub(end, x)) > fabsf(t))) return false; // collision at `end` (|edge - x| == |x - edge| exactly)
+                        const float t = fsub(xc, edge);
+                        if (!(fabsf(fsub(end, xc)) > fabsf(t))) return false; // collision at `end` (|edge - x| == |x - edge| exactly)
                         // cross_mesh, src/mc_code.rs:171-181
                         score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
                         ds = fadd(ds, t);
-                        x = edge;
-                        cell += dir;
-                        e_addr += kStep * dir;
-                        t_addr += kStep * dir;
-                        if (TRACE) ++h_cross;
-                        return cell != stop_cell; // left the material run, reached the boundary cell, or time to regroup
+                        xc = edge;
+                        e_addr += stride;
+                        t_addr += stride;
+                        return t_addr != t_stop; // left the material run, reached the boundary cell, or time to regroup
                     };
-                    while (step() && step() && step() && step()) {} // unrolled by four: no loop-carried moves, one back branch per four crossings
-                    if (cell == run_exit) ev = EV_MATCHANGE;
-                    else if (cell == stop_cell) pending = true;
-                    else ev = EV_COLLIDE;
+                    while (step() && step() && step() && step()) {} // unrolled by four: one back branch per four crossings
+                    const int moved = (int)(e_addr - e_first) / kStep; // signed cells travelled
+                    if (moved) {
+                        // x after a crossing is the edge just crossed, bit for bit (src/mc_code.rs:72,77)
+                        const uint32_t behind = e_addr - (uint32_t)stride;
+                        x = BIG ? __ldg(P.edges + behind) : lds_f32(behind);
+                        cell += moved;
+                        if (TRACE) h_cross += (uint32_t)(moved * dir);
+                    }
+                    if (moved != dir * steps) ev = EV_COLLIDE;
+                    else if (cell == run_exit) ev = EV_MATCHANGE;
+                    else pending = true;
                 }
             }
         }

@@ -28,6 +28,27 @@ static __device__ __forceinline__ float lds_f32(uint32_t saddr)
     return v;
 }
 
+static __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+static __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+static __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // 64-bit fixed-point bin += score.  Shared-memory mode: two u32 words with an explicit carry, `ref` is the shared
 // address of the low word and the high word sits hi_off bytes above.  BIG mode (mesh too large for shared
 // memory): `ref` is the bin index and the add goes to the global 64-bit bin directly.
@@ -131,6 +152,28 @@ struct SmemView {
     uint16_t *fuel;
     uint8_t *matid;
     uint16_t *bucket;
+};
+
+// Read-only mesh tables as the kernels look them up.  They sit in shared memory, or in BIG mode in global memory;
+// the pointers of SmemView are generic because of that choice, and a lookup through them costs 64-bit address
+// arithmetic plus a generic load.  With BIG known at compile time the shared case becomes a 32-bit address and an LDS.
+template <bool BIG> struct MeshRef {
+    const float *edges;
+    const uint32_t *runb;
+    const uint8_t *matid;
+    const uint16_t *bucket;
+    uint32_t s_edges, s_runb, s_matid, s_bucket; // shared byte addresses (!BIG)
+    __device__ __forceinline__ explicit MeshRef(const SmemView &S) : edges(S.edges), runb(S.runb), matid(S.matid), bucket(S.bucket)
+    {
+        s_edges = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(S.edges);
+        s_runb = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(S.runb);
+        s_matid = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(S.matid);
+        s_bucket = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(S.bucket);
+    }
+    __device__ __forceinline__ float edge(int i) const { return BIG ? __ldg(edges + i) : lds_f32(s_edges + 4u * (uint32_t)i); }
+    __device__ __forceinline__ uint32_t run_bounds(int i) const { return BIG ? __ldg(runb + i) : lds_u32(s_runb + 4u * (uint32_t)i); }
+    __device__ __forceinline__ int material(int i) const { return BIG ? (int)__ldg(matid + i) : (int)lds_u8(s_matid + (uint32_t)i); }
+    __device__ __forceinline__ int bucket_cell(int i) const { return BIG ? (int)__ldg(bucket + i) : (int)lds_u16(s_bucket + 2u * (uint32_t)i); }
 };
 
 static __device__ __forceinline__ SmemView load_block_tables(unsigned char *smem_raw, const TransportParams &P, const SmemLayout &L)

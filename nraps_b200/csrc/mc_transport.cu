@@ -41,8 +41,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     const SmemView S = load_block_tables(smem_raw, P, L);
     uint32_t *s_lo = S.lo;
     const float *s_edges = S.edges, *s_xs = S.xs;
-    const uint32_t *s_runb = S.runb;
-    const uint8_t *s_matid = S.matid;
+    const MeshRef<BIG> mesh(S);
     const int tid = threadIdx.x;
     const int MG = M * G;
     const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_nusigf = s_xs + 3 * MG,
@@ -101,10 +100,10 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     g = (int)(r0.z >> 16);
                     row0 = (int)r0.w; // first tally row of this history's generation (0 unless generations are batched)
                     rng = (uint64_t)r1.x | ((uint64_t)r1.y << 32);
-                    mat = s_matid[cell];
+                    mat = mesh.material(cell);
                     xsg = g;
                     h_bank = 0;
-                    const uint32_t rb = s_runb[cell];
+                    const uint32_t rb = mesh.run_bounds(cell);
                     run_lo = (int)(rb & 0xffffu);
                     run_hi = (int)(rb >> 16);
                     h_coll = h_cross = h_flight = h_refl = 0;
@@ -264,9 +263,9 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 fate = NRAPS_FATE_TRUNCATED; // unreachable for validated input
                 cell = cell < 0 ? 0 : N - 1;
             } else {
-                mat = s_matid[cell];
+                mat = mesh.material(cell);
                 xsg = g;
-                const uint32_t rb = s_runb[cell];
+                const uint32_t rb = mesh.run_bounds(cell);
                 run_lo = (int)(rb & 0xffffu);
                 run_hi = (int)(rb >> 16);
             }

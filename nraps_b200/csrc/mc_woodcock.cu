@@ -27,16 +27,14 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
     const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG, P.rows);
     const SmemView S = load_block_tables(smem_raw, P, L);
     const float *s_edges = S.edges, *s_xs = S.xs;
-    const uint32_t *s_runb = S.runb;
-    const uint16_t *s_bucket = S.bucket;
-    const uint8_t *s_matid = S.matid;
+    const MeshRef<BIG> mesh(S);
     const int tid = threadIdx.x, MG = M * G;
     const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_nusigf = s_xs + 3 * MG,
                 *s_sigtr = s_xs + 4 * MG, *s_scat = s_xs + 5 * MG, *s_inv_maj = s_xs + 5 * MG + MG * G * G;
     const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
     const uint32_t lo_base = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(S.lo);
     const uint32_t hi_off = L.tally_hi - L.tally_lo;
-    const float len = s_edges[N];
+    const float len = mesh.edge(N);
 
     const unsigned lane = tid & 31;
     const uint64_t inc = P.rng_inc;
@@ -81,7 +79,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
                     row0 = (int)r0.w; // first tally row of this history's generation (0 unless generations are batched)
                     rng = (uint64_t)r1.x | ((uint64_t)r1.y << 32);
                     xsg = g;
-                    const uint32_t rb = s_runb[cell];
+                    const uint32_t rb = mesh.run_bounds(cell);
                     home_lo = (int)(rb & 0xffffu);
                     home_hi = (int)(rb >> 16);
                     left = false;
@@ -127,16 +125,16 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
             // cell containing xn: bucket guess (a bucket is no wider than a cell, so at most one step right),
             // then an exact check against the edges with a rarely-taken repair path
             int c = __float2int_rz(fmul(xn, P.inv_h));
-            c = s_bucket[c < NB - 1 ? c : NB - 1];
-            c += (c < N - 1 && s_edges[c + 1] <= xn) ? 1 : 0;
-            if (xn < s_edges[c] || (xn >= s_edges[c + 1] && c < N - 1)) {
-                while (c < N - 1 && s_edges[c + 1] <= xn) ++c;
-                while (c > 0 && s_edges[c] > xn) --c;
+            c = mesh.bucket_cell(c < NB - 1 ? c : NB - 1);
+            c += (c < N - 1 && mesh.edge(c + 1) <= xn) ? 1 : 0;
+            if (xn < mesh.edge(c) || (xn >= mesh.edge(c + 1) && c < N - 1)) {
+                while (c < N - 1 && mesh.edge(c + 1) <= xn) ++c;
+                while (c > 0 && mesh.edge(c) > xn) --c;
             }
             cell = c;
             x = xn;
             left = left || cell < home_lo || cell >= home_hi;
-            mat = s_matid[cell];
+            mat = mesh.material(cell);
             g_eff = left ? g : xsg;
             score<BIG>(tally_ref<BIG>(lo_base, (row0 + g) * N + cell), hi_off, inv_maj, P.tally);
             accepted = pcg32_unit(rng, inc) < fmul(s_sigtr[mat + M * g_eff], inv_maj);
@@ -168,7 +166,7 @@ __global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams
                 g = g_new;
                 mu = mu_new;
                 xsg = P.stale_xs ? g_eff : g;
-                const uint32_t rb = s_runb[cell];
+                const uint32_t rb = mesh.run_bounds(cell);
                 home_lo = (int)(rb & 0xffffu);
                 home_hi = (int)(rb >> 16);
                 left = false;

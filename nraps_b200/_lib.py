@@ -16,6 +16,7 @@ CT_NAMES = ["histories", "collisions", "crossings", "flights", "reflections", "l
 TR_WORDS = 10
 TR_NAMES = ["collisions", "crossings", "flights", "reflections", "rng_lo", "rng_hi", "cell", "xbits", "fate", "group"]
 TALLY_FRAC_BITS = 28
+ABI_VERSION = 3  # NRAPS_ABI_VERSION of include/nraps_mc.h this binding was written against
 
 _fp = C.POINTER(C.c_float)
 _u8p = C.POINTER(C.c_uint8)
@@ -100,6 +101,8 @@ def lib() -> C.CDLL:
             "(make -C nraps_b200/csrc). nraps_b200 has no fallback path."
         )
     L = C.CDLL(LIB_PATH)
+    if L.nraps_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} has ABI version {L.nraps_abi_version()}, this binding needs {ABI_VERSION}: rebuild it")
     vp = C.c_void_p
     L.nraps_mc_run.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(Results)]
     L.nraps_mc_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(vp)]

@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.nraps_abi_version() == 3
+    hdr = open(os.path.join(ROOT, "include", "nraps_mc.h")).read()
+    assert L.nraps_abi_version() == int(re.search(r"#define NRAPS_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION
 
 
 def test_mc_entry_points_fail_loudly_without_arguments_or_gpu():

@@ -189,7 +189,13 @@ extern "C" int nraps_process_input(const char *path, nraps_deck *d)
         !to_f32_list(slots[S_CHIT], &chit) || !to_f32_list(slots[S_SCAT], &scat))
         return NRAPS_ERR_IO;
     const size_t nxs = sigt.size();
-    if (sigs.size() < nxs || mu.size() < nxs) return NRAPS_ERR_SHAPE; // the reference would index out of bounds
+    // sigs / mu shorter than sigt: the reference indexes out of bounds at :152-156; a short siga / sigf / nut / chit
+    // panics later, on the first lookup past its end (src/mc_code.rs:121,347).  Every table is handed out as [n_xs],
+    // so all of that is one shape error here; entries past n_xs (harmless upstream) are dropped.
+    for (std::vector<float> *t : {&sigs, &mu, &siga, &sigf, &nut, &chit}) {
+        if (t->size() < nxs) return NRAPS_ERR_SHAPE;
+        t->resize(nxs);
+    }
     std::vector<float> inv(nxs);
     for (size_t i = 0; i < nxs; ++i) {
         const float prod = mu[i] * sigs[i];

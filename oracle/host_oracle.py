@@ -51,6 +51,8 @@ def scan_ascii_chunk(buf: bytes) -> list[str]:
             if name_end > line_start:
                 key = buf[line_start:name_end].decode("utf-8", "replace").strip().lower()
                 value = buf[val_start:pos].decode("utf-8", "replace").strip()
+                if len(key) < 2:
+                    raise IndexError("key shorter than two characters: `&key[length - 2..length]` panics (:72)")
                 temp[get_index(key[-2:], len(key))] += " " + value
             line_start = pos + 1
         pos += 1
@@ -101,7 +103,11 @@ def process_input(path: str) -> Deck:
     rodpitch = f32(f32(t[9].strip()) - roddia)
     mpfr, mpwr = int(t[10]), int(t[11])
     sigt, sigs, mu = _floats(t[14]), _floats(t[15]), _floats(t[16])
-    inv_sigtr = (f32(1.0) / (sigt - (mu * sigs).astype(f32)).astype(f32)).astype(f32)
+    if len(mu) < len(sigt) or len(sigs) < len(sigt):
+        raise IndexError("mu / sigs shorter than sigt: the loop at src/process_input.rs:152-156 indexes out of bounds")
+    n = len(sigt)  # :152 iterates over sigt.len(); longer mu / sigs are simply not read
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv_sigtr = (f32(1.0) / (sigt - (mu[:n] * sigs[:n]).astype(f32)).astype(f32)).astype(f32)
     return Deck(
         analk=int(t[0]), mattypes=int(t[1]), energygroups=int(t[2]), generations=int(t[3]),
         histories=int(t[4]), skip=int(t[5]), numass=int(t[6]), numrods=int(t[7]),
@@ -111,7 +117,7 @@ def process_input(path: str) -> Deck:
         sigt=sigt, sigs=sigs, mu=mu, siga=_floats(t[17]), sigf=_floats(t[18]), nut=_floats(t[19]),
         chit=_floats(t[20]), scat=_floats(t[21]), inv_sigtr=inv_sigtr,
         matid=np.array([int(v) for v in t[22].split()], dtype=np.uint8),
-        solution=int(t[23]), solver=int(t[24].strip() or 0),
+        solution=int(t[23]), solver={"1": 1, "2": 2, "3": 3}.get(t[24].strip(), 0),  # :168-173: anything else is LinAlg
     )
 
 

@@ -234,3 +234,87 @@ def test_diffusion_driver_and_csv(tmp_path):
     assert rows[0].split(",")[0] == nb.format_f32(float(got.flux[0, 0]))
     nb.plot_solution(got, v.energygroups, v.generations, len(mesh), float(mesh.mesh_right[-1]), str(tmp_path))
     assert open(tmp_path / "interface.csv").read().splitlines() == rows
+
+
+def _mutate_deck(text: str, rng) -> str:
+    """Random, format-preserving and format-breaking edits of a deck: the scanner's quirks (src/process_input.rs:44-83)
+    decide what each one means, and both parsers must decide the same."""
+    lines = text.split("\n")
+    for _ in range(int(rng.integers(1, 7))):
+        i = int(rng.integers(0, len(lines)))
+        kind = int(rng.integers(0, 12))
+        ln = lines[i]
+        if kind == 0:
+            lines.insert(i, "# " + "x" * int(rng.integers(0, 5)))                 # comment line (eats the next line's first byte)
+        elif kind == 1:
+            lines[i] = ln + "  # trailing"                                          # kills a pending key = value
+        elif kind == 2:
+            lines.insert(i, "")                                                     # blank line
+        elif kind == 3 and "=" in ln:
+            k, v = ln.split("=", 1)
+            lines[i] = k.upper() + "=" + v if rng.integers(0, 2) else "  " + k.lower() + " =   " + v + "  "
+        elif kind == 4 and "=" in ln and len(ln.split("=", 1)[1].split()) > 3:
+            k, v = ln.split("=", 1)                                                 # split a list over a repeated key
+            toks = v.split()
+            cut = int(rng.integers(1, len(toks)))
+            lines[i] = k + "= " + " ".join(toks[:cut])
+            lines.insert(i + 1, k + "= " + " ".join(toks[cut:]))
+        elif kind == 5:
+            lines[i] = ln + "\r"                                                    # CRLF
+        elif kind == 6 and "=" in ln:
+            lines[i] = ln.replace(" =", "=", 1)                                     # key loses its last char (name_end = pos - 1)
+        elif kind == 7 and "=" in ln:
+            lines[i] = ln + " = 3"                                                  # second '=' moves key end and value start
+        elif kind == 8:
+            lines.insert(i, "NoSuchKey = 12 13")                                    # junk slot
+        elif kind == 9 and "=" in ln:
+            lines[i] = ln.split("=", 1)[0] + "="                                    # empty value
+        elif kind == 10:
+            lines.insert(i, "just some words without the sign")
+        elif kind == 11 and "=" in ln:
+            lines.insert(i, ln)                                                     # duplicated key: lists double, scalars break
+    out = "\n".join(lines)
+    if rng.integers(0, 6) == 0:
+        out = out.rstrip("\n")                                                      # last line without a newline is never seen
+    return out
+
+
+def test_parser_fuzz_against_numpy_restatement(tmp_path):
+    """300 randomly edited decks: the product parser and the numpy restatement of src/process_input.rs either both
+    reject the deck or agree on every field, bit for bit."""
+    rng = np.random.default_rng(2024)
+    accepted = rejected = 0
+    for n in range(300):
+        base = open(DECKS["abc"[n % 3]]).read()
+        text = _mutate_deck(base, rng)
+        if text.rstrip("\n").rsplit("\n", 1)[-1].lstrip().startswith("#") and not text.endswith("\n"):
+            continue  # a comment on an unterminated last line indexes past the buffer upstream (skip_line, :6-10)
+        path = tmp_path / f"fuzz{n}.txt"
+        path.write_bytes(text.encode())
+        try:
+            d = ho.process_input(str(path))
+            # a pin list that is not u8, or a table shorter than SigT, is a panic upstream
+            ok = all(0 <= int(m) <= 255 for m in d.matid)
+            ok = ok and all(len(getattr(d, t)) >= len(d.sigt) for t in ("sigs", "mu", "siga", "sigf", "nut", "chit"))
+            ok = ok and all(0 <= getattr(d, f) <= 255 for f in ("analk", "mattypes", "energygroups", "numass", "numrods", "solution"))
+            ok = ok and all(getattr(d, f) >= 0 for f in ("generations", "histories", "skip", "mpfr", "mpwr"))
+        except (ValueError, IndexError, OverflowError, ZeroDivisionError):
+            ok = False
+        if not ok:
+            with pytest.raises(_lib.NrapsError):
+                nb.process_input(str(path))
+            rejected += 1
+            continue
+        v, xs, pins, dx, sol, solver = nb.process_input(str(path))
+        for name in ("analk", "mattypes", "energygroups", "generations", "histories", "skip", "numass", "numrods", "mpfr", "mpwr"):
+            assert getattr(v, name) == getattr(d, name), (n, name)
+        for name in ("roddia", "rodpitch", "boundl", "boundr"):
+            assert bits(getattr(v, name)) == bits(getattr(d, name)), (n, name)
+        assert bits(dx.fuel) == bits(d.dx_fuel) and bits(dx.water) == bits(d.dx_water), n
+        for a, b in [(xs.sigt, d.sigt), (xs.sigs, d.sigs), (xs.mu, d.mu), (xs.siga, d.siga), (xs.sigf, d.sigf),
+                     (xs.nut, d.nut), (xs.chit, d.chit), (xs.inv_sigtr, d.inv_sigtr)]:
+            assert len(a) == len(d.sigt) and np.array_equal(bits(a), bits(b[:len(a)])), n  # tables are handed out as [n_xs]
+        assert np.array_equal(bits(xs.scat_matrix), bits(d.scat)), n
+        assert np.array_equal(pins, d.matid) and sol == d.solution and solver == d.solver, n
+        accepted += 1
+    assert accepted > 60 and rejected > 60, (accepted, rejected)

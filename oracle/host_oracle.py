@@ -129,7 +129,13 @@ def mesh_gen(matid, mpfr: int, mpwr: int, numass: int, dx_fuel, dx_water):
     for index1 in range(1, numass):
         for _ in range(mpwr):
             del temp[(index1 * len(temp)) // numass]
+    if len(temp) < mpwr // 2:
+        raise IndexError("drain(0..mpwr/2) past the end panics (src/main.rs:107)")
     del temp[0 : mpwr // 2]
+    if len(temp) < mpwr // 2:
+        # `temp.len() - mpwr/2` underflows (:108): a panic with overflow checks, a no-op truncate without; no mesh
+        # of a real deck gets here and the product rejects it as a shape error
+        raise IndexError("mesh shorter than the edge trim")
     del temp[len(temp) - (mpwr // 2) :]
     fuel = np.array([i for i, m in enumerate(temp) if m in (0, 1)], dtype=np.uint64)
     n = len(temp)

@@ -318,3 +318,45 @@ def test_parser_fuzz_against_numpy_restatement(tmp_path):
         assert np.array_equal(pins, d.matid) and sol == d.solution and solver == d.solver, n
         accepted += 1
     assert accepted > 60 and rejected > 60, (accepted, rejected)
+
+
+def test_mesh_gen_fuzz_against_numpy_restatement():
+    """Random pin lists (fuel, water, control rods), cells per pin and assembly counts: same cells, same fuel list, same
+    f32 edges bit for bit -- or the same refusal (src/main.rs:85-143 panics where these return a shape error)."""
+    rng = np.random.default_rng(77)
+    built = refused = 0
+    for _ in range(1500):
+        numass, mpfr, mpwr = int(rng.integers(1, 4)), int(rng.integers(1, 10)), int(rng.integers(1, 9))
+        pins = rng.integers(0, 4, int(rng.integers(3, 40))).astype(np.uint8)
+        v = nb.Variables(analk=1, mattypes=4, energygroups=2, generations=2, histories=1, skip=1, numass=numass, numrods=len(pins),
+                         roddia=0.94, rodpitch=0.322, mpfr=mpfr, mpwr=mpwr, boundl=1.0, boundr=1.0)
+        dx = nb.DeltaX(fuel=float(f32(0.94) / f32(mpfr)), water=float(f32(0.322) / f32(mpwr)))
+        try:
+            m = ho.mesh_gen(pins, mpfr, mpwr, numass, f32(dx.fuel), f32(dx.water))
+            ok = len(m[0]) > 0
+        except IndexError:
+            ok = False
+        if not ok:
+            with pytest.raises(_lib.NrapsError):
+                nb.mesh_gen(pins, v, dx)
+            refused += 1
+            continue
+        mesh, fuel = nb.mesh_gen(pins, v, dx)
+        assert np.array_equal(mesh.matid, m[0]) and np.array_equal(fuel, m[4])
+        for a, b in [(mesh.delta_x, m[1]), (mesh.mesh_left, m[2]), (mesh.mesh_right, m[3])]:
+            assert np.array_equal(bits(a), bits(b))
+        built += 1
+    assert built > 1000 and refused > 0
+
+
+def test_rust_float_display_random_bit_patterns():
+    """Shortest round-trip digits in positional notation for arbitrary binary32 / binary64 bit patterns (subnormals,
+    extremes, NaN payloads), against the restatement of Rust's Display (src/plot_solution.rs:14-34 uses to_string())."""
+    rng = np.random.default_rng(9)
+    pat = rng.integers(0, 1 << 32, 20000, dtype=np.uint64).astype(np.uint32)
+    pat[:8] = [1, 0x007FFFFF, 0x00800000, 0x7F7FFFFF, 0x80000001, 0x3F800001, 0x4B800000, 0x4B7FFFFF]
+    for v in pat.view(np.float32):
+        assert nb.format_f32(float(v)) == ho.rust_f32_display(float(v)), v
+    pat64 = rng.integers(0, 1 << 63, 5000, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, 5000, dtype=np.uint64)
+    for v in pat64.view(np.float64):
+        assert nb.format_f64(float(v)) == ho.rust_f64_display(float(v)), v

@@ -360,3 +360,39 @@ def test_rust_float_display_random_bit_patterns():
     pat64 = rng.integers(0, 1 << 63, 5000, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, 5000, dtype=np.uint64)
     for v in pat64.view(np.float64):
         assert nb.format_f64(float(v)) == ho.rust_f64_display(float(v)), v
+
+
+def test_validation_codes_come_before_any_cuda_call_and_there_is_no_fallback():
+    """Every malformed problem is refused with its own code on a host without a GPU; a well-formed one gets as far as
+    the CUDA runtime and fails with NRAPS_ERR_CUDA when no device exists -- the product never computes on the CPU."""
+    import torch
+
+    v, xs, dx, mesh, fuel = load_case("a")
+
+    def code(**kw):
+        args = dict(variables=v, xsdata=xs, delta_x=dx, meshid=mesh, fuel_indices=fuel, generations=2, histories=10, skip=1)
+        opts = {k: kw.pop(k) for k in list(kw) if k in ("scatter_mode", "tracking_mode", "kernel_variant", "source_mode", "bank_cap")}
+        args.update(kw)
+        with pytest.raises(_lib.NrapsError) as e:
+            nb.monte_carlo(args["variables"], args["xsdata"], args["delta_x"], args["meshid"], args["fuel_indices"], args.get("k_new", 1.0),
+                           generations=args["generations"], histories=args["histories"], skip=args["skip"], **opts)
+        return e.value.code
+
+    assert code(generations=3, skip=3) == 2                                   # k_fund[skip] out of range upstream
+    assert code(histories=0) == 2
+    assert code(k_new=0.0) == 2 and code(k_new=float("nan")) == 2
+    bad = nb.Mesh(mesh.matid.copy(), mesh.delta_x, mesh.mesh_left, mesh.mesh_right.copy())
+    bad.mesh_right[10] += f32(1e-3)
+    assert code(meshid=bad) == 3                                              # right[i] != left[i+1]
+    bad = nb.Mesh(mesh.matid.copy(), mesh.delta_x, mesh.mesh_left, mesh.mesh_right)
+    bad.matid[5] = 9
+    assert code(meshid=bad) == 3                                              # matid >= M
+    assert code(fuel_indices=np.r_[fuel[:-1], np.uint64(len(mesh))]) == 3     # fuel index >= N
+    assert code(xsdata=nb.XSData(**{**xs.__dict__, "inv_sigtr": xs.inv_sigtr * f32(-1)})) == 4
+    assert code(xsdata=nb.XSData(**{**xs.__dict__, "inv_sigtr": xs.inv_sigtr * f32(np.inf)})) == 4
+    assert code(kernel_variant="event") == 7                                  # the event pipeline is Woodcock-only
+    assert code(bank_cap=300) == 7
+    v1 = nb.Variables(**{**v.__dict__, "energygroups": 1})
+    assert code(variables=v1) == 2                                            # G >= 2: nut[M*1] (src/mc_code.rs:356)
+    if not torch.cuda.is_available():
+        assert code() == 6                                                    # well-formed: NRAPS_ERR_CUDA, no CPU path

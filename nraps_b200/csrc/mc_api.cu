@@ -841,17 +841,26 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
     return bail(NRAPS_OK);
 }
 
+// device scratch of the unit probes below: released on every return path
+namespace {
+struct Scratch {
+    void *p = nullptr;
+    ~Scratch() { dev_free(p); }
+    cudaError_t alloc(size_t bytes) { return dev_malloc(&p, std::max<size_t>(1, bytes)); }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+} // namespace
+
 extern "C" int nraps_dev_logf(const float *x, float *out, uint32_t n, int32_t device)
 {
     if (!x || !out) return NRAPS_ERR_NULL;
     CU(cudaSetDevice(device));
-    float *dx = nullptr, *dout = nullptr;
-    CU(dev_malloc((void **)&dx, std::max<size_t>(1, n) * sizeof(float)));
-    CU(dev_malloc((void **)&dout, std::max<size_t>(1, n) * sizeof(float)));
-    CU(cudaMemcpy(dx, x, n * sizeof(float), cudaMemcpyHostToDevice));
-    CU(launch_probe_logf(dx, dout, n, nullptr));
-    CU(cudaMemcpy(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost));
-    dev_free(dx); dev_free(dout);
+    Scratch dx, dout;
+    CU(dx.alloc(n * sizeof(float)));
+    CU(dout.alloc(n * sizeof(float)));
+    CU(cudaMemcpy(dx.p, x, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_probe_logf(dx.as<float>(), dout.as<float>(), n, nullptr));
+    CU(cudaMemcpy(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return NRAPS_OK;
 }
 
@@ -859,14 +868,13 @@ extern "C" int nraps_dev_div(const float *t, const float *mu, float *out_fast, f
 {
     if (!t || !mu || !out_fast || !out_ieee) return NRAPS_ERR_NULL;
     CU(cudaSetDevice(device));
-    float *d[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (auto &p : d) CU(dev_malloc((void **)&p, std::max<size_t>(1, n) * sizeof(float)));
-    CU(cudaMemcpy(d[0], t, n * sizeof(float), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d[1], mu, n * sizeof(float), cudaMemcpyHostToDevice));
-    CU(launch_probe_div(d[0], d[1], d[2], d[3], n, nullptr));
-    CU(cudaMemcpy(out_fast, d[2], n * sizeof(float), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(out_ieee, d[3], n * sizeof(float), cudaMemcpyDeviceToHost));
-    for (auto &p : d) dev_free(p);
+    Scratch d[4];
+    for (Scratch &b : d) CU(b.alloc(n * sizeof(float)));
+    CU(cudaMemcpy(d[0].p, t, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d[1].p, mu, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_probe_div(d[0].as<float>(), d[1].as<float>(), d[2].as<float>(), d[3].as<float>(), n, nullptr));
+    CU(cudaMemcpy(out_fast, d[2].p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_ieee, d[3].p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return NRAPS_OK;
 }
 
@@ -878,13 +886,11 @@ extern "C" int nraps_dev_pcg32(uint64_t seed, uint64_t stream, uint64_t stride, 
     Pcg m = pcg_seed(seed, stream);
     uint64_t jm, jp;
     pcg_jump_coeffs(m.inc, hid * stride, &jm, &jp);
-    uint32_t *du = nullptr;
-    float *df = nullptr;
-    CU(dev_malloc((void **)&du, std::max<size_t>(1, n) * sizeof(uint32_t)));
-    CU(dev_malloc((void **)&df, std::max<size_t>(1, n) * sizeof(float)));
-    CU(launch_probe_pcg(jm * m.state + jp, m.inc, n, du, df, nullptr));
-    CU(cudaMemcpy(out_u32, du, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(out_unit, df, n * sizeof(float), cudaMemcpyDeviceToHost));
-    dev_free(du); dev_free(df);
+    Scratch du, df;
+    CU(du.alloc(n * sizeof(uint32_t)));
+    CU(df.alloc(n * sizeof(float)));
+    CU(launch_probe_pcg(jm * m.state + jp, m.inc, n, du.as<uint32_t>(), df.as<float>(), nullptr));
+    CU(cudaMemcpy(out_u32, du.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_unit, df.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return NRAPS_OK;
 }

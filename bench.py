@@ -34,6 +34,29 @@ UNIT = "histories/s"
 RECORD_BYTES = 24  # SURVEY 8d bank record: x, mu, cell, packed groups/flags, rng state
 
 
+_json_fd = None
+
+
+def reserve_stdout():
+    """stdout carries the one JSON line and nothing else: from here on file descriptor 1 points at stderr, so that
+    whatever a library prints there (NCCL's version banner when the box sets NCCL_DEBUG=VERSION, for one) cannot land
+    in front of the line; emit() writes to the original stdout."""
+    global _json_fd
+    if _json_fd is None:
+        sys.stdout.flush()
+        _json_fd = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _json_fd is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_json_fd, data)
+
+
 def workload(name: str):
     from tests.util import load_case
 
@@ -137,6 +160,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    reserve_stdout()
     args, desc, per_gpu = workload(a.workload)
     cores = os.cpu_count() or 2
     threads = max(1, cores - 1)
@@ -164,7 +188,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "k_mean": float(r.k.mean()),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(a):
@@ -183,6 +207,7 @@ def run_ours(a):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr",
                "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    reserve_stdout()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -325,7 +350,7 @@ def run_ours(a):
                 "value": sample_h * sample_g / r.seconds_transport, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"{sample_g} generations x {sample_h} histories of the same workload, C restatement of src/mc_code.rs "
                           f"threaded like the reference ({threads} workers of {cores} cores, per-worker f32 tallies)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

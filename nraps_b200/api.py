@@ -177,6 +177,16 @@ class _Marshalled:
         self.skip = int(variables.skip if skip is None else skip)
         self.G, self.M, self.N = int(variables.energygroups), int(variables.mattypes), len(k["matid"])
         self.numass = int(variables.numass)
+        # The C ABI takes bare pointers (the tables' extents follow from M, G and N), so a short array would be read
+        # past its end; the reference indexes Vecs and panics instead.
+        for name in ("sigt", "sigs", "mu", "siga", "sigf", "nut", "chit", "inv_sigtr"):
+            if k[name].size < self.M * self.G:
+                raise ValueError(f"xsdata.{name} holds {k[name].size} values, mattypes * energygroups = {self.M * self.G} are indexed")
+        if k["scat"].size < self.M * self.G * self.G:
+            raise ValueError(f"xsdata.scat_matrix holds {k['scat'].size} values, mattypes * energygroups^2 = {self.M * self.G * self.G} are indexed")
+        for name in ("dx", "left", "right"):
+            if k[name].size != self.N:
+                raise ValueError(f"mesh arrays differ in length: matid has {self.N} cells, {name} has {k[name].size}")
         self.problem = Problem(
             M=self.M, G=self.G, N=self.N, NF=len(k["fuel"]), numass=self.numass,
             generations=self.generations, histories=self.histories, skip=self.skip,

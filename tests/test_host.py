@@ -402,3 +402,19 @@ def test_validation_codes_come_before_any_cuda_call_and_there_is_no_fallback():
     assert code(variables=v1) == 2                                            # G >= 2: nut[M*1] (src/mc_code.rs:356)
     if not os.path.exists("/dev/nvidiactl"):
         assert code() == 6                                                    # well-formed: NRAPS_ERR_CUDA, no CPU path
+
+
+def test_python_mirror_refuses_arrays_shorter_than_the_abi_reads():
+    """nraps_problem carries no array lengths (include/nraps_mc.h): the Python mirror checks them before the call."""
+    v, xs, dx, mesh, fuel = load_case("c")
+    short = nb.XSData(**{**xs.__dict__, "siga": xs.siga[:-1]})
+    with pytest.raises(ValueError, match="siga"):
+        nb.monte_carlo(v, short, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1)
+    short = nb.XSData(**{**xs.__dict__, "scat_matrix": xs.scat_matrix[:60]})
+    with pytest.raises(ValueError, match="scat_matrix"):
+        nb.monte_carlo(v, short, dx, mesh, fuel, 1.0, generations=2, histories=10, skip=1)
+    ragged = nb.Mesh(mesh.matid, mesh.delta_x, mesh.mesh_left[:-1], mesh.mesh_right)
+    with pytest.raises(ValueError, match="left"):
+        nb.monte_carlo(v, xs, dx, ragged, fuel, 1.0, generations=2, histories=10, skip=1)
+    with pytest.raises(ValueError, match="sigt"):
+        nb.nalgebra_method(nb.XSData(**{**xs.__dict__, "sigt": xs.sigt[:3]}), mesh, v.energygroups, v.mattypes, 1.0, 1.0, v.numass)

@@ -114,3 +114,47 @@ def test_two_rank_gloo_equals_single_rank(tmp_path):
     run_generations(eng, tally, 0, 1)
     assert np.array_equal(np.stack(eng.per_gen), r0)  # and it is the single-rank tally, bit for bit
     assert r0.any()
+
+
+def _bank_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def counts_fn(n):  # same shape of exchange as make_bank_callback's NCCL version
+        out = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(out, torch.tensor([n], dtype=torch.int64))
+        return [int(t.item()) for t in out]
+
+    def padded_fn(padded, max_n):
+        out = [torch.zeros(max_n, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(out, padded)
+        return torch.stack(out)
+
+    banks = []
+    for gen, sizes in enumerate([(5, 3), (0, 4), (7, 0), (0, 0)]):  # ragged, one side empty, both empty
+        local = torch.arange(sizes[rank], dtype=torch.int64) + 1000 * rank + 100 * gen
+        full, counts = gather_bank(local, world, counts_fn, padded_fn)
+        assert counts == list(sizes)
+        banks.append(full.numpy().copy())
+    np.save(os.path.join(out_dir, f"bank{rank}.npy"), np.concatenate(banks))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_bank_gather_is_rank_ordered_and_identical_everywhere(tmp_path):
+    """The fission-bank exchange of nraps_b200.dist over real collectives (gloo, world size 2): every rank ends with
+    the same bank, rank 0's sites first -- what makes generation g+1 independent of the number of GPUs."""
+    import torch.multiprocessing as mp
+
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_bank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    b0, b1 = np.load(tmp_path / "bank0.npy"), np.load(tmp_path / "bank1.npy")
+    assert np.array_equal(b0, b1)
+    want = np.r_[np.arange(5), 1000 + np.arange(3), 1100 + np.arange(4), 200 + np.arange(7)]
+    assert np.array_equal(b0, want)

@@ -112,3 +112,29 @@ def test_worker_split_and_inclusive_ranges_q4():
 
 def test_other_master_stream():
     _compare("c", H=60, gens=2, seed=7, seq=3, stride=1000)
+
+
+@pytest.mark.parametrize("M,G,pins,mpfr,mpwr,bl,br,mode", [
+    (2, 3, [1, 0, 1], 3, 2, 1.0, 1.0, "single_xi"),                 # three groups, fuel touching both walls
+    (3, 5, [2, 0, 2, 1, 2, 0, 2], 5, 4, 1.0, 0.0, "rust_pre182"),   # five groups, vacuum on the right, per-probe draws
+    (5, 8, [4, 0, 3, 1, 2, 0, 4], 4, 6, 0.7, 1.0, "rust_182"),      # eight groups: three probes + the final comparison
+    (5, 8, [4, 0, 3, 1, 2, 0, 4], 4, 6, 0.7, 1.0, "rust_pre182"),
+    (2, 2, [0], 1, 0, 1.0, 1.0, "single_xi"),                       # N = 1: both walls belong to the only cell
+    (3, 4, [2, 1, 2], 64, 2, 0.0, 0.0, "single_xi"),                # one long fuel run between vacuum walls
+])
+def test_synthetic_shapes(M, G, pins, mpfr, mpwr, bl, br, mode):
+    """The shapes of tests/test_gpu_parity.py::test_synthetic_shapes_bit_exact (generic group counts, up to five
+    materials, a single cell, long runs, albedo 0.7), restatement against restatement."""
+    from tests.util import synthetic_case
+
+    v, xs, dx, mesh, fuel = synthetic_case(M, G, pins, mpfr, mpwr, seed=M * 10 + G, boundl=bl, boundr=br)
+    v.generations, v.histories, v.skip = 2, 80, 1
+    variables, xsdata, dxf, meshid, fi = rp.from_product_inputs(v, xs, dx, mesh, fuel)
+    got = rp.monte_carlo(variables, xsdata, dxf, meshid, fi, 1.0, rp.Switches(scatter_mode=mode), exact_tally=True, trace_gen=1)
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=2, histories=80, skip=1, threads=1, want_tally=True, trace_gen=1, scatter_mode=mode)
+    assert np.array_equal(got["trace"], want.trace)
+    assert np.array_equal(got["tally_fixed"], want.tally_fixed)
+    for name in ("k", "k_fund", "flux", "fission_source", "assembly_average"):
+        assert np.array_equal(bits(got[name]), bits(getattr(want, name))), name
+    assert got["trace"][:, 0].sum() > 0

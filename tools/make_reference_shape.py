@@ -1,7 +1,7 @@
 """tests/golden/reference_shipped_shape.json from the reference's shipped interface.csv / k_eff.csv.
 
 Those files are the only end-to-end artefacts the reference ships for the Monte Carlo path.  They come from an
-older (f64) build whose normalisation differs from HEAD (k = 5.67, flux 3.7x ours), so only
+older (f64) build whose results differ from HEAD's semantics (k = 5.67 = 3.11x, flux 2.9x in fuel to 4.2x in water), so only
 scale-free quantities are kept: the fission-source shape, the thermal-flux shape and the group-mean flux ratios.
 Usage (build container only): python tools/make_reference_shape.py
 """

@@ -254,11 +254,14 @@ def scat_mat_calc(energygroups, matid, neutron_energy, inv_sigs, scat_matrix):
     return out
 
 
-def interaction(interaction_xi, scat_mat, xsdata, xs_index, neutron_energy, rnd: Stream, mode: str):
-    """src/mc_code.rs:114-132: mu and the group are drawn before the absorption test."""
+def interaction(interaction_xi, scat_mat, xsdata, xs_index, neutron_energy, rnd: Stream, mode: str, after_draws=None):
+    """src/mc_code.rs:114-132: mu and the group are drawn before the absorption test.  `after_draws` (fission_bank
+    mode only, not in the reference) runs between the draws and the test, where the bank draw sits in the stream."""
     absorption = f32(xsdata.siga[xs_index]) / f32(xsdata.sigt[xs_index])
     mu = TWO * rnd.random() - ONE
     scatter_energy = partition_point_min(scat_mat, rnd.random, mode)
+    if after_draws is not None:
+        after_draws()
     if interaction_xi < absorption:
         return False, neutron_energy, ZERO
     return True, scatter_energy, mu
@@ -273,7 +276,7 @@ class Events:
 
 
 def particle_travel(tally, meshid, mesh_index, neutron_energy, mu, start_x, mattypes, energygroups, boundr, boundl,
-                    xsdata, rnd: Stream, sw: Switches, ev: Events):
+                    xsdata, rnd: Stream, sw: Switches, ev: Events, bank=None):
     """src/mc_code.rs:134-213.  `tally(g, cell, v)` stands for `tally[g][cell] += v`."""
     xs_index = meshid[mesh_index].matid + mattypes * neutron_energy                      # :147
     delta_s = mu * -ln(rnd.random()) * f32(xsdata.inv_sigtr[xs_index])                    # :148
@@ -305,8 +308,11 @@ def particle_travel(tally, meshid, mesh_index, neutron_energy, mu, start_x, matt
             with np.errstate(divide="ignore", invalid="ignore"):  # SigS = 0 (control rod): 1/0 and 0*inf, as upstream
                 scat_mat = scat_mat_calc(energygroups, meshid[mesh_index].matid, neutron_energy,
                                          ONE / f32(xsdata.sigs[xs_index]), xsdata.scat_matrix)
+            hook = None
+            if bank is not None:
+                hook = lambda: bank(mesh_index, end_x, meshid[mesh_index].matid, neutron_energy, xs_index, rnd)  # noqa: E731
             alive, new_energy, new_mu = interaction(rnd.random(), scat_mat, xsdata, xs_index, neutron_energy, rnd,
-                                                    sw.scatter_mode)
+                                                    sw.scatter_mode, hook)
             if not alive:
                 ev.fate = 1
                 return False, mesh_index, mu, neutron_energy, start_x
@@ -439,3 +445,227 @@ def from_product_inputs(v, xs, dx, mesh, fuel):
     meshid = [Mesh(int(m), f32(d), f32(l), f32(r)) for m, d, l, r in
               zip(mesh.matid, mesh.delta_x, mesh.mesh_left, mesh.mesh_right)]
     return variables, xsdata, f32(dx.fuel), meshid, [int(i) for i in fuel]
+
+
+# ---------------------------------------------------------------------------------------------
+# The two capabilities the north star adds and the reference does not have: the fission-bank power
+# iteration and Woodcock delta tracking.  There is no reference source to cite; what is restated is
+# the definition in DESIGN.md section 5 ("Fission bank", "woodcock_kernel"), so that the C oracle's
+# implementation of it -- the checker of the GPU kernels in those modes -- has a second opinion too.
+# ---------------------------------------------------------------------------------------------
+BANK_CAP = 8
+
+
+def _bits(x) -> int:
+    return struct.unpack("<I", struct.pack("<f", float(x)))[0]
+
+
+def _from_bits(b: int) -> np.float32:
+    return f32(struct.unpack("<f", struct.pack("<I", b))[0])
+
+
+class FissionBank:
+    """Sites banked by one generation: per history at most BANK_CAP of them, kept in (history, site) order."""
+
+    def __init__(self, xsdata, mattypes, inv_k):
+        self.xsdata, self.M, self.inv_k = xsdata, mattypes, inv_k
+        self.rows = {}
+        self.current = None
+
+    def begin(self, y):
+        self.current = self.rows.setdefault(y, [])
+        self.produced = 0
+
+    def __call__(self, cell, x, mat, g, xs_index, rnd):
+        """n = floor(nu Sigma_f(mat, g) * inv_sigtr[xs] / k_prev + xi) sites at the collision point; the draw is only
+        made in fissile material."""
+        nusigf = f32(self.xsdata.nut[mat + self.M * g]) * f32(self.xsdata.sigf[mat + self.M * g])
+        if nusigf > ZERO:
+            wgt = nusigf * f32(self.xsdata.inv_sigtr[xs_index]) * self.inv_k
+            n = int(wgt + rnd.random())
+            for _ in range(n):
+                if self.produced < BANK_CAP:
+                    self.current.append((cell << 32) | _bits(x))
+                self.produced += 1
+
+    def dense(self):
+        return [site for y in sorted(self.rows) for site in self.rows[y]]
+
+
+def entropy_bits(bank, n_cells) -> float:
+    """Shannon entropy of the bank over mesh cells, in bits, summed in cell order."""
+    import math
+
+    hist = [0] * n_cells
+    for site in bank:
+        hist[site >> 32] += 1
+    e = 0.0
+    for h in hist:
+        if h:
+            pr = h / len(bank)
+            e -= pr * math.log2(pr)
+    return e
+
+
+def spawn_from(source_bank, fuel_indices, variables, xsdata, meshid, delta_x_fuel, rnd):
+    """Birth of one history: from the bank (site index, mu, chi: no position draw) or, with an empty bank, the
+    reference's flat fuel source (cell, position, mu, chi)."""
+    if source_bank:
+        site = source_bank[rnd.gen_range(len(source_bank))]
+        mesh_index, start_x = site >> 32, _from_bits(site & 0xFFFFFFFF)
+        mu = direction(rnd.random())
+        return mesh_index, start_x, mu, energy(rnd.random(), mesh_index, variables, xsdata, meshid)
+    mesh_index, sub, mu, g = spawn_neutron(fuel_indices, variables, xsdata, meshid, rnd)
+    return mesh_index, meshid[mesh_index].mesh_left + (sub * delta_x_fuel), mu, g
+
+
+def material_runs(meshid):
+    lo, hi = [0] * len(meshid), [0] * len(meshid)
+    i = 0
+    while i < len(meshid):
+        j = i
+        while j < len(meshid) and meshid[j].matid == meshid[i].matid:
+            j += 1
+        for q in range(i, j):
+            lo[q], hi[q] = i, j
+        i = j
+    return lo, hi
+
+
+def woodcock_tables(variables, xsdata, meshid):
+    """sigtr = sigt - mu*sigs (the collision density flights are sampled with, src/process_input.rs:152-156) and, for
+    every (stale group, current group) pair, 1 / the largest sigtr of either group over the materials in the mesh."""
+    M, G = variables.mattypes, variables.energygroups
+    sigtr = [f32(xsdata.sigt[i]) - f32(xsdata.mu[i]) * f32(xsdata.sigs[i]) for i in range(M * G)]
+    present = sorted({c.matid for c in meshid})
+    inv_maj = {}
+    for a in range(G):
+        for b in range(G):
+            mx = ZERO
+            for m in present:
+                mx = max(mx, sigtr[m + M * a], sigtr[m + M * b])
+            inv_maj[(a, b)] = ONE / mx
+    return sigtr, inv_maj
+
+
+def locate(meshid, x) -> int:
+    """Cell containing x: the number of interior edges <= x."""
+    c = 0
+    while c < len(meshid) - 1 and meshid[c].mesh_right <= x:
+        c += 1
+    return c
+
+
+def woodcock_history(score, variables, xsdata, meshid, runs, tables, mesh_index, start_x, mu, g, rnd, sw, ev, bank):
+    """Delta tracking: flights against the majorant, every tentative collision scores 1/Sigma_maj into the cell it
+    lands in and is real with probability sigtr/Sigma_maj.  The group that sets the cross sections (Q1) is the one the
+    neutron had when it entered its material run, until it is seen outside that run."""
+    M, G, N = variables.mattypes, variables.energygroups, len(meshid)
+    run_lo, run_hi = runs
+    sigtr, inv_maj_of = tables
+    length = meshid[N - 1].mesh_right
+    x, cell, xsg = start_x, mesh_index, g
+    home_lo, home_hi, left = run_lo[cell], run_hi[cell], False
+    while True:
+        inv_maj = inv_maj_of[(xsg, g)]
+        xn = x + mu * -ln(rnd.random()) * inv_maj
+        ev.flights += 1
+        while xn < ZERO or xn > length:                       # albedo walls act on the direction cosine (Q8)
+            lo_wall = xn < ZERO
+            wall, b = (ZERO, variables.boundl) if lo_wall else (length, variables.boundr)
+            if not b > ZERO:
+                ev.fate = 2
+                return cell, x, g
+            rem = xn - wall
+            mu = mu * (-b)
+            xn = wall + rem * (-b)
+            if (home_lo != 0) if lo_wall else (home_hi != N):
+                left = True
+            ev.reflections += 1
+        cell, x = locate(meshid, xn), xn
+        if cell < home_lo or cell >= home_hi:
+            left = True
+        mat = meshid[cell].matid
+        g_eff = g if left else xsg
+        xs_index = mat + M * g_eff
+        score(g, cell, inv_maj)
+        if rnd.random() < sigtr[xs_index] * inv_maj:
+            ev.collisions += 1
+            with np.errstate(divide="ignore", invalid="ignore"):
+                scat_mat = scat_mat_calc(G, mat, g, ONE / f32(xsdata.sigs[xs_index]), xsdata.scat_matrix)
+            hook = None
+            if bank is not None:
+                hook = lambda: bank(cell, x, mat, g, xs_index, rnd)  # noqa: E731
+            alive, g_new, mu_new = interaction(rnd.random(), scat_mat, xsdata, xs_index, g, rnd, sw.scatter_mode, hook)
+            if not alive:
+                ev.fate = 1
+                return cell, x, g
+            g, mu = g_new, mu_new
+            xsg = g_eff if sw.stale_xs else g
+            home_lo, home_hi, left = run_lo[cell], run_hi[cell], False
+
+
+def monte_carlo_extended(variables: Variables, xsdata: XSData, delta_x_fuel, meshid, fuel_indices, k_new, sw: Switches,
+                         tracking: str = "surface", source: str = "uniform_fuel", trace_gen=None):
+    """Generation loop of `monte_carlo` (exact tallies, one worker) with the two added modes.  Returns what
+    `monte_carlo` returns plus bank_sizes, entropy and the dense bank of every generation."""
+    G, N, gens = variables.energygroups, len(meshid), variables.generations
+    flux_out = [[ZERO] * N for _ in range(G)]
+    fission_out = [ZERO] * N
+    k_out = [ZERO] * gens
+    fixed_out = np.zeros((gens, G, N), np.uint64)
+    trace_rows, bank_sizes, entropy, banks = [], [], [], []
+    runs = material_runs(meshid)
+    tables = woodcock_tables(variables, xsdata, meshid) if tracking == "woodcock" else None
+    source_bank = []
+    k_new = f32(k_new)
+    for x in range(gens):
+        fixed = [[0] * N for _ in range(G)]
+        k, k_new = k_new, ZERO
+
+        def score(g, cell, v):
+            fixed[g][cell] += int(v * f32(2.0 ** 28))
+
+        bank = FissionBank(xsdata, variables.mattypes, ONE / k) if source == "fission_bank" else None
+        for y in range(variables.histories):
+            rnd = Stream(sw.seed, sw.seq, sw.stride, x * variables.histories + y)
+            mesh_index, start_x, mu, g = spawn_from(source_bank, fuel_indices, variables, xsdata, meshid, delta_x_fuel, rnd)
+            ev = Events()
+            if bank is not None:
+                bank.begin(y)
+            if tracking == "woodcock":
+                mesh_index, start_x, g = woodcock_history(score, variables, xsdata, meshid, runs, tables, mesh_index,
+                                                          start_x, mu, g, rnd, sw, ev, bank)
+            else:
+                alive = True
+                while alive:
+                    alive, mesh_index, mu, g, start_x = particle_travel(
+                        score, meshid, mesh_index, g, mu, start_x, variables.mattypes, G, variables.boundr,
+                        variables.boundl, xsdata, rnd, sw, ev, bank)
+            if trace_gen == x:
+                trace_rows.append((ev.collisions, ev.crossings, ev.flights, ev.reflections, rnd.rng.state & 0xFFFFFFFF,
+                                   rnd.rng.state >> 32, mesh_index, _bits(start_x), ev.fate, g))
+        if bank is not None:
+            source_bank = bank.dense()
+            banks.append(source_bank)
+            bank_sizes.append(len(source_bank))
+            entropy.append(entropy_bits(source_bank, N) if source_bank else 0.0)
+        fixed_out[x] = np.array(fixed, dtype=np.uint64)
+        tally = [[f32(float(fixed[e][i]) * (1.0 / 2.0 ** 28)) for i in range(N)] for e in range(G)]
+        fund = ONE / f32((gens - (variables.skip - 1)) % (1 << 64))
+        for e in range(G):                                                                   # src/mc_code.rs:342-362
+            for i in range(N):
+                dx, matid = meshid[i].delta_x, meshid[i].matid
+                flux = tally[e][i] / (k * f32(variables.histories) * dx)
+                xi = matid + variables.mattypes * e
+                fission_source = f32(xsdata.nut[xi]) * f32(xsdata.sigf[xi]) * flux
+                k_new = k_new + k * dx * fission_source
+                if x >= variables.skip:
+                    conversion = (f32(3565e6) * k * f32(36.2)) / (
+                        f32(200e6) * f32(1.602176634e-19) * f32(xsdata.nut[0 + variables.mattypes * 1]) * meshid[N - 1].mesh_right)
+                    flux_out[e][i] = flux_out[e][i] + flux * conversion * fund
+                    fission_out[i] = fission_out[i] + fission_source * fund
+        k_out[x] = k_new
+    return dict(flux=np.array(flux_out, f32), fission_source=np.array(fission_out, f32), k=np.array(k_out, f32),
+                tally_fixed=fixed_out, trace=np.array(trace_rows, dtype=np.uint32) if trace_rows else None,
+                bank_sizes=np.array(bank_sizes, np.uint64), entropy=np.array(entropy), banks=banks)

@@ -138,3 +138,47 @@ def test_synthetic_shapes(M, G, pins, mpfr, mpwr, bl, br, mode):
     for name in ("k", "k_fund", "flux", "fission_source", "assembly_average"):
         assert np.array_equal(bits(got[name]), bits(getattr(want, name))), name
     assert got["trace"][:, 0].sum() > 0
+
+
+@pytest.mark.parametrize("case,tracking,source", [
+    ("c", "surface", "fission_bank"), ("b", "surface", "fission_bank"),
+    ("a", "woodcock", "uniform_fuel"), ("b", "woodcock", "uniform_fuel"), ("c", "woodcock", "uniform_fuel"),
+    ("c", "woodcock", "fission_bank"),
+])
+def test_added_modes_fission_bank_and_woodcock(case, tracking, source):
+    """The modes the north star adds (no reference counterpart): the C oracle's implementation, which the GPU kernels
+    are bit-compared with, against a second statement of DESIGN.md section 5 -- per-history records, tally bins, k,
+    flux, bank sizes, the dense bank itself and its entropy."""
+    v, xs, dx, mesh, fuel = load_case(case)
+    gens, H = 3, 90
+    v.generations, v.histories, v.skip = gens, H, 1
+    variables, xsdata, dxf, meshid, fi = rp.from_product_inputs(v, xs, dx, mesh, fuel)
+    got = rp.monte_carlo_extended(variables, xsdata, dxf, meshid, fi, 1.0, rp.Switches(), tracking=tracking, source=source,
+                                  trace_gen=gens - 1)
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=gens, histories=H, skip=1, threads=1, want_tally=True, trace_gen=gens - 1,
+                           tracking_mode=tracking, source_mode=source, bank_gen=gens - 1)
+    assert np.array_equal(got["trace"], want.trace), np.flatnonzero((got["trace"] != want.trace).any(axis=1))[:5]
+    assert np.array_equal(got["tally_fixed"], want.tally_fixed)
+    for name in ("k", "flux", "fission_source"):
+        assert np.array_equal(bits(got[name]), bits(getattr(want, name))), name
+    if source == "fission_bank":
+        assert np.array_equal(got["bank_sizes"], want.bank_sizes)
+        assert np.array_equal(np.array(got["banks"][-1], np.uint64), want.bank_sites)
+        assert np.allclose(got["entropy"], want.entropy, rtol=0, atol=1e-12)
+        assert got["bank_sizes"].min() > H // 2  # the bank really fed generations 1 and 2
+
+
+def test_added_modes_with_walls_and_switches():
+    v, xs, dx, mesh, fuel = load_case("b")
+    v.boundl, v.boundr = 0.6, 0.0
+    v.generations, v.histories, v.skip = 2, 120, 1
+    variables, xsdata, dxf, meshid, fi = rp.from_product_inputs(v, xs, dx, mesh, fuel)
+    sw = rp.Switches(stale_xs=False, scatter_mode="rust_pre182")
+    got = rp.monte_carlo_extended(variables, xsdata, dxf, meshid, fi, 1.0, sw, tracking="woodcock", source="fission_bank", trace_gen=1)
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=2, histories=120, skip=1, threads=1, want_tally=True, trace_gen=1,
+                           tracking_mode="woodcock", source_mode="fission_bank", stale_xs=False, scatter_mode="rust_pre182")
+    assert np.array_equal(got["trace"], want.trace) and np.array_equal(got["tally_fixed"], want.tally_fixed)
+    assert np.array_equal(got["bank_sizes"], want.bank_sizes)
+    assert (got["trace"][:, 8] == 2).any() and (got["trace"][:, 3] > 0).any()  # leaks on the right, reflections on the left

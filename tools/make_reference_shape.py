@@ -23,6 +23,9 @@ out = {
     "fission_source_shape": (fission / fission.sum()).round(9).tolist(),
     "thermal_flux_shape": (flux[3] / flux[3].sum()).round(9).tolist(),
     "k_relative_sd_per_generation": float(k.std(ddof=1) / k.mean()),
+    # the four flux rows themselves (7 significant digits), for the piecewise-proportionality test: within one material
+    # the shipped flux is a constant multiple of the flux of HEAD's semantics
+    "flux_rows": [[float(f"{v:.7g}") for v in row] for row in flux],
     "generations": int(len(k)),
 }
 json.dump(out, open(OUT, "w"))

@@ -1,0 +1,58 @@
+"""GPU-vs-oracle differential fuzz on random slab problems (through the C ABI, bit-exact).
+
+Same generator as the CPU-side fuzz of the two restatements (tools/fuzz_restatements.py): random material / group
+counts (G = 2..8), pin layouts, mesh refinements, wall albedos, master streams, scatter probe orders, the stale-index
+switch, both tracking modes and both source modes, at a few thousand histories per generation.
+
+Opt-in: NRAPS_GPU_FUZZ=<number of problems> (unset => skipped).  Written after this round's GPU budget was spent, so it
+has not yet run on a device; the fixed shapes of test_gpu_parity.py::test_synthetic_shapes_bit_exact remain the
+default coverage of the generic-G / many-material kernels."""
+import os
+
+import numpy as np
+import pytest
+
+import nraps_b200 as nb
+from oracle import oracle as orc
+from tests.util import bits, oracle_inputs, synthetic_case
+
+pytestmark = pytest.mark.gpu
+N_CASES = int(os.environ.get("NRAPS_GPU_FUZZ", "0"))
+
+
+@pytest.mark.skipif(N_CASES == 0, reason="opt-in: set NRAPS_GPU_FUZZ=<number of random problems>")
+def test_random_problems_bit_exact_on_the_gpu():
+    from tools.fuzz_restatements import random_case
+
+    rng = np.random.default_rng(int(os.environ.get("NRAPS_GPU_FUZZ_SEED", "11")))
+    ran, failures = 0, []
+    while ran < N_CASES:
+        c = random_case(rng)
+        try:
+            args = synthetic_case(c["M"], c["G"], c["pins"], c["mpfr"], c["mpwr"], seed=c["seed"], boundl=c["bl"], boundr=c["br"],
+                                  numass=c["numass"])
+        except Exception:
+            continue  # the reference panics on this layout (mesh_gen trims past the ends)
+        if len(args[4]) == 0 or len(args[3].matid) < c["numass"]:
+            continue
+        H, gens = 100 * c["H"], c["gens"]
+        kw = dict(scatter_mode=c["scatter_mode"], stale_xs=c["stale_xs"], tracking_mode=c["tracking"], source_mode=c["source"],
+                  seed=c["rng_seed"], stride=c["stride"])
+        got = nb.monte_carlo(*args, 1.0, generations=gens, histories=H, skip=1, want_tally=True, stream=c["rng_seq"], **kw)
+        deck, m = oracle_inputs(*args)
+        want = orc.monte_carlo(deck, m, generations=gens, histories=H, skip=1, threads=8, want_tally=True, seq=c["rng_seq"], **kw)
+        bad = []
+        if not np.array_equal(got.tally_fixed, want.tally_fixed):
+            bad.append("tally_fixed")
+        for name in ("k", "k_fund", "flux", "assembly_average", "fission_source"):
+            if not np.array_equal(bits(getattr(got, name)), bits(getattr(want, name))):
+                bad.append(name)
+        for name in ("histories", "collisions", "flights", "leaks", "truncated"):
+            if got.counters[name] != want.counters[name]:
+                bad.append(name)
+        if c["source"] == "fission_bank" and not np.array_equal(got.bank_sizes, want.bank_sizes):
+            bad.append("bank_sizes")
+        if bad:
+            failures.append((bad, c))
+        ran += 1
+    assert not failures, failures[:5]

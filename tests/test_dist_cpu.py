@@ -77,6 +77,15 @@ class OracleEngine:
         self.per_gen.append(self.tally.numpy().copy())
 
 
+def _free_port() -> int:
+    """A TCP port nobody listens on right now (asked of the OS), so two suites on one host do not collide."""
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
@@ -101,7 +110,7 @@ def test_two_rank_gloo_equals_single_rank(tmp_path):
     import torch
     import torch.multiprocessing as mp
 
-    port = 29500 + (os.getpid() % 400)
+    port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
     assert np.array_equal(r0, r1)  # every rank holds the same reduced tally
@@ -152,7 +161,7 @@ def test_two_rank_gloo_bank_gather_is_rank_ordered_and_identical_everywhere(tmp_
     the same bank, rank 0's sites first -- what makes generation g+1 independent of the number of GPUs."""
     import torch.multiprocessing as mp
 
-    port = 29900 + (os.getpid() % 90)
+    port = _free_port()
     mp.spawn(_bank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     b0, b1 = np.load(tmp_path / "bank0.npy"), np.load(tmp_path / "bank1.npy")
     assert np.array_equal(b0, b1)

@@ -221,7 +221,7 @@ def run_ours(a):
     gens_total = W + K
 
     base_opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode,
-                     spawn_batch=a.spawn_batch, walk_cap=a.walk_cap)
+                     spawn_batch=a.spawn_batch, walk_cap=a.walk_cap, slots_per_thread=a.slots_per_thread)
     opts = dict(base_opts, tracking_mode=a.tracking, kernel_variant=a.variant)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
@@ -368,9 +368,11 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--spawn-batch", type=int, default=0)
     ap.add_argument("--walk-cap", type=int, default=0)
+    ap.add_argument("--slots-per-thread", type=int, default=0, help="block_event variant: neutrons banked per thread")
     ap.add_argument("--tracking", default="surface", choices=["surface", "woodcock"],
                     help="surface = the reference's cell-by-cell tracking (headline, bit-comparable); woodcock = delta tracking")
-    ap.add_argument("--variant", default="fused", choices=["fused", "event"], help="kernel variant (event = SoA-bank pipeline, woodcock only)")
+    ap.add_argument("--variant", default="fused", choices=["fused", "event", "block_event"],
+                    help="kernel variant (event = SoA-bank pipeline in HBM, woodcock only; block_event = experimental on-chip bank, surface only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other-tracking-mode measurement")
     a = ap.parse_args()

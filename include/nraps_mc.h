@@ -61,7 +61,10 @@ typedef struct nraps_problem {
 enum { NRAPS_SCATTER_SINGLE_XI = 0, NRAPS_SCATTER_RUST_PRE182 = 1, NRAPS_SCATTER_RUST_182 = 2 };
 enum { NRAPS_SOURCE_UNIFORM_FUEL = 0, NRAPS_SOURCE_FISSION_BANK = 1 };
 enum { NRAPS_TRACK_SURFACE = 0, NRAPS_TRACK_WOODCOCK = 1 };
-enum { NRAPS_KERNEL_FUSED = 0, NRAPS_KERNEL_EVENT = 1 };
+/* FUSED: one persistent lane per neutron (default).  EVENT: the structure-of-arrays bank pipeline in HBM (Woodcock only).
+ * BLOCK_EVENT (experimental): surface tracking with the neutrons of a block banked in shared memory and sorted by their
+ * next event every round (uniform source only; no trace, no generation batching, mesh image must fit shared memory). */
+enum { NRAPS_KERNEL_FUSED = 0, NRAPS_KERNEL_EVENT = 1, NRAPS_KERNEL_BLOCK_EVENT = 2 };
 
 typedef struct nraps_options {
     uint64_t seed, stream, stride; /* PCG32 master (seed, sequence) and per-history jump; 0,0,0 => 42,54,152917 */
@@ -78,7 +81,7 @@ typedef struct nraps_options {
     int32_t bank_cap;              /* fission_bank: sites kept per history, 1..255; 0 = 8 */
     int32_t spawn_batch;           /* refill a warp's dead lanes only once this many are dead (0 = auto) */
     int32_t walk_cap;              /* surface tracking: crossings per lane before the warp regroups; 0 = auto, -1 = unlimited */
-    int32_t reserved1;
+    int32_t slots_per_thread;      /* block_event variant: neutrons banked per thread of a block; 0 = 3 (was reserved1) */
     uint64_t max_flights;          /* per-history safety cap; 0 = 1<<24               */
 } nraps_options;
 

@@ -42,7 +42,7 @@ class Options(C.Structure):
         ("device", C.c_int32), ("scatter_mode", C.c_int32), ("stale_xs", C.c_int32), ("source_mode", C.c_int32),
         ("tracking_mode", C.c_int32), ("kernel_variant", C.c_int32), ("threads_per_block", C.c_int32),
         ("blocks_per_sm", C.c_int32), ("chunk", C.c_int32), ("quiet", C.c_int32), ("bank_cap", C.c_int32),
-        ("spawn_batch", C.c_int32), ("walk_cap", C.c_int32), ("reserved1", C.c_int32), ("max_flights", C.c_uint64),
+        ("spawn_batch", C.c_int32), ("walk_cap", C.c_int32), ("slots_per_thread", C.c_int32), ("max_flights", C.c_uint64),
     ]
 
 

@@ -25,7 +25,7 @@ from ._lib import CT_NAMES, CT_WORDS, TR_NAMES, TR_WORDS, Options, Problem, Resu
 SCATTER_MODES = {"single_xi": 0, "rust_pre182": 1, "rust_182": 2}
 SOURCE_MODES = {"uniform_fuel": 0, "fission_bank": 1}
 TRACKING_MODES = {"surface": 0, "woodcock": 1}
-KERNEL_VARIANTS = {"fused": 0, "event": 1}
+KERNEL_VARIANTS = {"fused": 0, "event": 1, "block_event": 2}
 
 
 @dataclass
@@ -200,12 +200,14 @@ class _Marshalled:
 
 def make_options(*, seed=0, stream=0, stride=0, device=0, scatter_mode="single_xi", stale_xs=True,
                  source_mode="uniform_fuel", tracking_mode="surface", kernel_variant="fused", threads_per_block=0,
-                 blocks_per_sm=0, chunk=0, quiet=True, max_flights=0, bank_cap=0, spawn_batch=0, walk_cap=0) -> Options:
+                 blocks_per_sm=0, chunk=0, quiet=True, max_flights=0, bank_cap=0, spawn_batch=0, walk_cap=0,
+                 slots_per_thread=0) -> Options:
     return Options(
         seed=seed, stream=stream, stride=stride, device=device, scatter_mode=SCATTER_MODES[scatter_mode],
         stale_xs=int(bool(stale_xs)), source_mode=SOURCE_MODES[source_mode], tracking_mode=TRACKING_MODES[tracking_mode],
         kernel_variant=KERNEL_VARIANTS[kernel_variant], threads_per_block=threads_per_block,
-        blocks_per_sm=blocks_per_sm, chunk=chunk, quiet=int(bool(quiet)), bank_cap=bank_cap, spawn_batch=spawn_batch, walk_cap=walk_cap, reserved1=0,
+        blocks_per_sm=blocks_per_sm, chunk=chunk, quiet=int(bool(quiet)), bank_cap=bank_cap, spawn_batch=spawn_batch, walk_cap=walk_cap,
+        slots_per_thread=slots_per_thread,
         max_flights=max_flights,
     )
 

@@ -186,6 +186,9 @@ struct nraps_mc_ctx {
     EventBank ev{};
     uint64_t ev_cap = 0;
     uint32_t ev_iterations = 0; // advance/collide/compact rounds of the last generation
+
+    // block-level event pipeline (kernel_variant = NRAPS_KERNEL_BLOCK_EVENT): launch geometry chosen at creation
+    uint32_t bev_block = 0, bev_grid = 0, bev_slots = 0, bev_smem = 0;
 };
 
 namespace {
@@ -203,7 +206,12 @@ int validate(const nraps_problem *p, const nraps_options *o)
     if ((uint64_t)p->M * p->G * p->G * p->G > 8192) return NRAPS_ERR_TOO_LARGE;
     if (o->scatter_mode < 0 || o->scatter_mode > NRAPS_SCATTER_RUST_182) return NRAPS_ERR_OPTION;
     if (o->source_mode < 0 || o->source_mode > NRAPS_SOURCE_FISSION_BANK || o->tracking_mode < 0 || o->tracking_mode > NRAPS_TRACK_WOODCOCK ||
-        o->kernel_variant < 0 || o->kernel_variant > NRAPS_KERNEL_EVENT || o->bank_cap < 0 || o->bank_cap > 255)
+        o->kernel_variant < 0 || o->kernel_variant > NRAPS_KERNEL_BLOCK_EVENT || o->bank_cap < 0 || o->bank_cap > 255 ||
+        o->slots_per_thread < 0 || o->slots_per_thread > 64)
+        return NRAPS_ERR_OPTION;
+    // the block-level event pipeline (experimental) is built for surface tracking with the uniform source
+    if (o->kernel_variant == NRAPS_KERNEL_BLOCK_EVENT &&
+        (o->tracking_mode != NRAPS_TRACK_SURFACE || o->source_mode != NRAPS_SOURCE_UNIFORM_FUEL))
         return NRAPS_ERR_OPTION;
     // the event pipeline is built for Woodcock tracking with the uniform source (one event = one tentative collision)
     if (o->kernel_variant == NRAPS_KERNEL_EVENT &&
@@ -334,6 +342,12 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         CU(run_event_generation(P, c->ev, c->layout.total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
         return NRAPS_OK;
     }
+    if (c->opt.kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) {
+        if (trace || nb != 1) return NRAPS_ERR_OPTION;
+        if (count >> 32) return NRAPS_ERR_TOO_LARGE; // the block's source cursor is 32-bit
+        CU(launch_block_event(P, dim3(c->bev_grid), dim3(c->bev_block), c->bev_smem, c->bev_slots, s));
+        return NRAPS_OK;
+    }
     const int ti = trace ? 1 : 0;
     if (!(c->prepared & (1u << ti))) { // once per (kernel, trace) instantiation: shared-memory opt-in and launch geometry
         if (!c->big)
@@ -413,12 +427,12 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     SmemLayout L = make_layout(M, G, N, NF, NB, 0);
     const uint32_t big = L.total > kMaxSmem ? 1u : 0u;
     if (big) L = make_layout(M, G, N, NF, NB, 1);
-    if (L.total > kMaxSmem || (big && o->kernel_variant == NRAPS_KERNEL_EVENT)) return NRAPS_ERR_TOO_LARGE;
+    if (L.total > kMaxSmem || (big && o->kernel_variant != NRAPS_KERNEL_FUSED)) return NRAPS_ERR_TOO_LARGE;
     // Generations of the uniform source are independent, and one of the shipped decks' 1e5..1e6 histories leaves most
     // of the 148 SMs idle: let a launch carry enough generations for ~2^23 histories, each scoring into its own G
     // tally rows, as long as the block still fits twice on an SM.
     uint32_t batch = 1;
-    if (allow_batch && !big && o->source_mode == NRAPS_SOURCE_UNIFORM_FUEL && o->kernel_variant != NRAPS_KERNEL_EVENT) {
+    if (allow_batch && !big && o->source_mode == NRAPS_SOURCE_UNIFORM_FUEL && o->kernel_variant == NRAPS_KERNEL_FUSED) {
         uint64_t want = std::min<uint64_t>(std::min<uint64_t>((1ull << 23) / p->histories, p->generations), 64);
         while (want > 1 && make_layout(M, G, N, NF, NB, 0, (uint32_t)want * G).total > 100u * 1024u) --want;
         if (want > 1) {
@@ -458,6 +472,23 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     uint32_t threads = o->threads_per_block > 0 ? (uint32_t)o->threads_per_block : 1024u / bps;
     threads = std::max(32u, std::min(1024u, threads / 32u * 32u));
     c->blocks_per_sm = bps; c->block = threads; c->grid = (uint32_t)c->sm_count * bps;
+    if (o->kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) {
+        // 2 x 512 threads per SM with 3 neutrons banked per thread unless told otherwise; shrink the bank, then the
+        // residency, until the mesh image + the bank of every resident block fit the 227 KB of one SM
+        uint32_t bb = o->threads_per_block > 0 ? threads : 512u, bbps = o->blocks_per_sm > 0 ? bps : 2u;
+        uint32_t spt = o->slots_per_thread > 0 ? (uint32_t)o->slots_per_thread : 3u;
+        TransportParams q{};
+        q.M = M; q.G = G; q.N = N; q.NF = NF; q.NB = NB; q.rows = G;
+        while (bb * spt > 65535u) --spt; // slot ids are 16-bit
+        while ((uint64_t)bbps * (block_event_smem(q, bb * spt) + 1024) > 233472ull) {
+            if (spt > 1) --spt;
+            else if (bbps > 1) { --bbps; spt = o->slots_per_thread > 0 ? (uint32_t)o->slots_per_thread : 3u; }
+            else { delete c; return NRAPS_ERR_TOO_LARGE; }
+        }
+        c->bev_block = bb; c->bev_grid = (uint32_t)c->sm_count * bbps; c->bev_slots = bb * spt;
+        c->bev_smem = block_event_smem(q, c->bev_slots);
+        if (o->chunk <= 0) c->chunk = 256u; // histories a block claims per global atomic
+    }
 
     // ---- derived tables
     std::vector<float> edges(N + 1);
@@ -789,6 +820,9 @@ extern "C" int nraps_mc_launch_info(nraps_mc_ctx *c, uint32_t out[6])
 {
     if (!c || !out) return NRAPS_ERR_NULL;
     out[0] = c->geo_grid[0] ? c->geo_grid[0] : c->grid; out[1] = c->geo_block[0] ? c->geo_block[0] : c->block; out[2] = c->layout.total; out[3] = c->blocks_per_sm;
+    if (c->opt.kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) {
+        out[0] = c->bev_grid; out[1] = c->bev_block; out[2] = c->bev_smem; out[3] = c->bev_grid / (uint32_t)c->sm_count;
+    }
     out[4] = (uint32_t)c->sm_count; out[5] = c->opt.kernel_variant == NRAPS_KERNEL_EVENT ? c->ev_iterations : c->chunk;
     return NRAPS_OK;
 }

@@ -137,6 +137,8 @@ cudaError_t launch_source(const TransportParams &p, bool bank, uint4 *out, cudaS
 cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
 cudaError_t prepare_woodcock(uint32_t smem_bytes, uint32_t G, bool trace, bool bank);
 cudaError_t run_event_generation(const TransportParams &p, const EventBank &b, uint32_t smem, int sm_count, cudaStream_t s, uint32_t *iters);
+uint32_t block_event_smem(const TransportParams &p, uint32_t slots);
+cudaError_t launch_block_event(const TransportParams &p, dim3 grid, dim3 block, uint32_t smem, uint32_t slots, cudaStream_t s);
 cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s);
 cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
                                 double *entropy_out, unsigned long long *size_out, cudaStream_t s);

@@ -73,7 +73,7 @@ template <bool BIG> static __device__ __forceinline__ uint32_t tally_ref(uint32_
     return BIG ? (uint32_t)bin : lo_base + 4u * (uint32_t)bin;
 }
 
-template <int TG> static __device__ __forceinline__ int search_cdf(const float *cdf, int G, float v)
+template <int TG> static NRAPS_HD int search_cdf(const float *cdf, int G, float v)
 {
     if (TG == 4) { // partition_point on 4 entries, probes 2 then 3 or 1 then 0
         const float4 c = *reinterpret_cast<const float4 *>(cdf);
@@ -105,7 +105,7 @@ template <int TG> static __device__ __forceinline__ int search_cdf_global(const 
 }
 
 template <int TG>
-static __device__ __forceinline__ int sample_group(const float *cdf, int G, int mode, uint64_t &rng, uint64_t inc)
+static NRAPS_HD int sample_group(const float *cdf, int G, int mode, uint64_t &rng, uint64_t inc)
 {
     const int n = TG ? TG : G;
     if (mode == NRAPS_SCATTER_SINGLE_XI) return search_cdf<TG>(cdf, G, pcg32_unit(rng, inc));

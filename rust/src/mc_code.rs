@@ -22,7 +22,7 @@ struct NrapsOptions {
     seed: u64, stream: u64, stride: u64,
     device: i32, scatter_mode: i32, stale_xs: i32, source_mode: i32, tracking_mode: i32,
     kernel_variant: i32, threads_per_block: i32, blocks_per_sm: i32, chunk: i32, quiet: i32,
-    bank_cap: i32, spawn_batch: i32, walk_cap: i32, reserved1: i32,
+    bank_cap: i32, spawn_batch: i32, walk_cap: i32, slots_per_thread: i32,
     max_flights: u64,
 }
 

@@ -397,6 +397,8 @@ def test_validation_codes_come_before_any_cuda_call_and_there_is_no_fallback():
     assert code(xsdata=nb.XSData(**{**xs.__dict__, "inv_sigtr": xs.inv_sigtr * f32(-1)})) == 4
     assert code(xsdata=nb.XSData(**{**xs.__dict__, "inv_sigtr": xs.inv_sigtr * f32(np.inf)})) == 4
     assert code(kernel_variant="event") == 7                                  # the event pipeline is Woodcock-only
+    assert code(kernel_variant="block_event", tracking_mode="woodcock") == 7  # the block-level pipeline is surface-only ...
+    assert code(kernel_variant="block_event", source_mode="fission_bank") == 7  # ... and uniform-source-only
     assert code(bank_cap=300) == 7
     v1 = nb.Variables(**{**v.__dict__, "energygroups": 1})
     assert code(variables=v1) == 2                                            # G >= 2: nut[M*1] (src/mc_code.rs:356)

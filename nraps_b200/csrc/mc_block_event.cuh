@@ -161,18 +161,21 @@ template <class C> NRAPS_HD int walk(C &c, const TransportParams &P, Neutron &n)
     const uint32_t e_first = e_ref;
     const uint32_t t_stop = t_ref + (uint32_t)(stride * steps);
     float xc = n.x;
-    for (;;) {
+    // one crossing; false = the walk is over (collision, or the stop edge reached).  Like the lane kernel's loop it
+    // carries neither x nor the cell (both are rebuilt from the edge reference afterwards) and is unrolled by four.
+    auto step = [&]() -> bool {
         end = fadd(xc, n.ds);
         const float edge = c.edge(e_ref);
         const float t = fsub(xc, edge);
-        if (!(fabsf(fsub(end, xc)) > fabsf(t))) break; // collision at `end`
-        c.score(t_ref, fabsf(fast_div(t, rc)));         // cross_mesh, src/mc_code.rs:171-181
+        if (!(fabsf(fsub(end, xc)) > fabsf(t))) return false; // collision at `end`
+        c.score(t_ref, fabsf(fast_div(t, rc)));                // cross_mesh, src/mc_code.rs:171-181
         n.ds = fadd(n.ds, t);
         xc = edge;
         e_ref += (uint32_t)stride;
         t_ref += (uint32_t)stride;
-        if (t_ref == t_stop) break;
-    }
+        return t_ref != t_stop;
+    };
+    while (step() && step() && step() && step()) {}
     const int moved = (int)(e_ref - e_first) / 4; // signed cells travelled
     if (moved) {
         n.x = c.edge(e_ref - (uint32_t)stride);   // x after a crossing is the edge just crossed (src/mc_code.rs:72,77)
@@ -272,6 +275,7 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
                        n_dead = c.load_shared(&b.k[K_DEAD0 + p]);
         // ---- phase AB: the three lists one after another; every entry ends in walk[p][class] or in dead[p^1]
         const uint32_t n_ab = n_coll + n_dead + n_fly;
+        if (C::kStats && tid == 0) c.note_round(n_coll, n_dead, n_fly);
         for (uint32_t base = 0; base < n_ab; base += nthr) {
             const uint32_t i = base + tid;
             const bool active = i < n_ab;
@@ -327,7 +331,9 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
                 if (active) {
                     slot = b.walk(p, cls)[i];
                     Neutron n = load_neutron(b, slot);
+                    const int cell0 = n.cell;
                     out = walk(c, P, n);
+                    if (C::kStats) c.note_walk(cls, i, n.cell > cell0 ? n.cell - cell0 : cell0 - n.cell); // emulation only
                     if (out == OUT_MATCHANGE) {
                         if ((unsigned)n.cell >= (unsigned)P.N) {
                             out = OUT_TRUNC; // unreachable for validated input

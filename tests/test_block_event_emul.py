@@ -26,7 +26,7 @@ def emul():
     L = C.CDLL(LIB)
     L.bev_emul_generation.argtypes = [C.POINTER(orc.Problem), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                       C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     return L
 
 
@@ -57,7 +57,7 @@ def _run(emul, args, *, H, gen, blocks=3, threads=8, slots=40, chunk=16, walk_ca
     counters = np.zeros(8, np.uint64)
     rc = emul.bev_emul_generation(C.byref(p), gen, 0, H, seed, seq, stride, SCATTER[scatter_mode], int(stale_xs), walk_cap, max_flights,
                                   blocks, threads, slots, chunk, tally.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                  counters.ctypes.data_as(C.POINTER(C.c_uint64)))
+                                  counters.ctypes.data_as(C.POINTER(C.c_uint64)), None)
     assert rc == 0
     want = orc.monte_carlo(deck, m, generations=gen + 1, histories=H, skip=1, threads=4, want_tally=True, trace_gen=gen,
                            scatter_mode=scatter_mode, stale_xs=stale_xs, seed=seed, seq=seq, stride=stride,

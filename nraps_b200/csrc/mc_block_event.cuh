@@ -5,23 +5,29 @@
 // the registers of one lane for its whole life and a warp trip runs flight / walk / collide for whatever mix of
 // neutrons its lanes hold (ncu, profiles/r1r: 18 of 32 lanes busy; the collide stage runs with 10 lanes, a walk lasts
 // as long as the longest of the warp, 8 cells in a fuel pin against 4 in a water gap).  Here the neutrons of a block
-// live in shared memory (28 bytes each, structure of arrays, several per thread) and every round sorts them by what
-// they need next:
+// are 28-byte records in shared memory (structure of arrays, several per thread) and a record MOVES to the list of
+// the event it needs next, so a warp always reads and writes 32 consecutive records (no bank conflicts):
 //
-//   phase AB   list `coll`  : collide (src/mc_code.rs:182-210), then the survivor's next flight draw (:147-148)
-//              list `dead`  : adopt a history born by source_kernel (src/mc_code.rs:40-53), then its first flight
-//              list `fly`   : flight draw only (the neutron entered another material run, :179-181)
-//   phase C    list `walk[0]`, `walk[1]` (short / long material runs): boundary + cross_mesh loop (:151-181, 56-79)
+//   arena A   `coll` grows up from record 0, `go` grows down from record S-1
+//   arena B   `walk[0]` (short material runs) grows up, `walk[1]` (long runs) grows down
 //
-// so that the lanes of a warp run the same stage on neutrons with walks of similar length.  That is the north star's
-// event-based pipeline over structure-of-arrays banks, kept on chip: the HBM version of it (mc_event.cu) lost 8x to
-// bank round trips and launch tails (profiles/r1e); 227 KB of shared memory per SM hold the bank instead.
+//   phase AB  reads arena A: coll -> collide (src/mc_code.rs:182-210), then the survivor's flight draw (:147-148);
+//                            go   -> flight draw (the neutron entered another material run, :179-181), or nothing
+//                                    for a walk that was only suspended (flag `pending`);
+//             and adopts histories born by source_kernel (src/mc_code.rs:40-53) into the free capacity;
+//             writes arena B by the length class of the material run the neutron sits in.
+//   phase C   reads arena B: boundary + cross_mesh loop (:151-181, 56-79); writes arena A: coll / go; leaked and
+//             truncated histories simply are not written back.
+//
+// A list that grows up and one that grows down share an arena of S records exactly, whatever their split.  That is the
+// north star's event-based pipeline over structure-of-arrays banks, kept on chip: the HBM version of it (mc_event.cu)
+// lost 8x to bank round trips and launch tails (profiles/r1e); 227 KB of shared memory per SM hold the bank instead.
 //
 // The per-thread body below is written against a small context type C (thread index, barrier, shared / global
 // atomics, warp-aggregated list claims, shared-space loads of the mesh tables and the tally score), so that the very
 // same code runs as a CUDA block (mc_block_event.cu) and, for tests only, on CPU threads (tests/emul) where it is
 // bit-compared with the oracle without a GPU.  Restrictions of this variant: uniform source, no trace records, no
-// generation batching, mesh image in shared memory (no BIG mode); everything else falls back to NRAPS_ERR_OPTION.
+// generation batching, mesh image in shared memory (no BIG mode); everything else is refused with NRAPS_ERR_OPTION.
 #pragma once
 #include "mc_lane.cuh"
 
@@ -30,44 +36,50 @@ namespace bev {
 
 enum { OUT_COLLIDE = 1, OUT_MATCHANGE = 2, OUT_PENDING = 3, OUT_LEAK = 4, OUT_TRUNC = 5 };
 
-// counters in shared memory (u32 words)
+// counters in shared memory (u32 words); list lengths exist once per round parity
 enum {
-    K_COLL0 = 0, K_COLL1, K_FLY0, K_FLY1, K_DEAD0, K_DEAD1, // list lengths, one per parity
-    K_WALK00, K_WALK01, K_WALK10, K_WALK11,                // walk[parity][class]
-    K_SRC_NEXT, K_SRC_END, K_EXHAUSTED, K_DONE, K_SPLIT,
+    K_COLL0 = 0, K_COLL1, K_GO0, K_GO1,                    // arena A lists, [parity]
+    K_WALK00, K_WALK01, K_WALK10, K_WALK11,                // arena B lists, [parity][class]
+    K_SRC_NEXT, K_SRC_END, K_EXHAUSTED, K_DONE, K_SPLIT, K_ADOPT,
     K_WORDS = 16
 };
 
-// the block's neutron bank and event lists (pointers into shared memory, or into a heap image on the host)
-struct Bank {
-    float *x, *mu, *ds;          // [S] position, direction cosine, signed distance left to the collision site (or the site itself)
-    uint32_t *pk, *rlo, *rhi, *hf; // [S] cell | g<<16 | xsg<<19 | mat<<22 | pending<<28, rng state, flights so far
-    uint16_t *lists;             // ten slot lists of [S] each, addressed arithmetically (a pointer table indexed by the
-                                 // parity would live in local memory): coll[2] | fly[2] | dead[2] | walk[2][2]
-    uint32_t *k;                 // [K_WORDS]
-    uint32_t S;
-    NRAPS_HD uint16_t *coll(uint32_t p) const { return lists + (0u + p) * S; }
-    NRAPS_HD uint16_t *fly(uint32_t p) const { return lists + (2u + p) * S; }
-    NRAPS_HD uint16_t *dead(uint32_t p) const { return lists + (4u + p) * S; }
-    NRAPS_HD uint16_t *walk(uint32_t p, uint32_t cls) const { return lists + (6u + 2u * p + cls) * S; }
+// one arena of S neutron records, structure of arrays
+struct Arena {
+    float *x, *mu, *ds;            // position, direction cosine, signed distance left to the collision site (or the site itself)
+    uint32_t *pk, *rlo, *rhi, *hf; // cell | g<<16 | xsg<<19 | mat<<22 | pending<<28, rng state, flights so far
 };
 
-__host__ __device__ inline uint32_t bank_bytes(uint32_t S) { return S * (7 * 4 + 10 * 2) + K_WORDS * 4; }
+struct Bank {
+    Arena A, B;
+    uint32_t *k; // [K_WORDS]
+    uint32_t S;
+};
 
-// carve a Bank out of `raw` (16-byte aligned)
+__host__ __device__ inline uint32_t bank_bytes(uint32_t S) { return 2 * S * 7 * 4 + K_WORDS * 4; }
+
+__host__ __device__ inline Arena make_arena(uint32_t *raw, uint32_t S)
+{
+    Arena a;
+    a.x = reinterpret_cast<float *>(raw);
+    a.mu = a.x + S;
+    a.ds = a.mu + S;
+    a.pk = raw + 3 * S;
+    a.rlo = a.pk + S;
+    a.rhi = a.rlo + S;
+    a.hf = a.rhi + S;
+    return a;
+}
+
+// carve a Bank out of `raw` (4-byte aligned)
 __host__ __device__ inline Bank make_bank(unsigned char *raw, uint32_t S)
 {
     Bank b;
     b.S = S;
-    b.x = reinterpret_cast<float *>(raw);
-    b.mu = b.x + S;
-    b.ds = b.mu + S;
-    b.pk = reinterpret_cast<uint32_t *>(b.ds + S);
-    b.rlo = b.pk + S;
-    b.rhi = b.rlo + S;
-    b.hf = b.rhi + S;
-    b.k = b.hf + S;
-    b.lists = reinterpret_cast<uint16_t *>(b.k + K_WORDS);
+    uint32_t *w = reinterpret_cast<uint32_t *>(raw);
+    b.k = w;
+    b.A = make_arena(w + K_WORDS, S);
+    b.B = make_arena(w + K_WORDS + 7 * S, S);
     return b;
 }
 
@@ -79,24 +91,24 @@ struct Neutron {
     uint32_t hf;
 };
 
-NRAPS_HD Neutron load_neutron(const Bank &b, uint32_t s)
+NRAPS_HD Neutron load_neutron(const Arena &a, uint32_t s)
 {
     Neutron n;
-    n.x = b.x[s]; n.mu = b.mu[s]; n.ds = b.ds[s];
-    const uint32_t pk = b.pk[s];
+    n.x = a.x[s]; n.mu = a.mu[s]; n.ds = a.ds[s];
+    const uint32_t pk = a.pk[s];
     n.cell = (int)(pk & 0xffffu); n.g = (int)((pk >> 16) & 7u); n.xsg = (int)((pk >> 19) & 7u); n.mat = (int)((pk >> 22) & 63u);
     n.pending = ((pk >> 28) & 1u) != 0;
-    n.rng = (uint64_t)b.rlo[s] | ((uint64_t)b.rhi[s] << 32);
-    n.hf = b.hf[s];
+    n.rng = (uint64_t)a.rlo[s] | ((uint64_t)a.rhi[s] << 32);
+    n.hf = a.hf[s];
     return n;
 }
 
-NRAPS_HD void store_neutron(const Bank &b, uint32_t s, const Neutron &n)
+NRAPS_HD void store_neutron(const Arena &a, uint32_t s, const Neutron &n)
 {
-    b.x[s] = n.x; b.mu[s] = n.mu; b.ds[s] = n.ds;
-    b.pk[s] = (uint32_t)n.cell | ((uint32_t)n.g << 16) | ((uint32_t)n.xsg << 19) | ((uint32_t)n.mat << 22) | ((n.pending ? 1u : 0u) << 28);
-    b.rlo[s] = (uint32_t)n.rng; b.rhi[s] = (uint32_t)(n.rng >> 32);
-    b.hf[s] = n.hf;
+    a.x[s] = n.x; a.mu[s] = n.mu; a.ds[s] = n.ds;
+    a.pk[s] = (uint32_t)n.cell | ((uint32_t)n.g << 16) | ((uint32_t)n.xsg << 19) | ((uint32_t)n.mat << 22) | ((n.pending ? 1u : 0u) << 28);
+    a.rlo[s] = (uint32_t)n.rng; a.rhi[s] = (uint32_t)(n.rng >> 32);
+    a.hf[s] = n.hf;
 }
 
 struct Counts {
@@ -106,6 +118,10 @@ struct Counts {
 // src/mc_code.rs:147-148 (and :209): one flight draw.  false = the flight cap truncated the history.
 template <class C> NRAPS_HD bool flight(C &c, const TransportParams &P, Neutron &n, Counts &ct)
 {
+    if (n.pending) { // a walk that was only suspended (walk cap, wall cell) goes on with the flight it has
+        n.pending = false;
+        return true;
+    }
     if (n.hf >= P.max_flights) return false;
     n.ds = fmul(fmul(n.mu, -mc_logf(pcg32_unit(n.rng, P.rng_inc))), c.inv_sigtr(n.mat + (int)P.M * n.xsg));
     ++n.hf;
@@ -210,7 +226,7 @@ template <int TG, class C> NRAPS_HD bool collide(C &c, const TransportParams &P,
     return true;
 }
 
-// a dead slot takes the next history of the block's source range; false = none left right now
+// the next history of the block's source range comes to life; false = none left right now
 template <class C> NRAPS_HD bool adopt(C &c, const TransportParams &P, const Bank &b, Neutron &n)
 {
     if (c.load_shared(&b.k[K_EXHAUSTED])) return false;
@@ -236,11 +252,9 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
 {
     const uint32_t tid = c.tid(), nthr = c.nthreads(), S = b.S;
     const uint32_t n_total = (uint32_t)(P.hist_end - P.hist_begin);
-    // ---- set-up: every slot starts dead; material runs longer than half the longest run are class 1 ("long")
-    for (uint32_t i = tid; i < S; i += nthr) b.dead(0)[i] = (uint16_t)i;
+    // ---- set-up: the bank starts empty; material runs longer than half the longest run are class 1 ("long")
     if (tid == 0) {
         for (int i = 0; i < K_WORDS; ++i) b.k[i] = 0u;
-        b.k[K_DEAD0] = S;
         uint32_t longest = 1;
         for (uint32_t i = 0; i < P.N;) {
             const uint32_t rb = c.run_bounds((int)i);
@@ -252,10 +266,11 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
     }
     uint32_t p = 0; // parity of the lists phase AB reads
     for (;;) {
-        c.sync(); // B1: every push of the previous round is visible
+        c.sync(); // B1: every record phase C of the previous round wrote is visible
         if (tid == 0) {
             b.k[K_WALK00 + 2 * (p ^ 1)] = 0u; // the walk lists phase C of the previous round consumed
             b.k[K_WALK01 + 2 * (p ^ 1)] = 0u;
+            const uint32_t live = b.k[K_COLL0 + p] + b.k[K_GO0 + p];
             if (!b.k[K_EXHAUSTED] && b.k[K_SRC_NEXT] >= b.k[K_SRC_END]) { // next chunk of histories for this block
                 const unsigned long long base = c.atomic_add_global(P.work, (unsigned long long)P.chunk);
                 if (base >= n_total) {
@@ -266,38 +281,36 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
                     b.k[K_SRC_END] = base + P.chunk < n_total ? (uint32_t)(base + P.chunk) : n_total;
                 }
             }
-            b.k[K_DONE] = (b.k[K_EXHAUSTED] && b.k[K_DEAD0 + p] == S) ? 1u : 0u;
+            // births this round: as many as the free capacity of the bank and the block's source range allow
+            const uint32_t avail = b.k[K_SRC_NEXT] < b.k[K_SRC_END] ? b.k[K_SRC_END] - b.k[K_SRC_NEXT] : 0u, room = S - live;
+            b.k[K_ADOPT] = avail < room ? avail : room;
+            b.k[K_DONE] = (b.k[K_EXHAUSTED] && live == 0u) ? 1u : 0u;
         }
         c.sync(); // B2
         if (c.load_shared(&b.k[K_DONE])) break;
         const uint32_t split = c.load_shared(&b.k[K_SPLIT]);
-        const uint32_t n_coll = c.load_shared(&b.k[K_COLL0 + p]), n_fly = c.load_shared(&b.k[K_FLY0 + p]),
-                       n_dead = c.load_shared(&b.k[K_DEAD0 + p]);
-        // ---- phase AB: the three lists one after another; every entry ends in walk[p][class] or in dead[p^1]
-        const uint32_t n_ab = n_coll + n_dead + n_fly;
-        if (C::kStats && tid == 0) c.note_round(n_coll, n_dead, n_fly);
+        const uint32_t n_coll = c.load_shared(&b.k[K_COLL0 + p]), n_go = c.load_shared(&b.k[K_GO0 + p]),
+                       n_adopt = c.load_shared(&b.k[K_ADOPT]);
+        // ---- phase AB: arena A -> arena B.  coll, then go, then births; every survivor lands in walk[class].
+        const uint32_t n_ab = n_coll + n_go + n_adopt;
+        if (C::kStats && tid == 0) c.note_round(n_coll, n_adopt, n_go);
         for (uint32_t base = 0; base < n_ab; base += nthr) {
             const uint32_t i = base + tid;
-            const bool active = i < n_ab;
             bool alive = false;
-            uint32_t slot = 0;
             Neutron n{};
-            if (active) {
+            if (i < n_ab) {
                 if (i < n_coll) {
-                    slot = b.coll(p)[i];
-                    n = load_neutron(b, slot);
+                    n = load_neutron(b.A, i);
                     alive = collide<TG>(c, P, n, ct);
                     if (!alive) {
                         ++ct.hist;
-                        alive = adopt(c, P, b, n);
+                        alive = adopt(c, P, b, n); // the freed record takes a new history at once, if there is one
                     }
-                } else if (i < n_coll + n_dead) {
-                    slot = b.dead(p)[i - n_coll];
-                    alive = adopt(c, P, b, n);
-                } else {
-                    slot = b.fly(p)[i - n_coll - n_dead];
-                    n = load_neutron(b, slot);
+                } else if (i < n_coll + n_go) {
+                    n = load_neutron(b.A, S - 1u - (i - n_coll));
                     alive = true;
+                } else {
+                    alive = adopt(c, P, b, n);
                 }
                 if (alive && !flight(c, P, n, ct)) { // flight cap: the history ends here
                     ++ct.hist;
@@ -309,28 +322,23 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
             if (alive) {
                 const uint32_t rb = c.run_bounds(n.cell);
                 cls = ((rb >> 16) - (rb & 0xffffu)) > split ? 1u : 0u;
-                store_neutron(b, slot, n);
             }
             c.converge();
             const uint32_t w0 = c.claim(&b.k[K_WALK00 + 2 * p], alive && cls == 0);
             const uint32_t w1 = c.claim(&b.k[K_WALK01 + 2 * p], alive && cls == 1);
-            const uint32_t d = c.claim(&b.k[K_DEAD0 + (p ^ 1)], active && !alive);
-            if (alive) b.walk(p, cls)[cls ? w1 : w0] = (uint16_t)slot;
-            else if (active) b.dead(p ^ 1)[d] = (uint16_t)slot;
+            if (alive) store_neutron(b.B, cls ? S - 1u - w1 : w0, n);
         }
-        c.sync(); // B3: the walk lists are complete
-        if (tid == 0) b.k[K_COLL0 + p] = b.k[K_FLY0 + p] = b.k[K_DEAD0 + p] = 0u; // consumed; phase C writes parity p^1 only
-        // ---- phase C: walks, short runs first, long runs second; outcomes go to the lists of parity p^1
+        c.sync(); // B3: arena B is complete, arena A is consumed
+        if (tid == 0) b.k[K_COLL0 + p] = b.k[K_GO0 + p] = 0u; // phase C fills the lists of parity p^1
+        // ---- phase C: arena B -> arena A.  Walks of short runs first, long runs second.
         for (uint32_t cls = 0; cls < 2; ++cls) {
             const uint32_t n_walk = c.load_shared(&b.k[K_WALK00 + 2 * p + cls]);
             for (uint32_t base = 0; base < n_walk; base += nthr) {
                 const uint32_t i = base + tid;
-                const bool active = i < n_walk;
                 int out = 0;
-                uint32_t slot = 0;
-                if (active) {
-                    slot = b.walk(p, cls)[i];
-                    Neutron n = load_neutron(b, slot);
+                Neutron n{};
+                if (i < n_walk) {
+                    n = load_neutron(b.B, cls ? S - 1u - i : i);
                     const int cell0 = n.cell;
                     out = walk(c, P, n);
                     if (C::kStats) c.note_walk(cls, i, n.cell > cell0 ? n.cell - cell0 : cell0 - n.cell); // emulation only
@@ -344,17 +352,12 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
                     }
                     if (out == OUT_LEAK) { ++ct.hist; ++ct.leak; }
                     else if (out == OUT_TRUNC) { ++ct.hist; ++ct.trunc; }
-                    else store_neutron(b, slot, n);
                 }
                 c.converge();
                 const uint32_t qc = c.claim(&b.k[K_COLL0 + (p ^ 1)], out == OUT_COLLIDE);
-                const uint32_t qf = c.claim(&b.k[K_FLY0 + (p ^ 1)], out == OUT_MATCHANGE);
-                const uint32_t qw = c.claim(&b.k[K_WALK00 + 2 * (p ^ 1) + cls], out == OUT_PENDING);
-                const uint32_t qd = c.claim(&b.k[K_DEAD0 + (p ^ 1)], out == OUT_LEAK || out == OUT_TRUNC);
-                if (out == OUT_COLLIDE) b.coll(p ^ 1)[qc] = (uint16_t)slot;
-                else if (out == OUT_MATCHANGE) b.fly(p ^ 1)[qf] = (uint16_t)slot;
-                else if (out == OUT_PENDING) b.walk(p ^ 1, cls)[qw] = (uint16_t)slot;
-                else if (out == OUT_LEAK || out == OUT_TRUNC) b.dead(p ^ 1)[qd] = (uint16_t)slot;
+                const uint32_t qg = c.claim(&b.k[K_GO0 + (p ^ 1)], out == OUT_MATCHANGE || out == OUT_PENDING);
+                if (out == OUT_COLLIDE) store_neutron(b.A, qc, n);
+                else if (out == OUT_MATCHANGE || out == OUT_PENDING) store_neutron(b.A, S - 1u - qg, n);
             }
         }
         p ^= 1;

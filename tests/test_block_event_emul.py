@@ -111,3 +111,23 @@ def test_synthetic_shapes(emul, M, G, pins, mpfr, mpwr, bl, br):
     """Generic group counts, five materials, a single cell (both walls in it), one long run."""
     args = synthetic_case(M, G, pins, mpfr, mpwr, seed=M * 10 + G, boundl=bl, boundr=br)
     _run(emul, args, H=1500, gen=1, walk_cap=24)
+
+
+def test_shards_of_a_generation_add_up(emul):
+    """Two ranks' shards [0, H/3) and [H/3, H) of one generation (contiguous history ranges, as nraps_b200.dist cuts
+    them): the integer tallies add up to the oracle's whole generation."""
+    args = load_case("c")
+    H, gen = 2400, 1
+    p, keep, deck, m = _problem(args, H, gen + 1)
+    total = np.zeros(p.G * p.N, np.uint64)
+    hist = 0
+    for begin, count in ((0, H // 3), (H // 3, H - H // 3)):
+        tally = np.zeros(p.G * p.N, np.uint64)
+        counters = np.zeros(8, np.uint64)
+        rc = emul.bev_emul_generation(C.byref(p), gen, begin, count, 42, 54, 152917, 0, 1, 8, 1 << 24, 2, 8, 24, 16,
+                                      tally.ctypes.data_as(C.POINTER(C.c_uint64)), counters.ctypes.data_as(C.POINTER(C.c_uint64)), None)
+        assert rc == 0
+        total += tally
+        hist += int(counters[0])
+    want = orc.monte_carlo(deck, m, generations=gen + 1, histories=H, skip=1, threads=4, want_tally=True)
+    assert hist == H and np.array_equal(total.reshape(p.G, p.N), want.tally_fixed[gen])

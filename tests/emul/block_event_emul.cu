@@ -66,7 +66,16 @@ struct HostCtx {
     }
     uint32_t tid() const { return tid_; }
     uint32_t nthreads() const { return nthr_; }
-    void sync() const { pthread_barrier_wait(bar); }
+    // Mutation hook for the race detector run (tools/tsan_block_event.sh): BEV_EMUL_DROP_SYNC=k makes every thread skip
+    // the k-th of the three barriers of a round (0 = B1, 1 = B2, 2 = B3), which ThreadSanitizer must then report.
+    mutable unsigned long long n_sync = 0;
+    int drop = -1;
+    void sync() const
+    {
+        const unsigned long long k = n_sync++;
+        if (drop >= 0 && (int)(k % 3ull) == drop) return;
+        pthread_barrier_wait(bar);
+    }
     void converge() const {}
     uint32_t atomic_add_shared(uint32_t *p, uint32_t v) const { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
     uint32_t load_shared(const uint32_t *p) const { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
@@ -220,6 +229,7 @@ extern "C" int bev_emul_generation(const nraps_problem *p, uint64_t gen, uint64_
         std::vector<pthread_t> th(n_threads);
         for (uint32_t t = 0; t < n_threads; ++t) {
             args[t].ctx = HostCtx{t, n_threads, &bar, &im, &stats};
+            if (const char *d = getenv("BEV_EMUL_DROP_SYNC")) args[t].ctx.drop = atoi(d);
             args[t].P = &P; args[t].bank = &bank; args[t].G = (int)G;
             if (pthread_create(&th[t], nullptr, thread_main, &args[t]) != 0) return -1;
         }

@@ -344,6 +344,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     }
     if (c->opt.kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) {
         if (trace || nb != 1) return NRAPS_ERR_OPTION;
+        P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)c->opt.spawn_batch : 0u; // walk-class threshold, 0 = by run length
         if (count >> 32) return NRAPS_ERR_TOO_LARGE; // the block's source cursor is 32-bit
         CU(launch_block_event(P, dim3(c->bev_grid), dim3(c->bev_block), c->bev_smem, c->bev_slots, s));
         return NRAPS_OK;

@@ -226,6 +226,26 @@ template <int TG, class C> NRAPS_HD bool collide(C &c, const TransportParams &P,
     return true;
 }
 
+// Which of the two walk lists a neutron about to walk belongs to.  P.spawn_batch == 0 (default): by the length of the
+// material run it sits in (> split cells = "long").  P.spawn_batch = T > 0: by a PREDICTION of how many cells its flight
+// will cross in this run (>= T = "long"), from the distance to the edge ahead and the cell width; the prediction only
+// sorts, so its rounding cannot change a result.
+template <class C> NRAPS_HD uint32_t walk_class(C &c, const TransportParams &P, const Neutron &n, uint32_t split)
+{
+    const uint32_t rb = c.run_bounds(n.cell);
+    const int run_lo = (int)(rb & 0xffffu), run_hi = (int)(rb >> 16);
+    if (P.spawn_batch == 0u) return (uint32_t)(run_hi - run_lo) > split ? 1u : 0u;
+    const int fwd = n.mu >= 0.0f ? 1 : 0;
+    const int room = fwd ? run_hi - n.cell : n.cell - run_lo + 1; // cells up to the end of the run, this one included
+    const float lo = c.edge(c.edge_ref(n.cell)), hi = c.edge(c.edge_ref(n.cell + 1));
+    const float d0 = fwd ? hi - n.x : n.x - lo, a = fabsf(n.ds);
+    if (!(a > d0)) return 0u;
+    float k = 1.0f + (a - d0) / (hi - lo);
+    const float cap = (float)(room < (int)P.walk_cap ? room : (int)P.walk_cap);
+    k = k < cap ? k : cap;
+    return k >= (float)P.spawn_batch ? 1u : 0u;
+}
+
 // the next history of the block's source range comes to life; false = none left right now
 template <class C> NRAPS_HD bool adopt(C &c, const TransportParams &P, const Bank &b, Neutron &n)
 {
@@ -319,10 +339,7 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
                 }
             }
             uint32_t cls = 0;
-            if (alive) {
-                const uint32_t rb = c.run_bounds(n.cell);
-                cls = ((rb >> 16) - (rb & 0xffffu)) > split ? 1u : 0u;
-            }
+            if (alive) cls = walk_class(c, P, n, split);
             c.converge();
             const uint32_t w0 = c.claim(&b.k[K_WALK00 + 2 * p], alive && cls == 0);
             const uint32_t w1 = c.claim(&b.k[K_WALK01 + 2 * p], alive && cls == 1);

@@ -210,6 +210,7 @@ extern "C" int bev_emul_generation(const nraps_problem *p, uint64_t gen, uint64_
     P.work = &work;
     P.chunk = chunk; P.max_flights = max_flights; P.walk_cap = walk_cap;
     P.scatter_mode = scatter_mode; P.stale_xs = stale_xs;
+    if (const char *t = getenv("BEV_EMUL_CLASS_T")) P.spawn_batch = (uint32_t)atoi(t); // walk-class threshold (schedule studies)
 
     std::fill(tally_out, tally_out + (size_t)G * N, 0ull);
     std::fill(counters_out, counters_out + 8, 0ull);

@@ -98,6 +98,16 @@ def test_vacuum_and_albedo_walls(emul, bl, br):
     assert (ct[5] > 0) == (bl == 0.0 or br == 0.0)
 
 
+@pytest.mark.parametrize("threshold", ["2", "5"])
+def test_walk_classes_by_predicted_crossings_change_nothing(emul, monkeypatch, threshold):
+    """nraps_options.spawn_batch = T for this variant: the two walk lists are split by a prediction of the crossing
+    count instead of the run length.  The prediction only sorts, so every bin must stay the same."""
+    monkeypatch.setenv("BEV_EMUL_CLASS_T", threshold)
+    v, xs, dx, mesh, fuel = load_case("c")
+    v.boundl = 0.5
+    _run(emul, (v, xs, dx, mesh, fuel), H=2000, gen=0, blocks=2, threads=8, slots=48, chunk=32)
+
+
 def test_flight_cap_truncates_like_the_oracle(emul):
     ct = _run(emul, load_case("a"), H=800, gen=0, max_flights=5)
     assert ct[6] > 0

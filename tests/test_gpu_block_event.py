@@ -36,7 +36,8 @@ def test_results_bit_exact(case, H, gens):
 
 
 @pytest.mark.parametrize("kw", [dict(threads_per_block=64, blocks_per_sm=1, slots_per_thread=1), dict(threads_per_block=1024, blocks_per_sm=1, slots_per_thread=3),
-                                dict(threads_per_block=256, blocks_per_sm=4, slots_per_thread=5, chunk=33), dict(walk_cap=3)])
+                                dict(threads_per_block=256, blocks_per_sm=4, slots_per_thread=5, chunk=33), dict(walk_cap=3), dict(spawn_batch=5),
+                                dict(spawn_batch=2, walk_cap=6)])
 def test_geometry_does_not_change_a_bit(kw):
     args = load_case("c")
     ref = nb.monte_carlo(*args, 1.0, generations=2, histories=200_000, skip=1, want_tally=True)

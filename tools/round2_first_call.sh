@@ -16,6 +16,8 @@ if [ $rc -eq 0 ]; then
     timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-variants --variant block_event --slots-per-thread $spt \
         > gpurun_out/r2_bench_block_event_spt$spt.json 2> gpurun_out/r2_bench_block_event_spt$spt.err; echo "bench block_event spt=$spt: rc=$?"
   done
+  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-variants --variant block_event --spawn-batch 5 \
+      > gpurun_out/r2_bench_block_event_T5.json 2> gpurun_out/r2_bench_block_event_T5.err; echo "bench block_event predicted classes T=5: rc=$?"
   timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-variants --variant block_event --threads 1024 --blocks-per-sm 1 \
       > gpurun_out/r2_bench_block_event_1024.json 2> gpurun_out/r2_bench_block_event_1024.err; echo "bench block_event 1024x1: rc=$?"
 fi

@@ -9,7 +9,7 @@ namespace {
 
 struct DevCtx {
     static constexpr bool kStats = false; // the schedule statistics hooks exist for the CPU emulation only
-    __device__ __forceinline__ void note_walk(uint32_t, uint32_t, int) const {}
+    __device__ __forceinline__ void note_walk(uint32_t, int) const {}
     __device__ __forceinline__ void note_round(uint32_t, uint32_t, uint32_t) const {}
     uint32_t s_edges, s_runb, s_matid, s_lo, hi_off;
     const float *xs;

@@ -347,35 +347,35 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
         }
         c.sync(); // B3: arena B is complete, arena A is consumed
         if (tid == 0) b.k[K_COLL0 + p] = b.k[K_GO0 + p] = 0u; // phase C fills the lists of parity p^1
-        // ---- phase C: arena B -> arena A.  Walks of short runs first, long runs second.
-        for (uint32_t cls = 0; cls < 2; ++cls) {
-            const uint32_t n_walk = c.load_shared(&b.k[K_WALK00 + 2 * p + cls]);
-            for (uint32_t base = 0; base < n_walk; base += nthr) {
-                const uint32_t i = base + tid;
-                int out = 0;
-                Neutron n{};
-                if (i < n_walk) {
-                    n = load_neutron(b.B, cls ? S - 1u - i : i);
-                    const int cell0 = n.cell;
-                    out = walk(c, P, n);
-                    if (C::kStats) c.note_walk(cls, i, n.cell > cell0 ? n.cell - cell0 : cell0 - n.cell); // emulation only
-                    if (out == OUT_MATCHANGE) {
-                        if ((unsigned)n.cell >= (unsigned)P.N) {
-                            out = OUT_TRUNC; // unreachable for validated input
-                        } else {
-                            n.mat = c.material(n.cell);
-                            n.xsg = n.g;
-                        }
+        // ---- phase C: arena B -> arena A.  One index space over both walk lists, long runs first (the longest work
+        // starts first and every warp gets its share of both lists: no warp is left with long walks only)
+        const uint32_t n_long = c.load_shared(&b.k[K_WALK01 + 2 * p]), n_walk = n_long + c.load_shared(&b.k[K_WALK00 + 2 * p]);
+        for (uint32_t base = 0; base < n_walk; base += nthr) {
+            const uint32_t i = base + tid;
+            int out = 0;
+            Neutron n{};
+            if (i < n_walk) {
+                const uint32_t cls = i < n_long ? 1u : 0u, j = cls ? i : i - n_long;
+                n = load_neutron(b.B, cls ? S - 1u - j : j);
+                const int cell0 = n.cell;
+                out = walk(c, P, n);
+                if (C::kStats) c.note_walk(i, n.cell > cell0 ? n.cell - cell0 : cell0 - n.cell); // emulation only
+                if (out == OUT_MATCHANGE) {
+                    if ((unsigned)n.cell >= (unsigned)P.N) {
+                        out = OUT_TRUNC; // unreachable for validated input
+                    } else {
+                        n.mat = c.material(n.cell);
+                        n.xsg = n.g;
                     }
-                    if (out == OUT_LEAK) { ++ct.hist; ++ct.leak; }
-                    else if (out == OUT_TRUNC) { ++ct.hist; ++ct.trunc; }
                 }
-                c.converge();
-                const uint32_t qc = c.claim(&b.k[K_COLL0 + (p ^ 1)], out == OUT_COLLIDE);
-                const uint32_t qg = c.claim(&b.k[K_GO0 + (p ^ 1)], out == OUT_MATCHANGE || out == OUT_PENDING);
-                if (out == OUT_COLLIDE) store_neutron(b.A, qc, n);
-                else if (out == OUT_MATCHANGE || out == OUT_PENDING) store_neutron(b.A, S - 1u - qg, n);
+                if (out == OUT_LEAK) { ++ct.hist; ++ct.leak; }
+                else if (out == OUT_TRUNC) { ++ct.hist; ++ct.trunc; }
             }
+            c.converge();
+            const uint32_t qc = c.claim(&b.k[K_COLL0 + (p ^ 1)], out == OUT_COLLIDE);
+            const uint32_t qg = c.claim(&b.k[K_GO0 + (p ^ 1)], out == OUT_MATCHANGE || out == OUT_PENDING);
+            if (out == OUT_COLLIDE) store_neutron(b.A, qc, n);
+            else if (out == OUT_MATCHANGE || out == OUT_PENDING) store_neutron(b.A, S - 1u - qg, n);
         }
         p ^= 1;
     }

@@ -29,12 +29,12 @@ struct Image { // what a block keeps in shared memory, on the heap
     int MG;
 };
 
-// schedule statistics of one emulated block (what a warp of 32 consecutive threads would see)
+// schedule statistics of one emulated block (what warps of 32 consecutive threads would see)
 struct Stats {
-    unsigned long long rounds = 0, coll = 0, dead = 0, fly = 0;                 // list entries phase AB consumed
-    unsigned long long walk_entries[2] = {0, 0}, crossings[2] = {0, 0};          // per walk class
-    unsigned long long warp_chunks[2] = {0, 0}, warp_crossing_slots[2] = {0, 0}; // chunks of 32 list entries; sum of the longest walk of each
-    std::vector<int> cur[2];                                                      // crossings by list position, this round
+    unsigned long long rounds = 0, coll = 0, dead = 0, fly = 0;     // entries phase AB consumed
+    unsigned long long walk_entries = 0, crossings = 0;            // phase C
+    unsigned long long warp_chunks = 0, warp_crossing_slots = 0;   // chunks of 32 entries of the walk index space; sum of the longest walk of each
+    std::vector<int> cur;                                          // crossings by position in the walk index space, this round
 };
 
 struct HostCtx {
@@ -43,25 +43,23 @@ struct HostCtx {
     pthread_barrier_t *bar;
     Image *im;
     Stats *st;
-    void note_walk(uint32_t cls, uint32_t i, int crossings) const
-    {   // distinct positions are written by distinct threads; the vectors are sized by thread 0 in note_round
-        st->cur[cls][i] = crossings;
+    void note_walk(uint32_t i, int crossings) const
+    {   // distinct positions are written by distinct threads; the vector is reset by thread 0 in note_round
+        st->cur[i] = crossings;
     }
     void note_round(uint32_t n_coll, uint32_t n_dead, uint32_t n_fly) const
     {   // thread 0, after barrier B2: fold the walk phase of the previous round, then make room for this one
-        for (int cls = 0; cls < 2; ++cls) {
-            std::vector<int> &v = st->cur[cls];
-            size_t n = v.size();
-            while (n && v[n - 1] < 0) --n; // positions never written: the list was shorter than the bank
-            st->walk_entries[cls] += n;
-            for (size_t b = 0; b < n; b += 32) {
-                int mx = 0;
-                for (size_t j = b; j < std::min(n, b + 32); ++j) { st->crossings[cls] += (unsigned long long)v[j]; mx = std::max(mx, v[j]); }
-                st->warp_chunks[cls] += 1;
-                st->warp_crossing_slots[cls] += (unsigned long long)std::max(mx, 1); // a walk executes the loop body at least once
-            }
-            std::fill(v.begin(), v.end(), -1);
+        std::vector<int> &v = st->cur;
+        size_t n = v.size();
+        while (n && v[n - 1] < 0) --n; // positions never written: fewer walks than records
+        st->walk_entries += n;
+        for (size_t b = 0; b < n; b += 32) {
+            int mx = 0;
+            for (size_t j = b; j < std::min(n, b + 32); ++j) { st->crossings += (unsigned long long)v[j]; mx = std::max(mx, v[j]); }
+            st->warp_chunks += 1;
+            st->warp_crossing_slots += (unsigned long long)std::max(mx, 1); // a walk executes the loop body at least once
         }
+        std::fill(v.begin(), v.end(), -1);
         st->rounds += 1; st->coll += n_coll; st->dead += n_dead; st->fly += n_fly;
     }
     uint32_t tid() const { return tid_; }
@@ -152,7 +150,7 @@ extern "C" int bev_emul_generation(const nraps_problem *p, uint64_t gen, uint64_
                                    uint32_t max_flights, uint32_t n_blocks, uint32_t n_threads, uint32_t slots, uint32_t chunk,
                                    unsigned long long *tally_out, unsigned long long *counters_out, unsigned long long *stats_out)
 {
-    if (stats_out) std::fill(stats_out, stats_out + 12, 0ull);
+    if (stats_out) std::fill(stats_out, stats_out + 8, 0ull);
     const uint32_t M = p->M, G = p->G, N = p->N, NF = p->NF, MG = M * G;
     // ---- derived tables, the expressions of mc_api.cu::create_ctx (binary32, reference order)
     std::vector<float> edges(N + 1);
@@ -222,8 +220,7 @@ extern "C" int bev_emul_generation(const nraps_problem *p, uint64_t gen, uint64_
         unsigned char *base = raw.data() + ((16 - ((uintptr_t)raw.data() & 15u)) & 15u);
         const bev::Bank bank = bev::make_bank(base, slots);
         Stats stats;
-        stats.cur[0].assign(slots, -1);
-        stats.cur[1].assign(slots, -1);
+        stats.cur.assign(slots, -1);
         pthread_barrier_t bar;
         pthread_barrier_init(&bar, nullptr, n_threads);
         std::vector<ThreadArg> args(n_threads);
@@ -237,11 +234,10 @@ extern "C" int bev_emul_generation(const nraps_problem *p, uint64_t gen, uint64_
         for (uint32_t t = 0; t < n_threads; ++t) pthread_join(th[t], nullptr);
         pthread_barrier_destroy(&bar);
         for (size_t i = 0; i < (size_t)G * N; ++i) tally_out[i] += im.bins[i];
-        if (stats_out) { // [rounds, coll, dead, fly, entries0, entries1, crossings0, crossings1, chunks0, chunks1, slots0, slots1]
-            const unsigned long long v[12] = {stats.rounds, stats.coll, stats.dead, stats.fly, stats.walk_entries[0], stats.walk_entries[1],
-                                              stats.crossings[0], stats.crossings[1], stats.warp_chunks[0], stats.warp_chunks[1],
-                                              stats.warp_crossing_slots[0], stats.warp_crossing_slots[1]};
-            for (int i = 0; i < 12; ++i) stats_out[i] += v[i];
+        if (stats_out) { // [rounds, coll, births, go, walk entries, crossings, warp chunks, warp crossing slots]
+            const unsigned long long v[8] = {stats.rounds, stats.coll, stats.dead, stats.fly, stats.walk_entries, stats.crossings,
+                                             stats.warp_chunks, stats.warp_crossing_slots};
+            for (int i = 0; i < 8; ++i) stats_out[i] += v[i];
         }
         for (uint32_t t = 0; t < n_threads; ++t) {
             const bev::Counts &c = args[t].counts;

@@ -38,7 +38,7 @@ def main():
     p, keep, deck, m = _problem(args, a.histories, 1)
     tally = np.zeros(p.G * p.N, np.uint64)
     counters = np.zeros(8, np.uint64)
-    st = np.zeros(12, np.uint64)
+    st = np.zeros(8, np.uint64)
     u64p = C.POINTER(C.c_uint64)
     L.bev_emul_generation.restype = C.c_int
     rc = L.bev_emul_generation(C.byref(p), C.c_uint64(0), C.c_uint64(0), C.c_uint64(a.histories), C.c_uint64(42), C.c_uint64(54),
@@ -46,20 +46,17 @@ def main():
                                C.c_uint32(1), C.c_uint32(a.threads), C.c_uint32(a.slots), C.c_uint32(a.chunk), tally.ctypes.data_as(u64p),
                                counters.ctypes.data_as(u64p), st.ctypes.data_as(u64p))
     assert rc == 0
-    rounds, coll, dead, fly, e0, e1, x0, x1, c0, c1, s0, s1 = (int(v) for v in st)
+    rounds, coll, births, go, entries, crossings, chunks, slots = (int(v) for v in st)
     H = a.histories
-    print(f"deck {a.case}: {H} histories through one block of {a.slots} slots (walk cap {a.walk_cap})")
-    print(f"  rounds {rounds} ({rounds * a.slots / H:.1f} slot-rounds per history); collisions/history {int(counters[1]) / H:.2f}, flights/history {int(counters[3]) / H:.2f}")
-    print(f"  phase AB per round: collide {coll / rounds:.0f}, adopt {dead / rounds:.0f}, flight-only {fly / rounds:.0f} entries "
-          f"({(coll + dead + fly) / rounds / a.slots:.2f} of the bank)")
-    for cls, (e, x, c, s) in enumerate(((e0, x0, c0, s0), (e1, x1, c1, s1))):
-        if not e:
-            continue
-        print(f"  walk class {cls}: {e / rounds:.0f} entries per round, {x / e:.2f} crossings per walk, warp chunks {c}, "
-              f"crossing slots {s} -> {x / (32 * s):.3f} of the lanes busy in the walk loop ({32 * x / (32 * s):.1f} of 32)")
-    tot_x, tot_s = x0 + x1, s0 + s1
-    print(f"  walk loop overall: {tot_x / H:.1f} crossings per history, {tot_s / H:.2f} warp crossing slots per history "
-          f"({32 * tot_x / (32 * tot_s):.1f} of 32 lanes busy; the lane kernel: 23.4 slots per history, ncu r1r)")
+    print(f"deck {a.case}: {H} histories through one block of {a.slots} records (walk cap {a.walk_cap}, "
+          f"walk classes {'by run length' if not os.environ.get('BEV_EMUL_CLASS_T', '0') != '0' else 'by predicted crossings >= ' + os.environ['BEV_EMUL_CLASS_T']})")
+    print(f"  rounds {rounds} ({entries / H:.1f} record visits of the walk phase per history); collisions/history {int(counters[1]) / H:.2f}, "
+          f"flights/history {int(counters[3]) / H:.2f}")
+    print(f"  phase AB per round: collide {coll / rounds:.0f}, births outside a collision {births / rounds:.0f}, flight-only or resumed {go / rounds:.0f} "
+          f"entries ({(coll + births + go) / rounds / a.slots:.2f} of the bank)")
+    print(f"  phase C per round: {entries / rounds:.0f} walks, {crossings / entries:.2f} crossings per walk")
+    print(f"  walk loop: {crossings / H:.1f} crossings per history in {slots / H:.2f} warp crossing slots per history "
+          f"({crossings / slots:.1f} of 32 lanes busy; the lane kernel: 23.4 slots per history, ncu r1r)")
 
 
 if __name__ == "__main__":

@@ -8,6 +8,10 @@ namespace nraps {
 namespace {
 
 struct DevCtx {
+    long long t0; // clock64() at block start, for the watchdog
+    // A block that is still running after 2e10 SM cycles (~10 s; a generation of 1.25e8 histories takes 0.2 s) stops
+    // and reports its live records as truncated histories: an experimental kernel must not be able to hang a GPU.
+    __device__ __forceinline__ bool expired() const { return clock64() - t0 > 20000000000ll; }
     static constexpr bool kStats = false; // the schedule statistics hooks exist for the CPU emulation only
     __device__ __forceinline__ void note_walk(uint32_t, int) const {}
     __device__ __forceinline__ void note_round(uint32_t, uint32_t, uint32_t) const {}
@@ -57,6 +61,7 @@ template <int TG> __global__ void __launch_bounds__(1024, 1) block_event_kernel(
     const SmemView V = load_block_tables(smem_raw, P, L); // zeroes the tally image, stages the tables, __syncthreads
     const bev::Bank b = bev::make_bank(smem_raw + L.total, S);
     DevCtx c;
+    c.t0 = clock64();
     c.s_edges = (uint32_t)__cvta_generic_to_shared(V.edges);
     c.s_runb = (uint32_t)__cvta_generic_to_shared(V.runb);
     c.s_matid = (uint32_t)__cvta_generic_to_shared(V.matid);

@@ -305,6 +305,11 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
             const uint32_t avail = b.k[K_SRC_NEXT] < b.k[K_SRC_END] ? b.k[K_SRC_END] - b.k[K_SRC_NEXT] : 0u, room = S - live;
             b.k[K_ADOPT] = avail < room ? avail : room;
             b.k[K_DONE] = (b.k[K_EXHAUSTED] && live == 0u) ? 1u : 0u;
+            if (c.expired()) { // watchdog (device: ~10 s of SM clock): give up, the records still live count as truncated
+                b.k[K_DONE] = 1u;
+                ct.hist += live;
+                ct.trunc += live;
+            }
         }
         c.sync(); // B2
         if (c.load_shared(&b.k[K_DONE])) break;

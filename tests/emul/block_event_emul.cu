@@ -62,6 +62,7 @@ struct HostCtx {
         std::fill(v.begin(), v.end(), -1);
         st->rounds += 1; st->coll += n_coll; st->dead += n_dead; st->fly += n_fly;
     }
+    bool expired() const { return false; } // the device context has a clock watchdog here
     uint32_t tid() const { return tid_; }
     uint32_t nthreads() const { return nthr_; }
     // Mutation hook for the race detector run (tools/tsan_block_event.sh): BEV_EMUL_DROP_SYNC=k makes every thread skip

@@ -56,7 +56,7 @@ def main():
           f"entries ({(coll + births + go) / rounds / a.slots:.2f} of the bank)")
     print(f"  phase C per round: {entries / rounds:.0f} walks, {crossings / entries:.2f} crossings per walk")
     print(f"  walk loop: {crossings / H:.1f} crossings per history in {slots / H:.2f} warp crossing slots per history "
-          f"({crossings / slots:.1f} of 32 lanes busy; the lane kernel: 23.4 slots per history, ncu r1r)")
+          f"({crossings / slots:.1f} of 32 lanes busy" + ("; the lane kernel on deck C as shipped: 23.4 slots per history, ncu r1r)" if not a.mpfr and a.case == "c" else ")"))
 
 
 if __name__ == "__main__":

@@ -420,3 +420,82 @@ def test_python_mirror_refuses_arrays_shorter_than_the_abi_reads():
         nb.monte_carlo(v, xs, dx, ragged, fuel, 1.0, generations=2, histories=10, skip=1)
     with pytest.raises(ValueError, match="sigt"):
         nb.nalgebra_method(nb.XSData(**{**xs.__dict__, "sigt": xs.sigt[:3]}), mesh, v.energygroups, v.mattypes, 1.0, 1.0, v.numass)
+
+
+def test_bindings_mirror_the_header_field_for_field(tmp_path):
+    """The three mirrors of include/nraps_mc.h -- the ctypes structures, the oracle's copy of nraps_problem and the
+    #[repr(C)] structs of the Rust shim (rust/src/mc_code.rs, which no toolchain here can compile) -- must list the
+    same fields in the same order with the same C types, and the ctypes layout must equal the C compiler's."""
+    import re
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "nraps_mc.h")).read()
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            m = re.match(r"(const )?(\w+) (.*)", decl)
+            const, base, names = bool(m.group(1)), m.group(2), m.group(3)
+            for name in names.split(","):
+                name = name.strip()
+                ptr = name.startswith("*")
+                name = name.lstrip("*")
+                arr = re.match(r"(\w+)\[(\w+)\]", name)
+                if arr:
+                    out.append((arr.group(1), base + "[]"))
+                else:
+                    out.append((name, ("const " if const and ptr else "") + base + ("*" if ptr else "")))
+        return out
+
+    rust = open(os.path.join(root, "rust", "src", "mc_code.rs")).read()
+    rust_types = {"u32": "uint32_t", "u64": "uint64_t", "i32": "int32_t", "f32": "float", "f64": "double",
+                  "*const f32": "const float*", "*const u8": "const uint8_t*", "*const u64": "const uint64_t*",
+                  "*mut f32": "float*", "*mut u64": "uint64_t*", "*mut f64": "double*", "[u64; 8]": "uint64_t[]"}
+
+    def rust_fields(struct):
+        body = re.search(r"struct %s \{(.*?)\n\}" % struct, rust, re.S).group(1)
+        return [(n.strip(), rust_types[t.strip()]) for n, t in re.findall(r"(\w+):\s*([^,]+?),", body)]
+
+    ctypes_types = {C.c_uint32: "uint32_t", C.c_uint64: "uint64_t", C.c_int32: "int32_t", C.c_float: "float", C.c_double: "double"}
+
+    def ct_fields(cls, drop_const=True):
+        out = []
+        for name, t in cls._fields_:
+            if t in ctypes_types:
+                out.append((name, ctypes_types[t]))
+            elif hasattr(t, "_length_"):
+                out.append((name, ctypes_types[t._type_] + "[]"))
+            else:
+                out.append((name, ctypes_types.get(t._type_, "uint8_t") + "*"))
+        return out
+
+    strip = lambda fields: [(n.lower(), t.replace("const ", "")) for n, t in fields]  # noqa: E731
+    for cname, rname, pycls in (("nraps_problem", "NrapsProblem", _lib.Problem), ("nraps_options", "NrapsOptions", _lib.Options),
+                                ("nraps_results", "NrapsResults", _lib.Results)):
+        want = c_fields(cname)
+        assert [(n.lower(), t) for n, t in rust_fields(rname)] == [(n.lower(), t) for n, t in want], rname
+        assert strip(ct_fields(pycls)) == strip(want), pycls
+    from oracle import oracle as orc
+    assert strip(ct_fields(orc.Problem)) == strip(c_fields("nraps_problem"))
+    # sizes and offsets as the C compiler lays them out
+    probe = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nraps_mc.h"', "int main(void) {"]
+    for cname in ("nraps_problem", "nraps_options", "nraps_results"):
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for name, _ in c_fields(cname):
+            lines.append(f'printf("{cname}.{name} %zu\\n", offsetof({cname}, {name}));')
+    lines.append("return 0; }")
+    probe.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(probe), "-o", str(exe)], check=True, stdin=subprocess.DEVNULL)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, pycls in (("nraps_problem", _lib.Problem), ("nraps_options", _lib.Options), ("nraps_results", _lib.Results)):
+        assert int(got[cname]) == C.sizeof(pycls)
+        for (name, _), (pyname, _t) in zip(c_fields(cname), pycls._fields_):
+            assert int(got[f"{cname}.{name}"]) == getattr(pycls, pyname).offset, (cname, name)

@@ -480,7 +480,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
         uint32_t spt = o->slots_per_thread > 0 ? (uint32_t)o->slots_per_thread : 3u;
         TransportParams q{};
         q.M = M; q.G = G; q.N = N; q.NF = NF; q.NB = NB; q.rows = G;
-        while (bb * spt > 65535u) --spt; // slot ids are 16-bit
+        while (bb * spt > 65535u) --spt; // list lengths are the 16-bit halves of a packed word
         while ((uint64_t)bbps * (block_event_smem(q, bb * spt) + 1024) > 233472ull) {
             if (spt > 1) --spt;
             else if (bbps > 1) { --bbps; spt = o->slots_per_thread > 0 ? (uint32_t)o->slots_per_thread : 3u; }

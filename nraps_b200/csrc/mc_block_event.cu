@@ -25,17 +25,19 @@ struct DevCtx {
     __device__ __forceinline__ uint32_t atomic_add_shared(uint32_t *p, uint32_t v) const { return atomicAdd(p, v); }
     __device__ __forceinline__ uint32_t load_shared(const uint32_t *p) const { return *reinterpret_cast<const volatile uint32_t *>(p); }
     __device__ __forceinline__ unsigned long long atomic_add_global(unsigned long long *p, unsigned long long v) const { return atomicAdd(p, v); }
-    // position in a list for every lane with `pred`: one shared atomic per warp (warp-aggregated claim)
-    __device__ __forceinline__ uint32_t claim(uint32_t *count, bool pred) const
+    // Positions in the two lists of an arena for the lanes that push (at most one of the predicates holds per lane):
+    // ONE shared atomic per warp on the packed length word (low half: list growing up, high half: list growing down).
+    __device__ __forceinline__ uint32_t claim2(uint32_t *word, bool up, bool down) const
     {
-        const unsigned m = __ballot_sync(kFull, pred);
+        const unsigned m_up = __ballot_sync(kFull, up), m_down = __ballot_sync(kFull, down), m = m_up | m_down;
         if (!m) return 0u;
         const unsigned lane = threadIdx.x & 31u;
         const int leader = __ffs((int)m) - 1;
-        uint32_t base = 0u;
-        if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
-        base = __shfl_sync(kFull, base, leader);
-        return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        uint32_t old = 0u;
+        if ((int)lane == leader) old = atomicAdd(word, (uint32_t)__popc(m_up) | ((uint32_t)__popc(m_down) << 16));
+        old = __shfl_sync(kFull, old, leader);
+        const unsigned below = (1u << lane) - 1u;
+        return down ? (old >> 16) + (uint32_t)__popc(m_down & below) : (old & 0xffffu) + (uint32_t)__popc(m_up & below);
     }
     __device__ __forceinline__ uint32_t run_bounds(int i) const { return lds_u32(s_runb + 4u * (uint32_t)i); }
     __device__ __forceinline__ int material(int i) const { return (int)lds_u8(s_matid + (uint32_t)i); }

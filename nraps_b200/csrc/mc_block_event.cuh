@@ -36,10 +36,12 @@ namespace bev {
 
 enum { OUT_COLLIDE = 1, OUT_MATCHANGE = 2, OUT_PENDING = 3, OUT_LEAK = 4, OUT_TRUNC = 5 };
 
-// counters in shared memory (u32 words); list lengths exist once per round parity
+// counters in shared memory (u32 words).  The two lists of an arena share ONE word -- length of the list growing up in
+// the low 16 bits, of the list growing down in the high 16 bits (S <= 65535) -- so that a warp claims its positions in
+// both with a single shared atomic; the words exist once per round parity.
 enum {
-    K_COLL0 = 0, K_COLL1, K_GO0, K_GO1,                    // arena A lists, [parity]
-    K_WALK00, K_WALK01, K_WALK10, K_WALK11,                // arena B lists, [parity][class]
+    K_A0 = 0, K_A1, // arena A, [parity]: coll | go << 16
+    K_B0, K_B1,     // arena B, [parity]: walk[short] | walk[long] << 16
     K_SRC_NEXT, K_SRC_END, K_EXHAUSTED, K_DONE, K_SPLIT, K_ADOPT,
     K_WORDS = 16
 };
@@ -288,9 +290,8 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
     for (;;) {
         c.sync(); // B1: every record phase C of the previous round wrote is visible
         if (tid == 0) {
-            b.k[K_WALK00 + 2 * (p ^ 1)] = 0u; // the walk lists phase C of the previous round consumed
-            b.k[K_WALK01 + 2 * (p ^ 1)] = 0u;
-            const uint32_t live = b.k[K_COLL0 + p] + b.k[K_GO0 + p];
+            b.k[K_B0 + (p ^ 1)] = 0u; // the walk lists phase C of the previous round consumed
+            const uint32_t live = (b.k[K_A0 + p] & 0xffffu) + (b.k[K_A0 + p] >> 16);
             if (!b.k[K_EXHAUSTED] && b.k[K_SRC_NEXT] >= b.k[K_SRC_END]) { // next chunk of histories for this block
                 const unsigned long long base = c.atomic_add_global(P.work, (unsigned long long)P.chunk);
                 if (base >= n_total) {
@@ -314,8 +315,8 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
         c.sync(); // B2
         if (c.load_shared(&b.k[K_DONE])) break;
         const uint32_t split = c.load_shared(&b.k[K_SPLIT]);
-        const uint32_t n_coll = c.load_shared(&b.k[K_COLL0 + p]), n_go = c.load_shared(&b.k[K_GO0 + p]),
-                       n_adopt = c.load_shared(&b.k[K_ADOPT]);
+        const uint32_t k_a = c.load_shared(&b.k[K_A0 + p]);
+        const uint32_t n_coll = k_a & 0xffffu, n_go = k_a >> 16, n_adopt = c.load_shared(&b.k[K_ADOPT]);
         // ---- phase AB: arena A -> arena B.  coll, then go, then births; every survivor lands in walk[class].
         const uint32_t n_ab = n_coll + n_go + n_adopt;
         if (C::kStats && tid == 0) c.note_round(n_coll, n_adopt, n_go);
@@ -346,15 +347,15 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
             uint32_t cls = 0;
             if (alive) cls = walk_class(c, P, n, split);
             c.converge();
-            const uint32_t w0 = c.claim(&b.k[K_WALK00 + 2 * p], alive && cls == 0);
-            const uint32_t w1 = c.claim(&b.k[K_WALK01 + 2 * p], alive && cls == 1);
-            if (alive) store_neutron(b.B, cls ? S - 1u - w1 : w0, n);
+            const uint32_t w = c.claim2(&b.k[K_B0 + p], alive && cls == 0, alive && cls == 1);
+            if (alive) store_neutron(b.B, cls ? S - 1u - w : w, n);
         }
         c.sync(); // B3: arena B is complete, arena A is consumed
-        if (tid == 0) b.k[K_COLL0 + p] = b.k[K_GO0 + p] = 0u; // phase C fills the lists of parity p^1
+        if (tid == 0) b.k[K_A0 + p] = 0u; // phase C fills the lists of parity p^1
         // ---- phase C: arena B -> arena A.  One index space over both walk lists, long runs first (the longest work
         // starts first and every warp gets its share of both lists: no warp is left with long walks only)
-        const uint32_t n_long = c.load_shared(&b.k[K_WALK01 + 2 * p]), n_walk = n_long + c.load_shared(&b.k[K_WALK00 + 2 * p]);
+        const uint32_t k_b = c.load_shared(&b.k[K_B0 + p]);
+        const uint32_t n_long = k_b >> 16, n_walk = n_long + (k_b & 0xffffu);
         for (uint32_t base = 0; base < n_walk; base += nthr) {
             const uint32_t i = base + tid;
             int out = 0;
@@ -377,10 +378,10 @@ template <int TG, class C> NRAPS_HD void block_event_thread(C &c, const Transpor
                 else if (out == OUT_TRUNC) { ++ct.hist; ++ct.trunc; }
             }
             c.converge();
-            const uint32_t qc = c.claim(&b.k[K_COLL0 + (p ^ 1)], out == OUT_COLLIDE);
-            const uint32_t qg = c.claim(&b.k[K_GO0 + (p ^ 1)], out == OUT_MATCHANGE || out == OUT_PENDING);
-            if (out == OUT_COLLIDE) store_neutron(b.A, qc, n);
-            else if (out == OUT_MATCHANGE || out == OUT_PENDING) store_neutron(b.A, S - 1u - qg, n);
+            const bool to_go = out == OUT_MATCHANGE || out == OUT_PENDING;
+            const uint32_t q = c.claim2(&b.k[K_A0 + (p ^ 1)], out == OUT_COLLIDE, to_go);
+            if (out == OUT_COLLIDE) store_neutron(b.A, q, n);
+            else if (to_go) store_neutron(b.A, S - 1u - q, n);
         }
         p ^= 1;
     }

@@ -79,7 +79,12 @@ struct HostCtx {
     uint32_t atomic_add_shared(uint32_t *p, uint32_t v) const { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
     uint32_t load_shared(const uint32_t *p) const { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
     unsigned long long atomic_add_global(unsigned long long *p, unsigned long long v) const { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-    uint32_t claim(uint32_t *count, bool pred) const { return pred ? atomic_add_shared(count, 1u) : 0u; }
+    uint32_t claim2(uint32_t *word, bool up, bool down) const
+    {   // the packed length word of an arena: low half = list growing up, high half = list growing down
+        if (up) return atomic_add_shared(word, 1u) & 0xffffu;
+        if (down) return atomic_add_shared(word, 0x10000u) >> 16;
+        return 0u;
+    }
     uint32_t run_bounds(int i) const { return im->runb[i]; }
     int material(int i) const { return (int)im->matid[i]; }
     uint32_t edge_ref(int i) const { return 4u * (uint32_t)i; }

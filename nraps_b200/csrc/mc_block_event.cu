@@ -34,10 +34,9 @@ struct DevCtx {
         const unsigned lane = threadIdx.x & 31u;
         const int leader = __ffs((int)m) - 1;
         uint32_t old = 0u;
-        if ((int)lane == leader) old = atomicAdd(word, (uint32_t)__popc(m_up) | ((uint32_t)__popc(m_down) << 16));
+        if ((int)lane == leader) old = atomicAdd(word, bev::claim2_increment(m_up, m_down));
         old = __shfl_sync(kFull, old, leader);
-        const unsigned below = (1u << lane) - 1u;
-        return down ? (old >> 16) + (uint32_t)__popc(m_down & below) : (old & 0xffffu) + (uint32_t)__popc(m_up & below);
+        return bev::claim2_position(m_up, m_down, lane, old, down);
     }
     __device__ __forceinline__ uint32_t run_bounds(int i) const { return lds_u32(s_runb + 4u * (uint32_t)i); }
     __device__ __forceinline__ int material(int i) const { return (int)lds_u8(s_matid + (uint32_t)i); }

@@ -85,6 +85,25 @@ __host__ __device__ inline Bank make_bank(unsigned char *raw, uint32_t S)
     return b;
 }
 
+// Arithmetic of a warp-aggregated claim on the packed length word of an arena (low half: the list growing up, high half:
+// the list growing down).  m_up / m_down are the ballots of the lanes pushing to either list; the warp's leader adds
+// claim2_increment() to the word once and every lane derives its own position from the value the word had before.
+// Kept apart from the CUDA intrinsics so that the CPU tests can check it lane by lane (tests/emul).
+NRAPS_HD uint32_t popc32(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+NRAPS_HD uint32_t claim2_increment(uint32_t m_up, uint32_t m_down) { return popc32(m_up) | (popc32(m_down) << 16); }
+NRAPS_HD uint32_t claim2_position(uint32_t m_up, uint32_t m_down, uint32_t lane, uint32_t old, bool down)
+{
+    const uint32_t below = (1u << lane) - 1u;
+    return down ? (old >> 16) + popc32(m_down & below) : (old & 0xffffu) + popc32(m_up & below);
+}
+
 struct Neutron {
     float x, mu, ds;
     int cell, g, xsg, mat;

@@ -149,6 +149,15 @@ uint64_t advance(uint64_t state, uint64_t inc, uint64_t delta)
 
 } // namespace
 
+// The arithmetic of DevCtx::claim2 (mc_block_event.cu), lane by lane: given the two ballots and the value the packed word
+// had, what the leader adds and where each of the 32 lanes lands.  pos_out[lane] is only meaningful for pushing lanes.
+extern "C" uint32_t bev_emul_claim2(uint32_t m_up, uint32_t m_down, uint32_t old, uint32_t *pos_out)
+{
+    for (uint32_t lane = 0; lane < 32; ++lane)
+        pos_out[lane] = bev::claim2_position(m_up, m_down, lane, old, ((m_down >> lane) & 1u) != 0);
+    return old + bev::claim2_increment(m_up, m_down);
+}
+
 // One generation of [hist_begin, hist_begin + hist_count) through `n_blocks` emulated blocks of `n_threads` threads
 // with `slots` neutron slots each.  tally_out: u64[G*N]; counters_out: u64[8] in NRAPS_CT order.
 extern "C" int bev_emul_generation(const nraps_problem *p, uint64_t gen, uint64_t hist_begin, uint64_t hist_count, uint64_t seed,

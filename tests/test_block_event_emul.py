@@ -141,3 +141,24 @@ def test_shards_of_a_generation_add_up(emul):
         hist += int(counters[0])
     want = orc.monte_carlo(deck, m, generations=gen + 1, histories=H, skip=1, threads=4, want_tally=True)
     assert hist == H and np.array_equal(total.reshape(p.G, p.N), want.tally_fixed[gen])
+
+
+def test_warp_claim_arithmetic(emul):
+    """DevCtx::claim2 (mc_block_event.cu): one atomic on the packed length word of an arena for both of its lists.  Lane
+    by lane, for random ballots: the pushing lanes of either list get consecutive positions starting at the list's
+    old length, in lane order, and the word grows by the two counts."""
+    emul.bev_emul_claim2.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    emul.bev_emul_claim2.restype = C.c_uint32
+    rng = np.random.default_rng(3)
+    pos = (C.c_uint32 * 32)()
+    for _ in range(3000):
+        up = int(rng.integers(0, 1 << 32)) & int(rng.integers(0, 1 << 32))
+        down = int(rng.integers(0, 1 << 32)) & ~up & 0xFFFFFFFF  # a lane pushes to at most one list
+        if rng.integers(0, 8) == 0:
+            up, down = (0xFFFFFFFF, 0) if rng.integers(0, 2) else (0, 0xFFFFFFFF)
+        n_up, n_down = int(rng.integers(0, 60000)), int(rng.integers(0, 5000))
+        new = emul.bev_emul_claim2(up, down, n_up | (n_down << 16), pos)
+        ups = [pos[i] for i in range(32) if (up >> i) & 1]
+        downs = [pos[i] for i in range(32) if (down >> i) & 1]
+        assert ups == list(range(n_up, n_up + len(ups))) and downs == list(range(n_down, n_down + len(downs)))
+        assert new == (n_up + len(ups)) | ((n_down + len(downs)) << 16)

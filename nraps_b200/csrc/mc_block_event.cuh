@@ -91,7 +91,7 @@ __host__ __device__ inline Bank make_bank(unsigned char *raw, uint32_t S)
 // Kept apart from the CUDA intrinsics so that the CPU tests can check it lane by lane (tests/emul).
 NRAPS_HD uint32_t popc32(uint32_t v)
 {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || !defined(NRAPS_EMUL)
     return (uint32_t)__popc(v);
 #else
     return (uint32_t)__builtin_popcount(v);

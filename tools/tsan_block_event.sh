@@ -7,7 +7,7 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p tests/emul/_build
-nvcc -gencode arch=compute_100a,code=sm_100a -Iinclude -O1 -g -std=c++17 -fmad=false -diag-suppress 20011,20014,177 \
+nvcc -gencode arch=compute_100a,code=sm_100a -Iinclude -DNRAPS_EMUL -O1 -g -std=c++17 -fmad=false -diag-suppress 20011,20014,177 \
     -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-pthread,-fsanitize=thread -shared -cudart static \
     -o tests/emul/_build/libbev_emul_tsan.so tests/emul/block_event_emul.cu -Xlinker -ltsan < /dev/null || exit 1
 TSAN=$(ldd tests/emul/_build/libbev_emul_tsan.so | awk '/libtsan/ {print $3}')

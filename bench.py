@@ -313,7 +313,7 @@ def run_ours(a):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "histories_per_generation": H, "histories_per_gpu": count, "generations_timed": K,
-                       "source_mode": source_mode, "tracking_mode": a.tracking, "parallelism": f"history-sharded x{world}, int64 tally all-reduce per generation",
+                       "source_mode": source_mode, "tracking_mode": a.tracking, "kernel_variant": a.variant, "parallelism": f"history-sharded x{world}, int64 tally all-reduce per generation",
                        "launch": info, "l2": "256 MiB device memset between steps inside the timed region (kernel inputs are ~12 KB of tables)"},
             "clocks": clocks,
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
@@ -322,7 +322,7 @@ def run_ours(a):
             "gpu_launches": (3 + (5 if has_bank else 0)) * K,  # source + transport + finalize (+ bank compaction / entropy)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel"),
-                         "peak_source": peak_src, "kernel": ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if has_bank else "false"), "kernel_ms": ms_kernel,
+                         "peak_source": peak_src, "kernel": ("block_event_kernel<4>" if a.variant == "block_event" else ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if has_bank else "false")), "kernel_ms": ms_kernel,
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
                          "actual_limiter": {"what": "instruction issue (ncu, profiles/)", **{k: v for k, v in ncu_facts(
                              "woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel").items() if k not in ("bytes", "source")}},

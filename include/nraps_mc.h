@@ -62,8 +62,9 @@ enum { NRAPS_SCATTER_SINGLE_XI = 0, NRAPS_SCATTER_RUST_PRE182 = 1, NRAPS_SCATTER
 enum { NRAPS_SOURCE_UNIFORM_FUEL = 0, NRAPS_SOURCE_FISSION_BANK = 1 };
 enum { NRAPS_TRACK_SURFACE = 0, NRAPS_TRACK_WOODCOCK = 1 };
 /* FUSED: one persistent lane per neutron (default).  EVENT: the structure-of-arrays bank pipeline in HBM (Woodcock only).
- * BLOCK_EVENT (experimental): surface tracking with the neutrons of a block banked in shared memory and sorted by their
- * next event every round (uniform source only; no trace, no generation batching, mesh image must fit shared memory). */
+ * BLOCK_EVENT: surface tracking with the neutrons of a block banked in shared memory and sorted by their next event
+ * every round.  Measured on a B200 (bit-exact, 0.72x the fused kernel) and therefore NOT compiled into the product
+ * library: the value is rejected with NRAPS_ERR_OPTION unless the library was built with `make BLOCK_EVENT=1`. */
 enum { NRAPS_KERNEL_FUSED = 0, NRAPS_KERNEL_EVENT = 1, NRAPS_KERNEL_BLOCK_EVENT = 2 };
 
 typedef struct nraps_options {
@@ -116,6 +117,11 @@ typedef struct nraps_results {
 } nraps_results;
 
 typedef struct nraps_mc_ctx nraps_mc_ctx;
+
+/* The parity defaults, i.e. the switch set every front end of this repository uses: everything
+ * zero except stale_xs = 1 (faithful to src/mc_code.rs:147) and quiet = 0.  A zero-initialised nraps_options differs
+ * from it in stale_xs -- C callers should start from this initialiser rather than from memset. */
+void nraps_options_default(nraps_options *o);
 
 /* Whole job on one GPU: the monte_carlo() replacement (src/mc_code.rs:276-380).  With the uniform source, generations
  * are independent, so one launch carries several small generations (up to ~2^23 histories, each generation scoring

@@ -82,7 +82,7 @@ EXPORTS = [
     "nraps_mc_finalize_generation", "nraps_mc_tally_buffer", "nraps_mc_set_tally_buffer", "nraps_mc_read_tally",
     "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_mc_bank_compact", "nraps_mc_bank_local",
     "nraps_mc_bank_set_source", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
-    "nraps_strerror", "nraps_last_cuda_error", "nraps_abi_version",
+    "nraps_strerror", "nraps_last_cuda_error", "nraps_abi_version", "nraps_options_default",
     "nraps_process_input", "nraps_deck_free", "nraps_mesh_gen", "nraps_mesh_free", "nraps_problem_from",
     "nraps_format_f32", "nraps_format_f64", "nraps_plot_solution", "nraps_average_assembly", "nraps_k_fund",
     "nraps_diffusion_run",
@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
     L.nraps_dev_logf.argtypes = [_fp, _fp, C.c_uint32, C.c_int32]
     L.nraps_dev_div.argtypes = [_fp, _fp, _fp, _fp, C.c_uint32, C.c_int32]
     L.nraps_dev_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _u32p, _fp, C.c_int32]
+    L.nraps_options_default.argtypes = [C.POINTER(Options)]
+    L.nraps_options_default.restype = None
     L.nraps_strerror.argtypes = [C.c_int]
     L.nraps_strerror.restype = C.c_char_p
     L.nraps_last_cuda_error.restype = C.c_char_p

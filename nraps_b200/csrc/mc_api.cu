@@ -209,13 +209,20 @@ int validate(const nraps_problem *p, const nraps_options *o)
         o->kernel_variant < 0 || o->kernel_variant > NRAPS_KERNEL_BLOCK_EVENT || o->bank_cap < 0 || o->bank_cap > 255 ||
         o->slots_per_thread < 0 || o->slots_per_thread > 64)
         return NRAPS_ERR_OPTION;
-    // the block-level event pipeline (experimental) is built for surface tracking with the uniform source
+    // The block-level event pipeline was measured on a B200 in round 2 (bit-exact, 0.72x the fused kernel: DESIGN.md
+    // section 5) and is compiled out of the product library; `make BLOCK_EVENT=1` builds it back in for experiments.
+#ifndef NRAPS_WITH_BLOCK_EVENT
+    if (o->kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) return NRAPS_ERR_OPTION;
+#endif
     if (o->kernel_variant == NRAPS_KERNEL_BLOCK_EVENT &&
         (o->tracking_mode != NRAPS_TRACK_SURFACE || o->source_mode != NRAPS_SOURCE_UNIFORM_FUEL))
         return NRAPS_ERR_OPTION;
+    // an albedo outside [0, 1] makes the reflected direction cosine leave [-1, 1] (mu' = -mu * b, src/mc_code.rs:56-62)
+    // and lets the Woodcock wall loop diverge; NaN fails both comparisons
+    if (!(p->boundl >= 0.0f && p->boundl <= 1.0f) || !(p->boundr >= 0.0f && p->boundr <= 1.0f)) return NRAPS_ERR_SHAPE;
     // the event pipeline is built for Woodcock tracking with the uniform source (one event = one tentative collision)
     if (o->kernel_variant == NRAPS_KERNEL_EVENT &&
-        (o->tracking_mode != NRAPS_TRACK_WOODCOCK || o->source_mode != NRAPS_SOURCE_UNIFORM_FUEL))
+        (o->tracking_mode != NRAPS_TRACK_WOODCOCK || o->source_mode != NRAPS_SOURCE_UNIFORM_FUEL || o->max_flights > 0xfffffull))
         return NRAPS_ERR_OPTION;
     for (uint32_t i = 0; i < p->N; ++i) {
         if (p->matid[i] >= p->M) return NRAPS_ERR_MESH;
@@ -269,20 +276,33 @@ int ensure_event_bank(nraps_mc_ctx *c, uint64_t count)
 }
 
 // (re)size the per-history slot rows and the dense banks for a shard of `count` histories
-int ensure_bank(nraps_mc_ctx *c, uint64_t count)
+int ensure_bank(nraps_mc_ctx *c, uint64_t count, cudaStream_t s)
 {
     if (count <= c->bank_hist_cap) return NRAPS_OK;
-    dev_free(c->d_slots); dev_free(c->d_counts); dev_free(c->d_block_sums); dev_free(c->d_dense[0]); dev_free(c->d_dense[1]);
-    c->d_slots = c->d_block_sums = c->d_dense[0] = c->d_dense[1] = nullptr;
-    c->d_counts = nullptr;
-    c->bank_hist_cap = 0;
     const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
-    c->dense_cap = 3 * count + 1024; // a bank larger than 3 sites per history is truncated (k / k_prev > 3)
+    // every history keeps at most bank_cap sites, so this bound is exact: no generation can overflow the dense bank
+    // (a tighter guess of 3 sites per history truncated the first generations of problems with k / k0 > 3, found by
+    // the GPU fuzz in round 2)
+    const uint64_t dense_cap = count * c->bank_cap + 1024;
+    unsigned long long *dense[2] = {nullptr, nullptr};
+    CU(dev_malloc((void **)&dense[0], dense_cap * sizeof(unsigned long long)));
+    CU(dev_malloc((void **)&dense[1], dense_cap * sizeof(unsigned long long)));
+    // the bank the next generation samples from may live in the buffers about to be replaced: carry it over
+    for (int w = 0; w < 2; ++w) {
+        if (!c->d_dense[w]) continue;
+        CU(cudaMemcpyAsync(dense[w], c->d_dense[w], c->dense_cap * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        if (c->src_bank == c->d_dense[w]) c->src_bank = dense[w];
+    }
+    CU(cudaStreamSynchronize(s));
+    dev_free(c->d_slots); dev_free(c->d_counts); dev_free(c->d_block_sums); dev_free(c->d_dense[0]); dev_free(c->d_dense[1]);
+    c->d_slots = c->d_block_sums = nullptr;
+    c->d_counts = nullptr;
+    c->d_dense[0] = dense[0]; c->d_dense[1] = dense[1];
+    c->dense_cap = dense_cap;
+    c->bank_hist_cap = 0;
     CU(dev_malloc((void **)&c->d_slots, padded * c->bank_cap * sizeof(unsigned long long)));
     CU(dev_malloc((void **)&c->d_counts, padded));
     CU(dev_malloc((void **)&c->d_block_sums, (padded / kBankTile) * sizeof(unsigned long long)));
-    CU(dev_malloc((void **)&c->d_dense[0], c->dense_cap * sizeof(unsigned long long)));
-    CU(dev_malloc((void **)&c->d_dense[1], c->dense_cap * sizeof(unsigned long long)));
     c->bank_hist_cap = count;
     return NRAPS_OK;
 }
@@ -295,7 +315,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     if (nb < 1 || nb > c->batch || gen + nb > c->generations || (nb > 1 && (trace || c->d_tally != c->d_tally_own))) return NRAPS_ERR_STATE;
     c->last_shard = count;
     if (c->bank_mode) {
-        int rc = ensure_bank(c, count);
+        int rc = ensure_bank(c, count, s);
         if (rc != NRAPS_OK) return rc;
         const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
         if (padded) CU(cudaMemsetAsync(c->d_counts, 0, padded, s));
@@ -342,6 +362,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         CU(run_event_generation(P, c->ev, c->layout.total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
         return NRAPS_OK;
     }
+#ifdef NRAPS_WITH_BLOCK_EVENT
     if (c->opt.kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) {
         if (trace || nb != 1) return NRAPS_ERR_OPTION;
         P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)c->opt.spawn_batch : 0u; // walk-class threshold, 0 = by run length
@@ -349,11 +370,14 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         CU(launch_block_event(P, dim3(c->bev_grid), dim3(c->bev_block), c->bev_smem, c->bev_slots, s));
         return NRAPS_OK;
     }
+#endif
     const int ti = trace ? 1 : 0;
     if (!(c->prepared & (1u << ti))) { // once per (kernel, trace) instantiation: shared-memory opt-in and launch geometry
         if (!c->big)
-            CU(c->woodcock ? prepare_woodcock(c->layout.total, c->G, trace, c->bank_mode)
-                           : prepare_transport(c->layout.total, c->G, trace, c->bank_mode));
+            // the attribute belongs to the kernel instantiation, not to this context: always opt in to the sm_100
+            // maximum, so that a second live context with a smaller image cannot lower it under this one
+            CU(c->woodcock ? prepare_woodcock(kMaxSmem, c->G, trace, c->bank_mode)
+                           : prepare_transport(kMaxSmem, c->G, trace, c->bank_mode));
         // auto geometry: 2 x 576 threads per SM (36 warps) when the instantiation's registers allow it, else 2 x 512;
         // ncu: the kernels are issue bound and the extra warps buy ~3 % (gpurun sweep, profiles/r1_sweeps.txt)
         uint32_t block = c->block, bps = c->blocks_per_sm;
@@ -386,6 +410,13 @@ extern "C" int nraps_mc_trim(int32_t device)
 }
 
 extern "C" int nraps_abi_version(void) { return NRAPS_ABI_VERSION; }
+
+extern "C" void nraps_options_default(nraps_options *o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->stale_xs = 1;
+}
 extern "C" const char *nraps_last_cuda_error(void) { return g_cuda_error.c_str(); }
 
 extern "C" const char *nraps_strerror(int code)
@@ -463,6 +494,9 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     c->stride = dflt ? 152917u : o->stride;
     c->layout = L; c->batch = batch;
     c->max_flights = (uint32_t)std::min<uint64_t>(o->max_flights ? o->max_flights : (1ull << 24), 0xffffffffull);
+    // the event pipeline packs the flight count of a record into 20 bits (mc_event.cu): a cap it cannot count to would
+    // never fire and the host-driven round loop would spin on a runaway history
+    if (o->kernel_variant == NRAPS_KERNEL_EVENT) c->max_flights = std::min<uint32_t>(c->max_flights, 0xfffffu); // validate(): <= 2^20-1 if given
     c->chunk = o->chunk > 0 ? (uint32_t)o->chunk : 64u;
     c->bank_mode = (o->source_mode == NRAPS_SOURCE_FISSION_BANK);
     c->bank_cap = o->bank_cap > 0 ? (uint32_t)o->bank_cap : 8u;
@@ -473,6 +507,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     uint32_t threads = o->threads_per_block > 0 ? (uint32_t)o->threads_per_block : 1024u / bps;
     threads = std::max(32u, std::min(1024u, threads / 32u * 32u));
     c->blocks_per_sm = bps; c->block = threads; c->grid = (uint32_t)c->sm_count * bps;
+#ifdef NRAPS_WITH_BLOCK_EVENT
     if (o->kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) {
         // 2 x 512 threads per SM with 3 neutrons banked per thread unless told otherwise; shrink the bank, then the
         // residency, until the mesh image + the bank of every resident block fit the 227 KB of one SM
@@ -490,6 +525,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
         c->bev_smem = block_event_smem(q, c->bev_slots);
         if (o->chunk <= 0) c->chunk = 256u; // histories a block claims per global atomic
     }
+#endif
 
     // ---- derived tables
     std::vector<float> edges(N + 1);

@@ -7,7 +7,7 @@ fn main() {
     let root = PathBuf::from(env::var("NRAPS_B200_DIR").unwrap_or_else(|_| "../nraps_b200/csrc".into()));
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     // same lists as CU_SRCS / CPP_SRCS of nraps_b200/csrc/Makefile (mc_multi.cu, the NCCL driver, is optional)
-    let cu = ["mc_source.cu", "mc_transport.cu", "mc_woodcock.cu", "mc_event.cu", "mc_block_event.cu", "mc_finalize.cu", "mc_bank.cu", "mc_api.cu"];
+    let cu = ["mc_source.cu", "mc_transport.cu", "mc_woodcock.cu", "mc_event.cu", "mc_finalize.cu", "mc_bank.cu", "mc_api.cu"];
     let cpp = ["host_input.cpp", "host_mesh.cpp", "host_output.cpp", "host_diffusion.cpp"];
     let mut objs = Vec::new();
     for f in cu.iter().chain(cpp.iter()) {

@@ -472,6 +472,15 @@ def test_event_pipeline_equals_fused_woodcock_and_oracle(case):
     assert e.value.code == 7
 
 
+def test_event_pipeline_flight_cap_truncates_like_the_fused_kernel():
+    """The event variant counts flights in 20 bits of a packed word: a small cap must cut the same histories at the same
+    point as the fused kernel and the oracle (a cap it cannot count to is refused at creation, tests/test_host.py)."""
+    got, want = _both("c", generations=2, histories=20_000, tracking_mode="woodcock", max_flights=7,
+                      gpu_kw=dict(kernel_variant="event"))
+    _assert_identical(got, want)
+    assert got.counters["truncated"] > 0
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(tracking_mode="woodcock"), dict(tracking_mode="woodcock", source_mode="fission_bank")])
 def test_analytic_k_infinity_deck_a_on_gpu(kw):
     """k = nu*Sigma_f / Sigma_a = 1.26 exactly for deck A once the stale-index quirk is off (see the CPU twin)."""

@@ -377,7 +377,7 @@ def test_validation_codes_come_before_any_cuda_call_and_there_is_no_fallback():
 
     def code(**kw):
         args = dict(variables=v, xsdata=xs, delta_x=dx, meshid=mesh, fuel_indices=fuel, generations=2, histories=10, skip=1)
-        opts = {k: kw.pop(k) for k in list(kw) if k in ("scatter_mode", "tracking_mode", "kernel_variant", "source_mode", "bank_cap")}
+        opts = {k: kw.pop(k) for k in list(kw) if k in ("scatter_mode", "tracking_mode", "kernel_variant", "source_mode", "bank_cap", "max_flights")}
         args.update(kw)
         with pytest.raises(_lib.NrapsError) as e:
             nb.monte_carlo(args["variables"], args["xsdata"], args["delta_x"], args["meshid"], args["fuel_indices"], args.get("k_new", 1.0),
@@ -397,8 +397,11 @@ def test_validation_codes_come_before_any_cuda_call_and_there_is_no_fallback():
     assert code(xsdata=nb.XSData(**{**xs.__dict__, "inv_sigtr": xs.inv_sigtr * f32(-1)})) == 4
     assert code(xsdata=nb.XSData(**{**xs.__dict__, "inv_sigtr": xs.inv_sigtr * f32(np.inf)})) == 4
     assert code(kernel_variant="event") == 7                                  # the event pipeline is Woodcock-only
-    assert code(kernel_variant="block_event", tracking_mode="woodcock") == 7  # the block-level pipeline is surface-only ...
-    assert code(kernel_variant="block_event", source_mode="fission_bank") == 7  # ... and uniform-source-only
+    assert code(kernel_variant="block_event") == 7                            # measured slower on a B200: compiled out of the product
+    assert code(kernel_variant="event", tracking_mode="woodcock", max_flights=1 << 21) == 7  # its flight counter is 20 bits wide
+    for b in (-0.1, 1.5, float("nan")):                                       # albedo outside [0, 1]: mu' = -mu * b leaves [-1, 1]
+        assert code(variables=nb.Variables(**{**v.__dict__, "boundl": b})) == 2
+        assert code(variables=nb.Variables(**{**v.__dict__, "boundr": b})) == 2
     assert code(bank_cap=300) == 7
     v1 = nb.Variables(**{**v.__dict__, "energygroups": 1})
     assert code(variables=v1) == 2                                            # G >= 2: nut[M*1] (src/mc_code.rs:356)

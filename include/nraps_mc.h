@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NRAPS_ABI_VERSION 3
+#define NRAPS_ABI_VERSION 4
 #define NRAPS_TALLY_FRAC_BITS 28 /* tallies are exact integers in 2^-28 cm */
 
 enum {
@@ -82,7 +82,7 @@ typedef struct nraps_options {
     int32_t bank_cap;              /* fission_bank: sites kept per history, 1..255; 0 = 8 */
     int32_t spawn_batch;           /* refill a warp's dead lanes only once this many are dead (0 = auto); block_event variant:
                                     * walks predicted to cross >= this many cells form the "long" list (0 = split by run length) */
-    int32_t walk_cap;              /* surface tracking: crossings per lane before the warp regroups; 0 = auto, -1 = unlimited */
+    int32_t walk_cap;              /* surface tracking: crossings per lane before the warp regroups; 0 or -1 = to the end of the segment */
     int32_t slots_per_thread;      /* block_event variant: neutrons banked per thread of a block; 0 = 3 (was reserved1) */
     uint64_t max_flights;          /* per-history safety cap; 0 = 1<<24               */
 } nraps_options;

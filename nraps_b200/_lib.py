@@ -9,14 +9,15 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnraps_b200.so")
+# NRAPS_LIB_DIR: an experiment build of the same library (make LIBDIR=...); there is still no non-CUDA path behind it
+LIB_PATH = os.path.join(os.environ.get("NRAPS_LIB_DIR") or os.path.join(_HERE, "lib"), "libnraps_b200.so")
 
 CT_WORDS = 8
 CT_NAMES = ["histories", "collisions", "crossings", "flights", "reflections", "leaks", "truncated", "banked"]
 TR_WORDS = 10
 TR_NAMES = ["collisions", "crossings", "flights", "reflections", "rng_lo", "rng_hi", "cell", "xbits", "fate", "group"]
 TALLY_FRAC_BITS = 28
-ABI_VERSION = 3  # NRAPS_ABI_VERSION of include/nraps_mc.h this binding was written against
+ABI_VERSION = 4  # NRAPS_ABI_VERSION of include/nraps_mc.h this binding was written against
 
 _fp = C.POINTER(C.c_float)
 _u8p = C.POINTER(C.c_uint8)

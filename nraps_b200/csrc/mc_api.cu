@@ -146,17 +146,21 @@ struct nraps_mc_ctx {
     Pcg master{};
     uint64_t stride = 0;
     SmemLayout layout{};
+    uint32_t smem_total = 0;       // dynamic shared memory of the transport launch
+    uint32_t surf_mode = SURF_SPLIT; // tally placement of the surface kernel (mc_internal.h)
     uint32_t grid = 0, block = 0, blocks_per_sm = 0, chunk = 0, max_flights = 0;
     uint32_t geo_grid[2] = {0, 0}, geo_block[2] = {0, 0}; // launch geometry of the plain / trace instantiation
 
     float *d_edges = nullptr, *d_xs = nullptr, *d_dx = nullptr, *d_nut = nullptr, *d_sigf = nullptr;
     uint32_t *d_runb = nullptr;
+    uint2 *d_segw = nullptr;                 // surface kernel: segment bounds + width bits per cell
+    unsigned long long *d_diff = nullptr;    // surface kernel: difference array of the full-cell scores [batch*G*N]
     uint8_t *d_matid = nullptr;
     uint16_t *d_fuel = nullptr, *d_bucket = nullptr;
     uint32_t NB = 0;
     float inv_h = 0.0f;
     bool woodcock = false;
-    uint32_t prepared = 0, big = 0, walk_cap_auto = 0x7fffffffu;
+    uint32_t prepared = 0, big = 0;
     uint32_t batch = 1; // generations one launch may carry (small generations do not fill the GPU on their own)
     ulonglong2 *d_jump = nullptr;
     unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
@@ -243,6 +247,7 @@ void free_ctx(nraps_mc_ctx *c)
 {
     if (!c) return;
     dev_free(c->d_edges); dev_free(c->d_xs); dev_free(c->d_dx); dev_free(c->d_nut); dev_free(c->d_sigf);
+    dev_free(c->d_segw); dev_free(c->d_diff);
     dev_free(c->d_runb); dev_free(c->d_matid); dev_free(c->d_fuel); dev_free(c->d_jump); dev_free(c->d_bucket);
     dev_free(c->d_tally_own); dev_free(c->d_work); dev_free(c->d_counters_total);
     dev_free(c->d_res_moments); dev_free(c->d_terms); dev_free(c->d_res_flux); dev_free(c->d_res_fission); dev_free(c->d_k_hist); dev_free(c->d_k_cur);
@@ -324,8 +329,11 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     CU(cudaMemsetAsync(c->d_tally, 0, words * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
     if (count == 0) return NRAPS_OK;
+    const bool surface_fused = !c->woodcock && c->opt.kernel_variant == NRAPS_KERNEL_FUSED;
+    if (surface_fused) CU(cudaMemsetAsync(c->d_diff, 0, (uint64_t)nb * c->G * c->N * sizeof(unsigned long long), s));
 
     TransportParams P{};
+    P.segw = c->d_segw; P.diff = c->d_diff; P.surf_mode = c->surf_mode;
     P.edges = c->d_edges; P.runb = c->d_runb; P.matid = c->d_matid; P.fuel = c->d_fuel; P.xs = c->d_xs; P.jump = c->d_jump;
     P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF; P.NB = c->NB; P.bucket = c->d_bucket; P.inv_h = c->inv_h; P.big = c->big;
     P.boundl = c->boundl; P.boundr = c->boundr; P.dx_fuel = c->dx_fuel;
@@ -340,7 +348,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;
     P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)std::min(c->opt.spawn_batch, 32) : (c->woodcock ? 2u : 1u);
-    P.walk_cap = c->opt.walk_cap > 0 ? (uint32_t)c->opt.walk_cap : (c->opt.walk_cap < 0 ? 0x7fffffffu : c->walk_cap_auto);
+    P.walk_cap = c->opt.walk_cap > 0 ? (uint32_t)c->opt.walk_cap : 0x7fffffffu;
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
     P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
@@ -359,7 +367,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         if (trace) return NRAPS_ERR_OPTION;
         int rc = ensure_event_bank(c, count);
         if (rc != NRAPS_OK) return rc;
-        CU(run_event_generation(P, c->ev, c->layout.total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
+        CU(run_event_generation(P, c->ev, c->smem_total, c->sm_count, s, &c->ev_iterations)); // synchronous: host-driven loop
         return NRAPS_OK;
     }
 #ifdef NRAPS_WITH_BLOCK_EVENT
@@ -377,14 +385,14 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
             // the attribute belongs to the kernel instantiation, not to this context: always opt in to the sm_100
             // maximum, so that a second live context with a smaller image cannot lower it under this one
             CU(c->woodcock ? prepare_woodcock(kMaxSmem, c->G, trace, c->bank_mode)
-                           : prepare_transport(kMaxSmem, c->G, trace, c->bank_mode));
+                           : prepare_transport(kMaxSmem, c->G, c->surf_mode, trace, c->bank_mode));
         // auto geometry: 2 x 576 threads per SM (36 warps) when the instantiation's registers allow it, else 2 x 512;
         // ncu: the kernels are issue bound and the extra warps buy ~3 % (gpurun sweep, profiles/r1_sweeps.txt)
         uint32_t block = c->block, bps = c->blocks_per_sm;
         if (c->opt.threads_per_block <= 0 && c->opt.blocks_per_sm <= 0 && bps == 2) {
             auto occ = [&](int b) {
-                return c->woodcock ? occupancy_woodcock(c->G, c->big, trace, c->bank_mode, b, c->layout.total)
-                                   : occupancy_transport(c->G, c->big, trace, c->bank_mode, b, c->layout.total);
+                return c->woodcock ? occupancy_woodcock(c->G, c->big, trace, c->bank_mode, b, c->smem_total)
+                                   : occupancy_transport(c->G, c->surf_mode, trace, c->bank_mode, b, c->smem_total);
             };
             block = occ(576) >= 2 ? 576u : 512u;
         }
@@ -392,8 +400,12 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         c->geo_grid[ti] = (uint32_t)c->sm_count * bps;
         c->prepared |= 1u << ti;
     }
-    if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->layout.total, s));
-    else CU(launch_transport(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->layout.total, s));
+    if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
+    else {
+        CU(launch_transport(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
+        // the cells a flight crossed completely were booked as range updates: fold their prefix sums into the tally
+        CU(launch_tally_prefix(c->d_diff, c->d_tally, nb * c->G, c->N, s));
+    }
     return NRAPS_OK;
 }
 
@@ -455,21 +467,47 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
         for (uint32_t i = 0; i < N; ++i) min_dx = std::min(min_dx, p->right[i] - p->left[i]);
         NB = (uint32_t)std::min(16384.0, std::max(1.0, std::ceil((double)p->right[N - 1] / (double)min_dx)));
     }
-    // a mesh too large for one SM's shared memory runs in BIG mode: tables through L1/L2, tally in global memory
+    // Shared-memory image and where the tallies live.  Surface tracking with the fused kernel: SurfLayout (direct bins +
+    // difference array in shared memory when two blocks still fit an SM, the difference array alone when not, both in
+    // global memory when even that exceeds one SM).  Woodcock and the event variants: SmemLayout; a mesh too large for
+    // one SM runs in BIG mode there (tables through L1/L2, tally in global memory).
+    const bool surface_fused = !woodcock && o->kernel_variant == NRAPS_KERNEL_FUSED;
     SmemLayout L = make_layout(M, G, N, NF, NB, 0);
-    const uint32_t big = L.total > kMaxSmem ? 1u : 0u;
-    if (big) L = make_layout(M, G, N, NF, NB, 1);
-    if (L.total > kMaxSmem || (big && o->kernel_variant != NRAPS_KERNEL_FUSED)) return NRAPS_ERR_TOO_LARGE;
+    uint32_t big = 0, surf_mode = SURF_SPLIT, smem_total = 0;
+    auto surf_total = [&](uint32_t mode, uint32_t rows) { return make_surface_layout(M, G, N, mode, rows).total; };
+    if (surface_fused) {
+        if (2ull * (surf_total(SURF_SPLIT, G) + 1024) <= 233472ull) surf_mode = SURF_SPLIT;
+        else if (surf_total(SURF_UNIFIED, G) <= kMaxSmem) surf_mode = SURF_UNIFIED;
+        else surf_mode = SURF_GLOBAL;
+        big = surf_mode == SURF_GLOBAL;
+        smem_total = surf_total(surf_mode, G);
+        if (smem_total > kMaxSmem) return NRAPS_ERR_TOO_LARGE;
+    } else {
+        big = L.total > kMaxSmem ? 1u : 0u;
+        if (big) L = make_layout(M, G, N, NF, NB, 1);
+        if (L.total > kMaxSmem || (big && o->kernel_variant != NRAPS_KERNEL_FUSED)) return NRAPS_ERR_TOO_LARGE;
+        smem_total = L.total;
+    }
     // Generations of the uniform source are independent, and one of the shipped decks' 1e5..1e6 histories leaves most
     // of the 148 SMs idle: let a launch carry enough generations for ~2^23 histories, each scoring into its own G
     // tally rows, as long as the block still fits twice on an SM.
     uint32_t batch = 1;
     if (allow_batch && !big && o->source_mode == NRAPS_SOURCE_UNIFORM_FUEL && o->kernel_variant == NRAPS_KERNEL_FUSED) {
         uint64_t want = std::min<uint64_t>(std::min<uint64_t>((1ull << 23) / p->histories, p->generations), 64);
-        while (want > 1 && make_layout(M, G, N, NF, NB, 0, (uint32_t)want * G).total > 100u * 1024u) --want;
-        if (want > 1) {
-            batch = (uint32_t)want;
-            L = make_layout(M, G, N, NF, NB, 0, batch * G);
+        const uint32_t budget = 100u * 1024u;
+        if (surface_fused) {
+            // the split image doubles the bins per generation: keep it if the whole batch still fits, else the unified one
+            uint32_t bm = surf_mode;
+            if (want > 1 && bm == SURF_SPLIT && surf_total(SURF_SPLIT, (uint32_t)want * G) > budget) bm = SURF_UNIFIED;
+            while (want > 1 && surf_total(bm, (uint32_t)want * G) > budget) --want;
+            if (want > 1) { batch = (uint32_t)want; surf_mode = bm; smem_total = surf_total(bm, batch * G); }
+        } else {
+            while (want > 1 && make_layout(M, G, N, NF, NB, 0, (uint32_t)want * G).total > budget) --want;
+            if (want > 1) {
+                batch = (uint32_t)want;
+                L = make_layout(M, G, N, NF, NB, 0, batch * G);
+                smem_total = L.total;
+            }
         }
     }
 
@@ -492,7 +530,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     const bool dflt = (o->seed == 0 && o->stream == 0 && o->stride == 0);
     c->master = pcg_seed(dflt ? 42u : o->seed, dflt ? 54u : o->stream);
     c->stride = dflt ? 152917u : o->stride;
-    c->layout = L; c->batch = batch;
+    c->layout = L; c->batch = batch; c->smem_total = smem_total; c->surf_mode = surf_mode;
     c->max_flights = (uint32_t)std::min<uint64_t>(o->max_flights ? o->max_flights : (1ull << 24), 0xffffffffull);
     // the event pipeline packs the flight count of a record into 20 bits (mc_event.cu): a cap it cannot count to would
     // never fire and the host-driven round loop would spin on a runaway history
@@ -503,7 +541,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
 
     // launch geometry: persistent grid, a multiple of the SM count
     uint32_t bps = o->blocks_per_sm > 0 ? (uint32_t)o->blocks_per_sm : 2u;
-    while (bps > 1 && (uint64_t)bps * (L.total + 1024) > 233472ull) --bps;
+    while (bps > 1 && (uint64_t)bps * (smem_total + 1024) > 233472ull) --bps;
     uint32_t threads = o->threads_per_block > 0 ? (uint32_t)o->threads_per_block : 1024u / bps;
     threads = std::max(32u, std::min(1024u, threads / 32u * 32u));
     c->blocks_per_sm = bps; c->block = threads; c->grid = (uint32_t)c->sm_count * bps;
@@ -541,23 +579,24 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
         i = j;
     }
     for (uint32_t j = 0; j < NF; ++j) fuel[j] = (uint16_t)p->fuel_indices[j];
-    {   // Walk cap (crossings before a warp regroups).  Lanes cross run after run roughly in step; a cap that divides
-        // every run longer than itself keeps them in step (all reach the run boundary on the same trip), any other
-        // cap leaves a short odd trip per run and the lanes drift apart.  Measured (profiles/r1_sweeps.txt): runs of
-        // 8 and 4 cells -> any cap >= 8; runs of 80 and 40 -> 20 (1.76e8 histories/s against 1.55e8 at 16 or 24).
-        // Pick the largest cap <= 24 that divides the runs longer than it (runs covering < 5 % of the cells ignored).
-        std::vector<uint32_t> cells_in_runs_of(N + 1, 0);
-        for (uint32_t i = 0; i < N; i = runb[i] >> 16) cells_in_runs_of[(runb[i] >> 16) - i] += (runb[i] >> 16) - i;
-        uint32_t cap = 0;
-        for (uint32_t cand = 24; cand >= 4 && !cap; --cand) {
-            uint32_t misfit = 0;
-            for (uint32_t len = cand + 1; len <= N; ++len)
-                if (len % cand) misfit += cells_in_runs_of[len];
-            if ((uint64_t)misfit * 20 <= N) cap = cand;
+    // Segments of the surface kernel: maximal ranges of cells of one material run whose widths e[i+1] - e[i] are the same
+    // binary32 number.  Edges accumulate in f32 upstream (src/main.rs:119-140), so the width of a fuel or water cell
+    // changes by an ulp where the position crosses a power of two: a material run is one segment, or two around such a
+    // point.  Inside a segment x - edge is the same number for every cell crossed completely (mc_transport.cu).
+    std::vector<uint2> segw(N);
+    for (uint32_t i = 0; i < N;) {
+        const float w = edges[i + 1] - edges[i];
+        uint32_t wbits;
+        std::memcpy(&wbits, &w, sizeof(wbits));
+        uint32_t j = i + 1;
+        while (j < (runb[i] >> 16)) {
+            const float wj = edges[j + 1] - edges[j];
+            if (std::memcmp(&wj, &w, sizeof(float)) != 0) break;
+            ++j;
         }
-        c->walk_cap_auto = cap ? cap : 8u;
+        for (uint32_t q = i; q < j; ++q) segw[q] = make_uint2(i | (j << 16), wbits);
+        i = j;
     }
-
     std::vector<float> xs(xs_floats(M, G));
     float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *nusigf = chi_cdf + MG, *sigtr = nusigf + MG,
           *scat_cdf = sigtr + MG, *inv_maj = scat_cdf + MG * G * G;
@@ -616,7 +655,8 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     const uint64_t GN = (uint64_t)G * N;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return r == cudaSuccess; };
-    ok(upload(&c->d_edges, edges)); ok(upload(&c->d_runb, runb)); ok(upload(&c->d_matid, matid));
+    ok(upload(&c->d_edges, edges)); ok(upload(&c->d_runb, runb)); ok(upload(&c->d_matid, matid)); ok(upload(&c->d_segw, segw));
+    ok(dev_malloc((void **)&c->d_diff, batch * GN * sizeof(unsigned long long)));
     ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump)); ok(upload(&c->d_bucket, bucket));
     ok(upload(&c->d_dx, dx)); ok(upload(&c->d_nut, nut)); ok(upload(&c->d_sigf, sigf));
     ok(dev_malloc((void **)&c->d_tally_own, (batch * GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
@@ -856,7 +896,7 @@ extern "C" int nraps_mc_bank_set_source(nraps_mc_ctx *c, uint64_t gen, const voi
 extern "C" int nraps_mc_launch_info(nraps_mc_ctx *c, uint32_t out[6])
 {
     if (!c || !out) return NRAPS_ERR_NULL;
-    out[0] = c->geo_grid[0] ? c->geo_grid[0] : c->grid; out[1] = c->geo_block[0] ? c->geo_block[0] : c->block; out[2] = c->layout.total; out[3] = c->blocks_per_sm;
+    out[0] = c->geo_grid[0] ? c->geo_grid[0] : c->grid; out[1] = c->geo_block[0] ? c->geo_block[0] : c->block; out[2] = c->smem_total; out[3] = c->blocks_per_sm;
     if (c->opt.kernel_variant == NRAPS_KERNEL_BLOCK_EVENT) {
         out[0] = c->bev_grid; out[1] = c->bev_block; out[2] = c->bev_smem; out[3] = c->bev_grid / (uint32_t)c->sm_count;
     }

@@ -54,6 +54,45 @@ __host__ __device__ inline SmemLayout make_layout(uint32_t M, uint32_t G, uint32
     return L;
 }
 
+// Shared-memory image of the surface-tracking kernel (mc_transport.cu).  A flight scores the same value into every
+// cell it crosses completely inside one *segment* (cells of one material run whose widths are the same binary32
+// number), so those scores are kept as a difference array `diff` (+v at the first cell, -v one past the last) and
+// only the partial cells at the two ends of a flight are scored one by one (`direct`); tally = direct + prefix(diff).
+// All bins are 64-bit integers in 2^-28 cm split in two u32 words, sums are exact mod 2^64, so the prefix sum at the
+// end reproduces the cell-by-cell tally of src/mc_code.rs:163,173,184 bit for bit.
+//   SURF_SPLIT   : direct[rows][N] and diff[rows][N+1] in shared memory (meshes that leave room for two blocks per SM)
+//   SURF_UNIFIED : diff only; a direct score is the point update +s at the cell, -s at the next (half the memory)
+//   SURF_GLOBAL  : mesh tables through L1/L2, both arrays in global memory (mesh too large for one SM)
+enum { SURF_SPLIT = 0, SURF_UNIFIED = 1, SURF_GLOBAL = 2 };
+struct SurfLayout {
+    uint32_t diff_lo, diff_hi;     // u32[rows*(N+1)] each
+    uint32_t direct_lo, direct_hi; // u32[rows*N] each (SURF_SPLIT only)
+    uint32_t edges;                // f32[N+1]
+    uint32_t segw;                 // u32x2[N]: segment bounds of the cell (lo | hi<<16), its width bits
+    uint32_t xs;                   // f32[xs_floats]
+    uint32_t matid;                // u8[N]
+    uint32_t total;
+};
+__host__ __device__ inline SurfLayout make_surface_layout(uint32_t M, uint32_t G, uint32_t N, uint32_t mode, uint32_t rows = 0)
+{
+    if (!rows) rows = G;
+    if (mode == SURF_GLOBAL) N = 0;
+    SurfLayout L;
+    uint32_t off = 0;
+    L.diff_lo = off;   off += (mode == SURF_GLOBAL ? 0u : rows * (N + 1) * 4u);
+    L.diff_hi = off;   off += (mode == SURF_GLOBAL ? 0u : rows * (N + 1) * 4u);
+    L.direct_lo = off; off += (mode == SURF_SPLIT ? rows * N * 4u : 0u);
+    L.direct_hi = off; off += (mode == SURF_SPLIT ? rows * N * 4u : 0u);
+    L.edges = off;     off += (mode == SURF_GLOBAL ? 0u : (N + 1) * 4u);
+    off = align_up(off, 8);
+    L.segw = off;      off += N * 8u;
+    off = align_up(off, 16); // float4 rows of the CDF tables
+    L.xs = off;        off += xs_floats(M, G) * 4u;
+    L.matid = off;     off += align_up(N, 4);
+    L.total = align_up(off, 16);
+    return L;
+}
+
 struct TransportParams {
     // read-only tables in global memory (device pointers)
     const float *edges;
@@ -64,6 +103,9 @@ struct TransportParams {
     const ulonglong2 *jump;
     const uint16_t *bucket;  // [NB] Woodcock position buckets (NB = 0 in surface mode)
     const uint4 *source;     // [hist_end-hist_begin][2] born neutrons written by source_kernel
+    const uint2 *segw;       // [N] surface kernel: {segment lo | hi << 16, width bits} of each cell
+    unsigned long long *diff; // [rows*N] surface kernel: difference array of the full-cell scores (global, summed over blocks)
+    uint32_t surf_mode;      // SURF_SPLIT / SURF_UNIFIED / SURF_GLOBAL
     uint32_t M, G, N, NF, NB, big;
     uint32_t rows;       // tally rows of this launch = batch * G: generations gen .. gen+batch-1 share the launch
     uint64_t hist_shard; // histories of one generation in this launch (hist_end - hist_begin = batch * hist_shard)
@@ -131,7 +173,9 @@ struct FinalizeParams {
 };
 
 cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
-int occupancy_transport(uint32_t G, bool big, bool trace, bool bank, int block, uint32_t smem);
+int occupancy_transport(uint32_t G, uint32_t surf_mode, bool trace, bool bank, int block, uint32_t smem);
+// tally[r][i] += sum_{j <= i} diff[r][j] for every tally row of a launch (one block per row)
+cudaError_t launch_tally_prefix(const unsigned long long *diff, unsigned long long *tally, uint32_t rows, uint32_t N, cudaStream_t s);
 int occupancy_woodcock(uint32_t G, bool big, bool trace, bool bank, int block, uint32_t smem);
 cudaError_t launch_source(const TransportParams &p, bool bank, uint4 *out, cudaStream_t s);
 cudaError_t launch_woodcock(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s);
@@ -142,7 +186,7 @@ cudaError_t launch_block_event(const TransportParams &p, dim3 grid, dim3 block, 
 cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s);
 cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
                                 double *entropy_out, unsigned long long *size_out, cudaStream_t s);
-cudaError_t prepare_transport(uint32_t smem_bytes, uint32_t G, bool trace, bool bank);
+cudaError_t prepare_transport(uint32_t smem_bytes, uint32_t G, uint32_t surf_mode, bool trace, bool bank);
 cudaError_t launch_finalize(const FinalizeParams &p, cudaStream_t s);
 cudaError_t launch_probe_logf(const float *x, float *out, uint32_t n, cudaStream_t s);
 cudaError_t launch_probe_div(const float *t, const float *mu, float *out_fast, float *out_ieee, uint32_t n, cudaStream_t s);

@@ -2,63 +2,152 @@
 // from a per-warp chunk of history indices the moment its neutron dies.
 //
 // Replaces, per history (reference src/mc_code.rs):
-//   spawn_neutron + energy ........ :7-53, 228-230   (stage SPAWN)
+//   spawn_neutron + energy ........ :7-53, 228-230   (source_kernel, mc_source.cu; the lane adopts the record)
 //   particle_travel flight draw ... :147-148, 209    (stage FLIGHT)
 //   boundary / cross_mesh loop .... :151-181, 56-79  (stage WALK)
 //   scat_mat_calc + interaction ... :82-132, 183-208 (stage COLLIDE)
-//   particle_lifetime tally ....... :224, 163/173/184 (shared-memory fixed-point bins)
+//   particle_lifetime tally ....... :224, 163/173/184 (fixed-point bins, see below)
 //
 // Warp structure: every trip of the outer loop each live lane draws one flight,
-// walks cell crossings until its flight ends (collision, material change, leak),
+// walks cell crossings until its flight ends (collision, segment end, leak),
 // then the warp reconverges (__syncwarp) and the lanes that collided run the
-// collision stage together.  The walk is bounded by the length of a material
-// run (8 fuel / 4 water cells in the shipped decks), so lanes of a warp stay
-// within a small factor of each other.  profiles/r1a_* is the ncu evidence that
-// drove this shape: without the explicit reconvergence points the compiler let
-// lanes fall out of the walk loop one by one (7.8 of 32 lanes active).
+// collision stage together.  profiles/r1a_* is the ncu evidence that drove this
+// shape: without the explicit reconvergence points the compiler let lanes fall
+// out of the walk loop one by one (7.8 of 32 lanes active).
 //
-// Tallies: score -> (u64)(score * 2^28), added to a 64-bit bin kept as two u32
-// words in shared memory (ATOMS.ADD is native for u32 only; f32 and u64 shared
-// atomics compile to CAS loops on sm_100a).  Integer sums are associative, so
-// the result is independent of lane / block / GPU scheduling and bit-identical
-// to the oracle's.
+// Tallies (round 2: range updates).  The reference scores |dx / mu| into every
+// cell a flight crosses (:163,173,184).  Round 1 did exactly that, one division
+// + one shared atomic per crossing: 23 SASS instructions per crossing, 44 % of
+// the kernel (profiles/r1r_*).  But a flight that crosses a cell completely
+// scores |(e[i] - e[i+1]) / mu|, and inside a *segment* -- consecutive cells of
+// one material whose widths e[i+1] - e[i] are the same binary32 number, i.e.
+// practically a whole material run -- that is one and the same value v for every
+// cell.  So the walk loop only replays what decides the trajectory (the two
+// additions and the compare of the reference's collision test and the running
+// ds += t, all in the reference's operation order, 9 instructions per
+// crossing), and the scores of the n cells crossed completely are booked as ONE
+// range update of a difference array: diff[first] += fx(v), diff[last+1] -=
+// fx(v).  fx() is the same float -> 2^-28 fixed-point conversion as before and
+// the bins are exact 64-bit integers (two u32 words, ATOMS.ADD is native for u32
+// only), so tally = direct + prefix_sum(diff) (tally_prefix_kernel) equals the
+// cell-by-cell sums of the oracle bit for bit, for any scheduling.  Only the
+// partial cells at the two ends of a flight are still scored one by one.
 #include "mc_lane.cuh"
 
 namespace nraps {
 
 namespace {
 
-enum { EV_NONE = 0, EV_COLLIDE = 1, EV_MATCHANGE = 2 };
+enum { EV_NONE = 0, EV_COLLIDE = 1, EV_SEGEXIT = 2 };
 
-template <int TG, bool TRACE, bool BANK, bool BIG>
+// 64-bit bin (low word at shared address `ref`, high word hi_off bytes above) += / -= fx.  The high word is touched
+// only when the low word wraps or fx itself needs it (a score >= 16 cm): both rare, one predicate pair guards the RED.
+// `wide` = the score itself needs the high word (fx >= 2^32, i.e. >= 16 cm), known from one compare on the scaled float.
+static __device__ __forceinline__ void bin_add(uint32_t ref, uint32_t hi_off, unsigned long long fx, bool wide)
+{
+    const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
+    const uint32_t old = atoms_add(ref, l);
+    const bool carry = old > ~l;
+    if (carry | wide) reds_add(ref + hi_off, h + (carry ? 1u : 0u));
+}
+static __device__ __forceinline__ void bin_sub(uint32_t ref, uint32_t hi_off, unsigned long long fx, bool wide)
+{
+    const uint32_t l = (uint32_t)fx, h = (uint32_t)(fx >> 32);
+    const uint32_t old = atoms_add(ref, 0u - l);
+    const bool borrow = old < l;
+    if (borrow | wide) reds_add(ref + hi_off, 0u - (h + (borrow ? 1u : 0u)));
+}
+
+// Where the tallies of this block live (see SurfLayout, mc_internal.h).
+template <int MODE> struct Tally {
+    uint32_t diff_base, direct_base, diff_hi_off, direct_hi_off; // shared byte addresses / offsets
+    uint32_t N;
+    unsigned long long *g_direct, *g_diff; // SURF_GLOBAL
+    // score of one partially crossed cell (the cell a flight starts or ends in, a wall cell)
+    __device__ __forceinline__ void direct(int row, int cell, float v) const
+    {
+        const float vs = fmul(v, kTallyScale);
+        const unsigned long long fx = __float2ull_rz(vs);
+        const bool wide = vs >= 4294967296.0f;
+        if (MODE == SURF_SPLIT) {
+            bin_add(direct_base + 4u * (uint32_t)(row * (int)N + cell), direct_hi_off, fx, wide);
+        } else if (MODE == SURF_UNIFIED) {
+            const uint32_t ref = diff_base + 4u * (uint32_t)(row * (int)(N + 1u) + cell);
+            bin_add(ref, diff_hi_off, fx, wide);
+            bin_sub(ref + 4u, diff_hi_off, fx, wide);
+        } else {
+            atomicAdd(g_direct + (size_t)row * N + cell, fx);
+        }
+    }
+    // the same score v for every cell of [lo, lo + n): one range update of the difference array
+    __device__ __forceinline__ void range(int row, int lo, int n, float v) const
+    {
+        const float vs = fmul(v, kTallyScale);
+        const unsigned long long fx = __float2ull_rz(vs);
+        const bool wide = vs >= 4294967296.0f;
+        if (MODE != SURF_GLOBAL) {
+            const uint32_t ref = diff_base + 4u * (uint32_t)(row * (int)(N + 1u) + lo);
+            bin_add(ref, diff_hi_off, fx, wide);
+            bin_sub(ref + 4u * (uint32_t)n, diff_hi_off, fx, wide);
+        } else {
+            unsigned long long *d = g_diff + (size_t)row * N + lo;
+            atomicAdd(d, fx);
+            if ((uint32_t)(lo + n) < N) atomicAdd(d + n, 0ull - fx); // the entry one past the last cell feeds no prefix
+        }
+    }
+};
+
+template <int TG, bool TRACE, bool BANK, int MODE>
 __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool BIG = (MODE == SURF_GLOBAL);
     const int G = TG ? TG : (int)P.G;
     const int M = (int)P.M, N = (int)P.N;
-    const SmemLayout L = make_layout(P.M, P.G, P.N, P.NF, P.NB, BIG, P.rows);
-
-    const SmemView S = load_block_tables(smem_raw, P, L);
-    uint32_t *s_lo = S.lo;
-    const float *s_edges = S.edges, *s_xs = S.xs;
-    const MeshRef<BIG> mesh(S);
-    const int tid = threadIdx.x;
+    const SurfLayout L = make_surface_layout(P.M, P.G, P.N, MODE, P.rows);
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int MG = M * G;
-    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_nusigf = s_xs + 3 * MG,
-                *s_scat = s_xs + 5 * MG;
+
+    // ---------------- block prologue: stage the tables, clear the bins
+    float *s_xs = reinterpret_cast<float *>(smem_raw + L.xs);
+    for (int i = tid; i < (int)xs_floats(P.M, P.G); i += nthr) s_xs[i] = P.xs[i];
+    if (!BIG) {
+        uint32_t *bins = reinterpret_cast<uint32_t *>(smem_raw + L.diff_lo);
+        const int n_words = (int)(L.edges - L.diff_lo) / 4; // diff lo/hi (+ direct lo/hi) are contiguous
+        for (int i = tid; i < n_words; i += nthr) bins[i] = 0u;
+        float *e = reinterpret_cast<float *>(smem_raw + L.edges);
+        for (int i = tid; i <= N; i += nthr) e[i] = P.edges[i];
+        uint2 *sw = reinterpret_cast<uint2 *>(smem_raw + L.segw);
+        for (int i = tid; i < N; i += nthr) { sw[i] = P.segw[i]; smem_raw[L.matid + i] = P.matid[i]; }
+    }
+    __syncthreads();
+
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    Tally<MODE> T;
+    T.diff_base = smem_base + L.diff_lo; T.diff_hi_off = L.diff_hi - L.diff_lo;
+    T.direct_base = smem_base + L.direct_lo; T.direct_hi_off = L.direct_hi - L.direct_lo;
+    T.N = P.N; T.g_direct = P.tally; T.g_diff = P.diff;
+    uint32_t edges_base = BIG ? 0u : smem_base + L.edges; // edge reference: shared byte address, or the edge index
+    uint32_t segw_base = smem_base + L.segw, matid_base = smem_base + L.matid;
+#ifndef NRAPS_NO_PIN
+    asm volatile("" : "+r"(edges_base), "+r"(segw_base), "+r"(matid_base));
+#endif
+    constexpr int kStep = BIG ? 1 : 4;
+    // keep the table addresses in registers: left to itself the compiler rebuilds them from SR_CgaCtaId on every trip
+#ifndef NRAPS_NO_PIN
+    asm volatile("" : "+r"(T.diff_base), "+r"(T.direct_base));
+#endif
+    auto ld_edge = [&](uint32_t ref) -> float { return BIG ? __ldg(P.edges + ref) : lds_f32(ref); };
+    auto ld_mat = [&](int c) -> int { return BIG ? (int)__ldg(P.matid + c) : (int)lds_u8(matid_base + (uint32_t)c); };
+
+    const float *s_inv_sigtr = s_xs, *s_p_abs = s_xs + MG, *s_nusigf = s_xs + 3 * MG, *s_scat = s_xs + 5 * MG;
     // fission_bank mode: sites are banked with weight nu*Sigma_f * inv_sigtr / k_prev; an empty bank => uniform source
     const float inv_k = BANK ? fdiv(1.0f, *P.k_cur) : 1.0f;
-    const uint32_t lo_base = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(s_lo);
-    const uint32_t hi_off = L.tally_hi - L.tally_lo;
-    // edge reference: shared byte address (running pointer of the walk) or, in BIG mode, the edge index
-    const uint32_t edges_base = BIG ? 0u : (uint32_t)__cvta_generic_to_shared(s_edges);
-    constexpr int kStep = BIG ? 1 : 4;
 
     const unsigned lane = tid & 31;
     const uint64_t inc = P.rng_inc;
 
-    // warp-uniform cursor over the chunk of history indices this warp owns, and
-    // the master stream positioned at history w_next
+    // warp-uniform cursor over the chunk of history indices this warp owns
     uint64_t w_next = 0, w_end = 0;
     bool exhausted = false;
 
@@ -66,7 +155,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     bool alive = false, pending = false;
     uint64_t rng = 0, y = 0;
     float x = 0.f, mu = 1.f, ds = 0.f;
-    int cell = 0, g = 0, xsg = 0, mat = 0, run_lo = 0, run_hi = 0, row0 = 0;
+    int cell = 0, g = 0, xsg = 0, mat = 0, row0 = 0;
     uint32_t h_coll = 0, h_cross = 0, h_flight = 0, h_refl = 0, h_bank = 0; // this history
     uint32_t c_hist = 0, c_coll = 0, c_cross = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0, c_bank = 0;
 
@@ -93,21 +182,20 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     y = w_next + rank;
                     // adopt the neutron source_kernel gave birth to (mc_source.cu)
                     const uint4 *rec = P.source + 2 * (y - P.hist_begin);
-                    const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+                    const uint4 r0 = __ldg(rec);
+                    const uint2 r1 = __ldg(reinterpret_cast<const uint2 *>(rec + 1));
                     x = __uint_as_float(r0.x);
                     mu = __uint_as_float(r0.y);
                     cell = (int)(r0.z & 0xffffu);
                     g = (int)(r0.z >> 16);
                     row0 = (int)r0.w; // first tally row of this history's generation (0 unless generations are batched)
                     rng = (uint64_t)r1.x | ((uint64_t)r1.y << 32);
-                    mat = mesh.material(cell);
+                    mat = ld_mat(cell);
                     xsg = g;
                     h_bank = 0;
-                    const uint32_t rb = mesh.run_bounds(cell);
-                    run_lo = (int)(rb & 0xffffu);
-                    run_hi = (int)(rb >> 16);
                     h_coll = h_cross = h_flight = h_refl = 0;
                     alive = true;
+                    pending = false;
                 }
                 const uint32_t want = __popc(need);
                 const uint32_t took = want < avail ? want : avail;
@@ -133,27 +221,26 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 }
             }
             if (!fate) {
-                // ------------ WALK: cell by cell inside one material run.  Single-exit loop with
-                // running shared addresses: ~30 SASS instructions per crossing (profiles/r1c_*).
+                // ------------ WALK: cell by cell inside one segment
                 rc = make_recip(mu);
+                // {first cell | one past the last cell << 16, width bits} of the segment `cell` lies in
+                const uint2 sw = BIG ? __ldg(P.segw + cell) : make_uint2(lds_u32(segw_base + 8u * (uint32_t)cell), lds_u32(segw_base + 8u * (uint32_t)cell + 4u));
                 int fwd = mu >= 0.0f ? 1 : 0;
                 int dir = 2 * fwd - 1;
                 int wall = fwd ? N - 1 : 0;
-                int run_exit = fwd ? run_hi : run_lo - 1;
                 uint32_t e_addr = edges_base + (uint32_t)(kStep * (cell + fwd)); // edge ahead of the neutron
-                uint32_t t_addr = tally_ref<BIG>(lo_base, (row0 + g) * N + cell);         // tally[g][cell]
-                // The hot loop below has two ways out and no wall logic.  The domain-boundary cell in the direction
-                // of travel is handled here, before the loop (src/mc_code.rs:159-170): a lane that reaches it
-                // inside the loop stops there (it is its stop_cell) and comes back through this block next trip.
+                // The loop below has no wall logic.  The domain-boundary cell in the direction of travel is handled
+                // here, before it (src/mc_code.rs:159-170): a lane that reaches that cell inside the loop stops there
+                // and comes back through this block on its next trip.
                 bool in_loop = true;
                 pending = false;
                 if (cell == wall) {
                     end = fadd(x, ds);
-                    const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
+                    const float edge = ld_edge(e_addr);
                     const float t = fsub(x, edge);
                     const bool beyond = fwd ? (end > edge) : (edge > end);
                     if (beyond) {
-                        score<BIG>(t_addr, hi_off, fabsf(fdiv(t, mu)), P.tally);
+                        T.direct(row0 + g, cell, fabsf(fdiv(t, mu)));
                         const float b = fwd ? P.boundr : P.boundl;
                         if (!(b > 0.0f)) {
                             fate = NRAPS_FATE_LEAKED;
@@ -166,73 +253,93 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                             fwd = mu >= 0.0f ? 1 : 0;
                             dir = 2 * fwd - 1;
                             wall = fwd ? N - 1 : 0;
-                            run_exit = fwd ? run_hi : run_lo - 1;
                             e_addr = edges_base + (uint32_t)(kStep * (cell + fwd));
                             if (TRACE) ++h_refl;
                             // N == 1, or albedo <= 0 after the flip: the other wall is this very cell -> next trip
                             if (cell == wall) { in_loop = false; pending = true; }
                         }
-                    } else if (!(fabsf(fsub(end, x)) > fabsf(t))) {
-                        ev = EV_COLLIDE; // collision inside the boundary cell
-                        in_loop = false;
                     } else {
-                        // unreachable for finite positive inv_sigtr (a crossing test that succeeds where the wall
-                        // test failed); keep the reference's order of tests and treat it as a collision at `end`
+                        // collision inside the boundary cell.  (A crossing test that succeeds where the wall test
+                        // failed is unreachable for finite positive inv_sigtr; the reference's order of tests is kept
+                        // and that case too is a collision at `end`.)
                         ev = EV_COLLIDE;
                         in_loop = false;
                     }
                 }
                 if (in_loop) {
-                    // a walk longer than `walk_cap` crossings is suspended (pending) and resumed on the next trip, so
-                    // the lanes that finished early are not kept waiting for the longest flight of the warp; the cap
-                    // and the boundary cell are folded into the loop's one exit compare (`stop_cell`)
-                    int steps = min((run_exit - cell) * dir, (int)P.walk_cap);
-                    const int to_wall = (wall - cell) * dir; // cells until the boundary cell, if it lies in this run
+                    // crossings this trip: to the end of the segment, at most `walk_cap` (a longer walk is suspended --
+                    // pending -- and resumed on the next trip, so that the lanes that finished early do not wait for
+                    // the longest flight of the warp), and not into the boundary cell
+                    const int seg_exit = fwd ? (int)(sw.x >> 16) : (int)(sw.x & 0xffffu) - 1;
+                    int steps = min((seg_exit - cell) * dir, (int)P.walk_cap);
+                    const int to_wall = (wall - cell) * dir;
                     if (to_wall < steps) steps = to_wall;
-                    const int stride = kStep * dir;
-                    const uint32_t e_first = e_addr;
-                    // the loop tests the tally address, which nothing reads afterwards: testing e_addr lets the compiler
-                    // substitute the stop value on that exit and brings the per-crossing moves back
-                    const uint32_t t_stop = t_addr + (uint32_t)(stride * steps);
-                    // The loop carries the two running addresses, ds and the position `xc` only.  x and cell are NOT
-                    // kept up to date inside it: an unrolled loop with an exit per crossing otherwise pays four
-                    // register moves per crossing to hold them in place for those exits (r1o SASS); both are rebuilt
-                    // from the edge address afterwards.
-                    float xc = x;
-                    // one crossing; false = the walk is over (collision, or the stop edge reached)
-                    auto step = [&]() -> bool {
-                        end = fadd(xc, ds);
-                        const float edge = BIG ? __ldg(P.edges + e_addr) : lds_f32(e_addr);
-                        const float t = fsub(xc, edge);
-                        if (!(fabsf(fsub(end, xc)) > fabsf(t))) return false; // collision at `end` (|edge - x| == |x - edge| exactly)
-                        // cross_mesh, src/mc_code.rs:171-181
-                        score<BIG>(t_addr, hi_off, fabsf(fast_div(t, rc)), P.tally);
-                        ds = fadd(ds, t);
-                        xc = edge;
-                        e_addr += stride;
-                        t_addr += stride;
-                        return t_addr != t_stop; // left the material run, reached the boundary cell, or time to regroup
-                    };
-                    while (step() && step() && step() && step()) {} // unrolled by four: one back branch per four crossings
-                    const int moved = (int)(e_addr - e_first) / kStep; // signed cells travelled
-                    if (moved) {
-                        // x after a crossing is the edge just crossed, bit for bit (src/mc_code.rs:72,77)
-                        const uint32_t behind = e_addr - (uint32_t)stride;
-                        x = BIG ? __ldg(P.edges + behind) : lds_f32(behind);
-                        cell += moved;
-                        if (TRACE) h_cross += (uint32_t)(moved * dir);
+                    // the cell the flight starts in: an arbitrary part of it is crossed (src/mc_code.rs:171-181)
+                    end = fadd(x, ds);
+                    const float edge0 = ld_edge(e_addr);
+                    const float t0 = fsub(x, edge0);
+                    if (!(fabsf(fsub(end, x)) > fabsf(t0))) {
+                        ev = EV_COLLIDE; // collision at `end`, before the first edge
+                    } else {
+                        T.direct(row0 + g, cell, fabsf(fast_div(t0, rc)));
+                        ds = fadd(ds, t0);
+                        const int stride = kStep * dir;
+                        const uint32_t e_first = e_addr;
+                        const uint32_t e_stop = e_first + (uint32_t)(stride * steps); // e_addr once `steps` edges are crossed
+                        float xc = edge0;
+                        e_addr += (uint32_t)stride;
+                        if (e_addr != e_stop) {
+                            // Cells crossed completely: x - edge is -+w for every one of them, w the segment's width,
+                            // so the loop carries ds, the position and the edge address only.  One step = the
+                            // reference's test `|end - x| > |edge - x|` and `ds += x - edge` in its operation order.
+                            const float w = __uint_as_float(sw.y);
+                            const float tn = fwd ? -w : w;
+                            auto step = [&]() -> bool {
+                                end = fadd(xc, ds);
+                                if (!(fabsf(fsub(end, xc)) > w)) return false; // collision at `end` inside this cell
+                                ds = fadd(ds, tn);
+                                xc = ld_edge(e_addr);
+                                e_addr += (uint32_t)stride;
+                                return e_addr != e_stop;
+                            };
+                            while (step() && step() && step() && step()) {} // one back branch per four crossings
+                            const int n_full = (int)((uint32_t)((int)(e_addr - e_first) * dir) / (uint32_t)kStep) - 1; // cells crossed completely
+                            if (n_full > 0) // [cell+1, cell+n_full] going right, [cell-n_full, cell-1] going left
+                                T.range(row0 + g, fwd ? cell + 1 : cell - n_full, n_full, fabsf(fast_div(tn, rc)));
+                        }
+                        const int n_cross = (int)((uint32_t)((int)(e_addr - e_first) * dir) / (uint32_t)kStep);
+                        if (e_addr != e_stop) ev = EV_COLLIDE;
+                        x = xc; // x after a crossing is the edge just crossed (src/mc_code.rs:72,77)
+                        cell += n_cross * dir;
+                        if (TRACE) h_cross += (uint32_t)n_cross;
+                        if (ev == EV_NONE) {
+                            if (cell == seg_exit) ev = EV_SEGEXIT;
+                            else pending = true;
+                        }
                     }
-                    if (moved != dir * steps) ev = EV_COLLIDE;
-                    else if (cell == run_exit) ev = EV_MATCHANGE;
-                    else pending = true;
+                }
+            }
+            if (ev == EV_SEGEXIT) { // ------------ end of the segment
+                ev = EV_NONE;
+                if ((unsigned)cell >= (unsigned)N) {
+                    fate = NRAPS_FATE_TRUNCATED; // unreachable for validated input
+                    cell = cell < 0 ? 0 : N - 1;
+                } else {
+                    const int m2 = ld_mat(cell);
+                    if (m2 != mat) { // material change: the flight ends here, alive (src/mc_code.rs:175-181)
+                        mat = m2;
+                        xsg = g;
+                    } else {
+                        pending = true; // next segment of the same material run (the cell width changed): the flight goes on
+                    }
                 }
             }
         }
         __syncwarp();
 
-        // ---------------- COLLIDE / material change
+        // ---------------- COLLIDE
         if (ev == EV_COLLIDE) {
-            score<BIG>(tally_ref<BIG>(lo_base, (row0 + g) * N + cell), hi_off, fabsf(fast_div(fsub(x, end), rc)), P.tally);
+            T.direct(row0 + g, cell, fabsf(fast_div(fsub(x, end), rc)));
             ++h_coll;
             const int xs = mat + M * xsg; // stale group index, src/mc_code.rs:147
             const float xi_int = pcg32_unit(rng, inc);
@@ -257,17 +364,6 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 g = g_new;
                 mu = mu_new;
                 if (!P.stale_xs) xsg = g;
-            }
-        } else if (ev == EV_MATCHANGE) {
-            if ((unsigned)cell >= (unsigned)N) {
-                fate = NRAPS_FATE_TRUNCATED; // unreachable for validated input
-                cell = cell < 0 ? 0 : N - 1;
-            } else {
-                mat = mesh.material(cell);
-                xsg = g;
-                const uint32_t rb = mesh.run_bounds(cell);
-                run_lo = (int)(rb & 0xffffu);
-                run_hi = (int)(rb >> 16);
             }
         }
 
@@ -302,19 +398,77 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
         }
     }
 
+    // ---------------- block epilogue: shared bins -> global 64-bit bins, lane counters -> global counters
+    __syncthreads();
+    const int rows = (int)P.rows;
+    if (!BIG) {
+        const uint32_t *d_lo = reinterpret_cast<const uint32_t *>(smem_raw + L.diff_lo), *d_hi = reinterpret_cast<const uint32_t *>(smem_raw + L.diff_hi);
+        const uint32_t *t_lo = reinterpret_cast<const uint32_t *>(smem_raw + L.direct_lo), *t_hi = reinterpret_cast<const uint32_t *>(smem_raw + L.direct_hi);
+        for (int i = tid; i < rows * N; i += nthr) {
+            const int r = i / N, c = i - r * N, j = r * (N + 1) + c; // the entry one past the last cell of a row feeds no prefix
+            const unsigned long long d = ((unsigned long long)d_hi[j] << 32) + d_lo[j];
+            if (d) atomicAdd(&P.diff[i], d);
+            if (MODE == SURF_SPLIT) {
+                const unsigned long long v = ((unsigned long long)t_hi[i] << 32) + t_lo[i];
+                if (v) atomicAdd(&P.tally[i], v);
+            }
+        }
+    }
+    unsigned long long *ct = P.tally + (size_t)rows * N;
     const uint32_t vals[8] = {c_hist, c_coll, c_cross, c_flight, c_refl, c_leak, c_trunc, c_bank};
-    flush_block(S, P, vals);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        unsigned long long v = vals[c];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if ((tid & 31) == 0 && v) atomicAdd(&ct[c], v);
+    }
 }
 
-template <int TG, bool BIG>
-cudaError_t launch_gb(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
+// tally[r][i] += sum_{j <= i} diff[r][j]: one block per tally row, warp-shuffle scan, 64-bit wrapping sums
+__global__ void __launch_bounds__(1024) tally_prefix_kernel(const unsigned long long *diff, unsigned long long *tally, const uint32_t N)
+{
+    __shared__ unsigned long long warp_tot[32];
+    const unsigned long long *d = diff + (size_t)blockIdx.x * N;
+    unsigned long long *t = tally + (size_t)blockIdx.x * N;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long carry = 0ull;
+    for (uint32_t base = 0; base < N; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned long long v = i < N ? d[i] : 0ull;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(kFull, v, o);
+            if (lane >= (unsigned)o) v += up;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(kFull, w, o);
+                if (lane >= (unsigned)o) w += up;
+            }
+            warp_tot[lane] = w; // inclusive totals of warps 0..lane
+        }
+        __syncthreads();
+        const unsigned long long incl = carry + v + (warp ? warp_tot[warp - 1] : 0ull);
+        if (i < N && incl) t[i] += incl;
+        carry += warp_tot[31];
+        __syncthreads();
+    }
+}
+
+template <int TG, int MODE>
+cudaError_t launch_gm(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
 {
     if (bank) {
-        if (trace) transport_kernel<TG, true, true, BIG><<<grid, block, smem, s>>>(p);
-        else transport_kernel<TG, false, true, BIG><<<grid, block, smem, s>>>(p);
+        if (trace) transport_kernel<TG, true, true, MODE><<<grid, block, smem, s>>>(p);
+        else transport_kernel<TG, false, true, MODE><<<grid, block, smem, s>>>(p);
     } else {
-        if (trace) transport_kernel<TG, true, false, BIG><<<grid, block, smem, s>>>(p);
-        else transport_kernel<TG, false, false, BIG><<<grid, block, smem, s>>>(p);
+        if (trace) transport_kernel<TG, true, false, MODE><<<grid, block, smem, s>>>(p);
+        else transport_kernel<TG, false, false, MODE><<<grid, block, smem, s>>>(p);
     }
     return cudaGetLastError();
 }
@@ -322,27 +476,39 @@ cudaError_t launch_gb(const TransportParams &p, bool trace, bool bank, dim3 grid
 template <int TG>
 cudaError_t launch_g(const TransportParams &p, bool trace, bool bank, dim3 grid, dim3 block, uint32_t smem, cudaStream_t s)
 {
-    return p.big ? launch_gb<TG, true>(p, trace, bank, grid, block, smem, s) : launch_gb<TG, false>(p, trace, bank, grid, block, smem, s);
+    switch (p.surf_mode) {
+    case SURF_SPLIT: return launch_gm<TG, SURF_SPLIT>(p, trace, bank, grid, block, smem, s);
+    case SURF_UNIFIED: return launch_gm<TG, SURF_UNIFIED>(p, trace, bank, grid, block, smem, s);
+    default: return launch_gm<TG, SURF_GLOBAL>(p, trace, bank, grid, block, smem, s);
+    }
 }
 
-template <int TG> cudaError_t set_smem(uint32_t bytes, bool trace, bool bank)
+template <typename F> cudaError_t set_smem_one(F *kernel, uint32_t bytes)
 {
-    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (bank) return trace ? cudaFuncSetAttribute(transport_kernel<TG, true, true, false>, attr, (int)bytes)
-                           : cudaFuncSetAttribute(transport_kernel<TG, false, true, false>, attr, (int)bytes);
-    return trace ? cudaFuncSetAttribute(transport_kernel<TG, true, false, false>, attr, (int)bytes)
-                 : cudaFuncSetAttribute(transport_kernel<TG, false, false, false>, attr, (int)bytes);
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <int TG, int MODE> cudaError_t set_smem(uint32_t bytes, bool trace, bool bank)
+{
+    if (bank) return trace ? set_smem_one(transport_kernel<TG, true, true, MODE>, bytes) : set_smem_one(transport_kernel<TG, false, true, MODE>, bytes);
+    return trace ? set_smem_one(transport_kernel<TG, true, false, MODE>, bytes) : set_smem_one(transport_kernel<TG, false, false, MODE>, bytes);
+}
+
+template <int TG> cudaError_t set_smem_g(uint32_t bytes, uint32_t mode, bool trace, bool bank)
+{
+    return mode == SURF_SPLIT ? set_smem<TG, SURF_SPLIT>(bytes, trace, bank) : set_smem<TG, SURF_UNIFIED>(bytes, trace, bank);
 }
 
 } // namespace
 
-// opt in to > 48 KB dynamic shared memory for the one instantiation about to be launched (BIG mode needs < 48 KB)
-cudaError_t prepare_transport(uint32_t smem_bytes, uint32_t G, bool trace, bool bank)
+// opt in to > 48 KB dynamic shared memory for the one instantiation about to be launched (SURF_GLOBAL needs < 48 KB)
+cudaError_t prepare_transport(uint32_t smem_bytes, uint32_t G, uint32_t surf_mode, bool trace, bool bank)
 {
+    if (surf_mode == SURF_GLOBAL) return cudaSuccess;
     switch (G) {
-    case 2: return set_smem<2>(smem_bytes, trace, bank);
-    case 4: return set_smem<4>(smem_bytes, trace, bank);
-    default: return set_smem<0>(smem_bytes, trace, bank);
+    case 2: return set_smem_g<2>(smem_bytes, surf_mode, trace, bank);
+    case 4: return set_smem_g<4>(smem_bytes, surf_mode, trace, bank);
+    default: return set_smem_g<0>(smem_bytes, surf_mode, trace, bank);
     }
 }
 
@@ -355,31 +521,41 @@ cudaError_t launch_transport(const TransportParams &p, bool trace, bool bank, di
     }
 }
 
+cudaError_t launch_tally_prefix(const unsigned long long *diff, unsigned long long *tally, uint32_t rows, uint32_t N, cudaStream_t s)
+{
+    if (!rows || !N) return cudaSuccess;
+    tally_prefix_kernel<<<rows, 1024, 0, s>>>(diff, tally, N);
+    return cudaGetLastError();
+}
 
 namespace {
-template <int TG, bool BIG> int occ_gb(bool trace, bool bank, int block, uint32_t smem)
+template <typename F> int occ_one(F *kernel, int block, uint32_t smem)
 {
     int n = 0;
-    cudaError_t e;
-    if (bank) e = trace ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, true, true, BIG>, block, smem)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, false, true, BIG>, block, smem);
-    else e = trace ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, true, false, BIG>, block, smem)
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, transport_kernel<TG, false, false, BIG>, block, smem);
-    return e == cudaSuccess ? n : 0;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block, smem) == cudaSuccess ? n : 0;
 }
-template <int TG> int occ_g(bool big, bool trace, bool bank, int block, uint32_t smem)
+template <int TG, int MODE> int occ_gm(bool trace, bool bank, int block, uint32_t smem)
 {
-    return big ? occ_gb<TG, true>(trace, bank, block, smem) : occ_gb<TG, false>(trace, bank, block, smem);
+    if (bank) return trace ? occ_one(transport_kernel<TG, true, true, MODE>, block, smem) : occ_one(transport_kernel<TG, false, true, MODE>, block, smem);
+    return trace ? occ_one(transport_kernel<TG, true, false, MODE>, block, smem) : occ_one(transport_kernel<TG, false, false, MODE>, block, smem);
+}
+template <int TG> int occ_g(uint32_t mode, bool trace, bool bank, int block, uint32_t smem)
+{
+    switch (mode) {
+    case SURF_SPLIT: return occ_gm<TG, SURF_SPLIT>(trace, bank, block, smem);
+    case SURF_UNIFIED: return occ_gm<TG, SURF_UNIFIED>(trace, bank, block, smem);
+    default: return occ_gm<TG, SURF_GLOBAL>(trace, bank, block, smem);
+    }
 }
 } // namespace
 
 // resident blocks per SM of the instantiation that would be launched (registers and shared memory both count)
-int occupancy_transport(uint32_t G, bool big, bool trace, bool bank, int block, uint32_t smem)
+int occupancy_transport(uint32_t G, uint32_t surf_mode, bool trace, bool bank, int block, uint32_t smem)
 {
     switch (G) {
-    case 2: return occ_g<2>(big, trace, bank, block, smem);
-    case 4: return occ_g<4>(big, trace, bank, block, smem);
-    default: return occ_g<0>(big, trace, bank, block, smem);
+    case 2: return occ_g<2>(surf_mode, trace, bank, block, smem);
+    case 4: return occ_g<4>(surf_mode, trace, bank, block, smem);
+    default: return occ_g<0>(surf_mode, trace, bank, block, smem);
     }
 }
 

@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """Throughput of the Monte Carlo transport path: neutron histories/s per generation.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config4|config5]
 
-A "step" is one generation: source -> all events -> tally flush -> (all-reduce) -> k.
-Workload at N = 1 is BASELINE config 3 (TestCaseC cross sections and geometry,
-G = 4, N = 408 cells, 10^7 histories per generation, uniform-fuel source, PCG32
-seed 42 / stream 54 / stride 152917).  For N > 1 (launched by torchrun, one rank
-per GPU) every GPU keeps 10^7 histories per generation (weak scaling); the only
-collective is the per-generation int64 all-reduce of the tally buffer.
+A "step" is one generation: births -> all flights and collisions -> tally -> (all-reduce) -> k.
+The headline workload is BASELINE config 3 (TestCaseC cross sections and geometry, G = 4, N = 408 cells, 10^7
+histories per generation and GPU, uniform-fuel source, PCG32 seed 42 / stream 54 / stride 152917), surface tracking
+(the reference's own algorithm, bit-comparable with the CPU arm).  For N > 1 (launched by torchrun, one rank per GPU)
+every GPU keeps 10^7 histories per generation (weak scaling); the only collective is the per-generation int64
+all-reduce of the tally buffer, issued on a side stream while the next generation already transports.
 
-Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of
-the reference algorithm (oracle/, all host threads) on bounded samples of the
-same workload; it is the only other place this file touches oracle/ besides the
-cpu_baseline leg.
+Besides the headline the JSON line carries, under "configs", the two multi-GPU configurations BASELINE names:
+config 4 (fine mesh N = 4080, 10^8 histories per generation in total: strong scaling) and config 5 (1.25e8 histories per
+GPU and generation, fission-bank source: weak scaling; the bank stays where it was compacted and is read over NVLink),
+each with a per-phase split, and "multi_gpu_bit_identical": the distributed result against a single-GPU run.
+
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference algorithm (oracle/, all
+host threads) on the same configuration; it is the only other place this file touches oracle/ besides the
+cpu_baseline leg, and it loads nothing of the product.
 """
 from __future__ import annotations
 
@@ -22,6 +26,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,7 +37,7 @@ if ROOT not in sys.path:
 METRIC = "neutron histories/s per generation"
 UNIT = "histories/s"
 RECORD_BYTES = 24  # SURVEY 8d bank record: x, mu, cell, packed groups/flags, rng state
-
+DECK_C = os.path.join(ROOT, "tests", "golden", "decks", "case_c.txt")
 
 _json_fd = None
 
@@ -57,25 +62,45 @@ def emit(line: dict):
         os.write(_json_fd, data)
 
 
-def workload(name: str):
+WORKLOADS = {
+    # name: (fine mesh?, histories per generation as a function of the world size, scaling, source mode, description)
+    "config3": (False, lambda w: 10_000_000 * w, "weak", "uniform_fuel",
+                "config3: TestCaseC XS+geometry (G=4, M=4, N=408 cells), 1e7 histories/generation/GPU, uniform_fuel source, "
+                "PCG32 seed 42/stream 54/stride 152917"),
+    "config4": (True, lambda w: 100_000_000, "strong", "uniform_fuel",
+                "config4: TestCaseC XS, fine mesh MPFR=80/MPWR=40 (G=4, N=4080 cells), 1e8 histories/generation total (strong scaling)"),
+    "config5": (False, lambda w: 125_000_000 * w, "weak", "fission_bank",
+                "config5: TestCaseC XS+geometry (G=4, N=408), 1.25e8 histories/generation/GPU, fission_bank source "
+                "(power iteration; every rank's bank read in place over NVLink) (weak scaling)"),
+}
+
+
+def workload_config(name: str, world: int, tracking: str = "surface") -> dict:
+    """The `config` object of the JSON line: the same for our arm and the reference arm."""
+    fine, hist, scaling, source, desc = WORKLOADS[name]
+    return {"workload": desc, "histories_per_generation": hist(world), "source_mode": source, "tracking_mode": tracking}
+
+
+def product_problem(name: str):
+    """Solver inputs through the product's own host side (nraps_b200.process_input / mesh_gen)."""
     from tests.util import load_case
 
-    if name == "config3":
-        args = load_case("c")
-        desc = "config3: TestCaseC XS+geometry (G=4, M=4, N=408 cells), 1e7 histories/generation/GPU, uniform_fuel source, PCG32 seed 42/stream 54/stride 152917"
-        per_gpu = 10_000_000
-    elif name == "config4":
-        args = load_case("c", mpfr=80, mpwr=40)
-        desc = "config4: TestCaseC XS, fine mesh MPFR=80/MPWR=40 (G=4, N=4080 cells), 1e8 histories/generation total (strong scaling)"
-        per_gpu = 100_000_000
-    elif name == "config5":
-        args = load_case("c")
-        desc = ("config5: TestCaseC XS+geometry (G=4, N=408), 1.25e8 histories/generation/GPU, fission_bank source "
-                "(power iteration), NCCL all-gather of the bank each generation (weak scaling)")
-        per_gpu = 125_000_000
-    else:
-        raise SystemExit(f"unknown workload {name}")
-    return args, desc, per_gpu
+    return load_case("c", mpfr=80, mpwr=40) if WORKLOADS[name][0] else load_case("c")
+
+
+def oracle_problem(name: str):
+    """Solver inputs through the oracle's numpy host side only (the reference arm maps no product library)."""
+    import numpy as np
+
+    from oracle import host_oracle as ho
+
+    deck = ho.process_input(DECK_C)
+    if WORKLOADS[name][0]:
+        deck.mpfr, deck.mpwr = 80, 40
+        deck.dx_fuel = np.float32(deck.roddia / np.float32(80))
+        deck.dx_water = np.float32(deck.rodpitch / np.float32(40))
+    mesh = ho.mesh_gen(deck.matid, deck.mpfr, deck.mpwr, deck.numass, deck.dx_fuel, deck.dx_water)
+    return deck, mesh
 
 
 class ClockSampler:
@@ -140,53 +165,55 @@ def ncu_facts(kernel: str) -> dict:
         return {}
 
 
-def measured_traffic(kernel: str):
-    return ncu_facts(kernel).get("bytes")
-
-
-def cpu_sample(args, histories: int, generations: int, threads: int, faithful: bool = True):
-    """Oracle in the reference's configuration: hardware_concurrency-1 workers, static ranges,
-    per-worker f32 tallies, ordered reduction (src/mc_code.rs:302-338)."""
+def cpu_run(problem, histories: int, generations: int, threads: int):
+    """The oracle in the reference's configuration: hardware_concurrency-1 workers, static ranges, per-worker f32
+    tallies, ordered reduction (src/mc_code.rs:302-338)."""
     from oracle import oracle as orc
-    from tests.util import oracle_inputs
 
-    deck, mesh = oracle_inputs(*args)
-    r = orc.monte_carlo(deck, mesh, generations=generations, histories=histories, skip=0, threads=threads,
-                        tally_mode="f32_per_worker" if faithful else "fixed64")
-    return r
+    deck, mesh = problem
+    return orc.monte_carlo(deck, mesh, generations=generations, histories=histories, skip=0, threads=threads,
+                           tally_mode="f32_per_worker")
+
+
+def cpu_sample_text(steps: int, sample: int, full: int, threads: int, cores: int) -> str:
+    part = "the full generation" if sample == full else f"a bounded sample of the {full:.3g}-history generation"
+    return (f"{steps} generations x {sample} histories ({part}), C restatement of src/mc_code.rs (no Rust toolchain in "
+            f"this image), threaded like the reference: {threads} workers of {cores} cores, per-worker f32 tallies")
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     reserve_stdout()
-    args, desc, per_gpu = workload(a.workload)
+    problem = oracle_problem(a.workload)
+    full = WORKLOADS[a.workload][1](max(world, a.gpus))
     cores = os.cpu_count() or 2
     threads = max(1, cores - 1)
-    sample = min(per_gpu, 1_000_000)
     t0 = time.perf_counter()
-    cpu_sample(args, max(1000, sample // 20), 1, threads)  # page-in + first estimate
-    est = (time.perf_counter() - t0) * 20
-    while sample > 20_000 and est * (a.steps + a.warmup) > 200.0:
+    cpu_run(problem, 50_000, 1, threads)  # page-in + first estimate
+    per_history = (time.perf_counter() - t0) / 50_000
+    # every step is the full generation when K + W of them fit ~4 minutes (they do at N = 1: ~3 s each on 15 threads),
+    # else a bounded sample of it -- the CPU rate does not depend on the sample size
+    sample = full
+    while sample > 100_000 and per_history * sample * (a.steps + a.warmup) > 240.0:
         sample //= 2
-        est /= 2
     for _ in range(a.warmup):
-        cpu_sample(args, sample, 1, threads)
+        cpu_run(problem, sample, 1, threads)
     t0 = time.perf_counter()
-    r = cpu_sample(args, sample, a.steps, threads)
+    r = cpu_run(problem, sample, a.steps, threads)
     wall = time.perf_counter() - t0
     value = sample * a.steps / wall
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": WORKLOADS[a.workload][2],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "histories_per_step_sampled": sample},
+        "config": workload_config(a.workload, max(world, a.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{a.steps} generations x {sample} histories (bounded sample of the 1e7/generation workload), "
-                                   f"C restatement of src/mc_code.rs (no Rust toolchain in this image), {threads} worker threads of {cores} cores"},
+                         "sample": cpu_sample_text(a.steps, sample, full, threads, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "k_mean": float(r.k.mean()),
+        "histories_per_step": sample, "k_mean": float(r.k.mean()),
     }
     emit(line)
 
@@ -197,7 +224,7 @@ def run_ours(a):
     import torch.distributed as dist
 
     import nraps_b200 as nb
-    from nraps_b200.dist import shard_range
+    from nraps_b200.dist import OverlappedReducer, setup_bank_peers, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,123 +236,212 @@ def run_ours(a):
         raise SystemExit(subprocess.call(cmd))
     reserve_stdout()
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    args, desc, per_gpu = workload(a.workload)
-    v, xs, dx, mesh, fuel = args
-    H = a.histories if a.histories else (per_gpu if a.workload == "config4" else per_gpu * world)
-    scaling = "strong" if a.workload == "config4" else "weak"
-    source_mode = "fission_bank" if a.workload == "config5" else "uniform_fuel"
     K, W = a.steps, a.warmup
-    gens_total = W + K
-
-    base_opts = dict(device=local, threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, source_mode=source_mode,
-                     spawn_batch=a.spawn_batch, walk_cap=a.walk_cap, slots_per_thread=a.slots_per_thread)
-    opts = dict(base_opts, tracking_mode=a.tracking, kernel_variant=a.variant)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
-    begin, count = shard_range(H, rank, world)
-    from nraps_b200.dist import make_bank_callback
+    tune = dict(threads_per_block=a.threads, blocks_per_sm=a.blocks_per_sm, chunk=a.chunk, spawn_batch=a.spawn_batch, walk_cap=a.walk_cap)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    main = torch.cuda.current_stream()
 
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_run(run_opts, sample_clocks):
-        """W warm-up + K timed generations with everything resident on the device."""
-        ctx = nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens_total, histories=H, skip=1, **run_opts)
-        tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{local}")
-        ctx.use_tally_tensor(tally)
-        bank = make_bank_callback(ctx, world, local, stream) if source_mode == "fission_bank" else None
+    def max_over_ranks(*vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
-        def step(gen, ev=None):
-            flush.zero_()
-            if ev:
-                ev[0].record()
-            ctx.transport(gen, begin, count, stream)
-            if ev:
-                ev[1].record()
-            if world > 1:
-                dist.all_reduce(tally)
-            ctx.finalize_generation(gen, stream)
-            if bank is not None:
-                bank(gen)
+    def timed_run(name, tracking, k_steps, w_steps, *, variant="fused", sample_clocks=False, phases=False):
+        """w_steps warm-up + k_steps timed generations of workload `name`, everything resident on the device.
 
-        for g in range(W):
-            step(g)
+        Uniform source: transport on the main stream, all-reduce + finalize of the same generation on a side stream
+        (OverlappedReducer).  Fission bank: transport -> compact -> all-reduce -> finalize -> advance, in order."""
+        fine, hist, scaling, source, desc = WORKLOADS[name]
+        v, xs, dx, mesh, fuel = product_problem(name)
+        H = a.histories if (a.histories and name == a.workload) else hist(world)
+        begin, count = shard_range(H, rank, world)
+        bank = source == "fission_bank"
+        ctx = nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=w_steps + k_steps, histories=H, skip=1, device=local,
+                                   source_mode=source, tracking_mode=tracking, kernel_variant=variant, profile_phases=phases, **tune)
+        kernel_ev, coll_ev = [], []
+        if bank:
+            setup_bank_peers(ctx, rank, world, max(shard_range(H, r, world)[1] for r in range(world)))
+            tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=dev)
+            ctx.use_tally_tensor(tally)
+
+            def step(gen, timed):
+                flush.zero_()
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+                if timed:
+                    e[0].record()
+                ctx.transport(gen, begin, count, main.cuda_stream)
+                if timed:
+                    e[1].record()
+                ctx.bank_compact(gen, main.cuda_stream)
+                if timed:
+                    e[2].record()
+                if world > 1:
+                    dist.all_reduce(tally)
+                if timed:
+                    e[3].record()
+                    kernel_ev.append((e[0], e[1]))
+                    coll_ev.append((e[2], e[3]))
+                ctx.finalize_generation(gen, main.cuda_stream)
+                ctx.bank_advance(gen, main.cuda_stream)
+
+            drain = lambda: None  # noqa: E731
+        else:
+            red = OverlappedReducer(ctx, world, local, main)
+
+            def step(gen, timed):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timed else None
+                red.step(gen, begin, count, before_transport=lambda: (flush.zero_(), timed and e[0].record()),
+                         after_transport=lambda: timed and e[1].record())
+                if timed:
+                    kernel_ev.append((e[0], e[1]))
+
+            drain = red.drain
+
+        for g in range(w_steps):
+            step(g, False)
+        drain()
         fence()
+        phase0 = ctx.phase_ms() if phases else None
         sampler = ClockSampler(local)
         if rank == 0 and sample_clocks:
             sampler.start()
-        k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_begin.record()
-        for i in range(K):
-            step(W + i, k_events[i])
+        for i in range(k_steps):
+            step(w_steps + i, True)
+        drain()
         t_end.record()
         fence()
         clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
-        out = dict(ms_total=t_begin.elapsed_time(t_end), ms_kernel=sum(e0.elapsed_time(e1) for e0, e1 in k_events) / K,
-                   res=ctx.fetch(stream), info=ctx.launch_info(), clocks=clocks, has_bank=bank is not None)
-        ctx.close()
+        ms_total = t_begin.elapsed_time(t_end)
+        ms_kernel = sum(e0.elapsed_time(e1) for e0, e1 in kernel_ev) / k_steps
+        ms_coll = sum(e0.elapsed_time(e1) for e0, e1 in coll_ev) / k_steps if coll_ev else 0.0
+        out = dict(H=H, count=count, res=ctx.fetch(main.cuda_stream), info=ctx.launch_info(), clocks=clocks, bank=bank,
+                   scaling=scaling, desc=desc)
+        if phases:
+            p1 = ctx.phase_ms()
+            out["phase_ms"] = {k: (p1[k] - phase0[k]) / k_steps for k in p1}
         if world > 1:
-            t = torch.tensor([out["ms_total"], out["ms_kernel"]], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out["ms_total"], out["ms_kernel"] = (float(x) for x in t.tolist())
+            dist.barrier()  # fission bank: peers may still hold mappings of this rank's bank buffers
+        ctx.close()
+        out["ms_total"], out["ms_kernel"], out["ms_coll"] = max_over_ranks(ms_total, ms_kernel, ms_coll)
         return out
 
-    main_run = device_run(opts, True)
-    ms_total, ms_kernel, res, info, clocks = (main_run[k] for k in ("ms_total", "ms_kernel", "res", "info", "clocks"))
-    has_bank = main_run["has_bank"]
-    coll_per_hist = res.counters["collisions"] / max(1, res.counters["histories"])
-    # the other tracking mode on the same workload, reported beside the headline (not instead of it)
-    other = "woodcock" if a.tracking == "surface" else "surface"
-    other_run = None if a.no_variants else device_run(dict(base_opts, tracking_mode=other), False)
+    def config_entry(name, tracking, k_steps, w_steps):
+        """One entry of "configs": throughput of the whole job and where a generation's time goes (max over ranks)."""
+        r = timed_run(name, tracking, k_steps, w_steps, phases=True)
+        ph = r["phase_ms"]
+        names = list(ph)
+        vals = max_over_ranks(*[ph[n] for n in names])
+        ph = dict(zip(names, vals))
+        ms_gen = r["ms_total"] / k_steps
+        phases = {"source": ph["source"], "transport": ph["transport"], "tally_prefix": ph["prefix"], "bank_compaction": ph["compact"],
+                  "all_reduce" + ("" if r["bank"] else " (side stream, overlapped)"): r["ms_coll"] if r["bank"] else None,
+                  "finalize": ph["finalize"]}
+        accounted = sum(v for v in phases.values() if v)
+        phases["other (L2 flush memset, launch gaps, bank bookkeeping)"] = max(0.0, ms_gen - accounted) if r["bank"] else None
+        timed = {k: v for k, v in phases.items() if v is not None}
+        return {"value": r["H"] * k_steps / (r["ms_total"] * 1e-3), "unit": UNIT, "ms_per_generation": ms_gen, "scaling": r["scaling"],
+                "histories_per_generation": r["H"], "histories_per_gpu": r["count"], "generations_timed": k_steps,
+                "warmup": w_steps, "tracking_mode": tracking, "workload": r["desc"], "k_last": float(r["res"].k[-1]),
+                "phases_ms_per_generation": phases, "slowest_phase": max(timed, key=timed.get), "launch": r["info"],
+                "collisions_per_history": r["res"].counters["collisions"] / max(1, r["res"].counters["histories"])}
 
-    # end to end through the public call: host arrays in, SolutionResults out (create + H2D + K generations + D2H)
+    # ---- the headline and the other tracking mode on the same workload
+    head = timed_run(a.workload, a.tracking, K, W, variant=a.variant, sample_clocks=True)
+    res, info, H, count = head["res"], head["info"], head["H"], head["count"]
+    coll_per_hist = res.counters["collisions"] / max(1, res.counters["histories"])
+    other = "woodcock" if a.tracking == "surface" else "surface"
+    other_run = None if a.no_variants else timed_run(a.workload, other, K, W)
+
+    # ---- end to end through the public call: host arrays in, SolutionResults out (create + H2D + K generations + D2H)
+    v, xs, dx, mesh, fuel = product_problem(a.workload)
+    e2e_opts = dict(tune, device=local, source_mode=WORKLOADS[a.workload][3], tracking_mode=a.tracking, kernel_variant=a.variant)
     fence()
     t0 = time.perf_counter()
     if world > 1:
-        e2e_res = nb.monte_carlo_distributed(v, xs, dx, mesh, fuel, 1.0, generations=K, histories=H, skip=1, **opts)
+        e2e_res = nb.monte_carlo_distributed(v, xs, dx, mesh, fuel, 1.0, generations=K, histories=H, skip=1, **e2e_opts)
     else:
-        e2e_res = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=K, histories=H, skip=1, **opts)
+        e2e_res = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=K, histories=H, skip=1, **e2e_opts)
     fence()
-    e2e_s = time.perf_counter() - t0
+    (e2e_s,) = max_over_ranks(time.perf_counter() - t0)
 
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    # ---- BASELINE configs 4 and 5, and the distributed result against one GPU
+    configs = {}
+    if not a.no_configs:
+        kc, wc = max(2, min(4, K)), 2
+        configs["config4_strong"] = config_entry("config4", "surface", kc, wc)
+        configs["config4_strong_woodcock"] = config_entry("config4", "woodcock", kc, wc)
+        configs["config5_weak"] = config_entry("config5", "surface", kc, wc)
+        configs["config5_weak_woodcock"] = config_entry("config5", "woodcock", kc, wc)
+    identical = None
+    if not a.no_configs:
+        vs, xss, dxs, meshs, fuels = product_problem("config3")
+        identical = {}
+        for mode in ("uniform_fuel", "fission_bank"):
+            kw = dict(generations=4, histories=50_001, skip=1, source_mode=mode)
+            many = nb.monte_carlo_distributed(vs, xss, dxs, meshs, fuels, 1.0, device=local, **kw) if world > 1 else None
+            if rank == 0:
+                one = nb.monte_carlo(vs, xss, dxs, meshs, fuels, 1.0, device=local, **kw)
+                if world == 1:  # the generation-level route (what the multi-GPU launcher drives) against the batched call
+                    with nb.MonteCarloContext(vs, xss, dxs, meshs, fuels, 1.0, device=local, **kw) as c1:
+                        for g in range(4):
+                            c1.transport(g)
+                            if mode == "fission_bank":
+                                c1.bank_compact(g)
+                            c1.finalize_generation(g)
+                            if mode == "fission_bank":
+                                c1.bank_advance(g)
+                        many = c1.fetch()
+                identical[mode] = bool(np.array_equal(many.k.view(np.uint32), one.k.view(np.uint32))
+                                       and np.array_equal(many.flux.view(np.uint32), one.flux.view(np.uint32))
+                                       and np.array_equal(many.bank_sizes, one.bank_sizes))
+        fence()
+
     if rank == 0:
         G, M, N, NF = v.energygroups, v.mattypes, len(mesh), len(fuel)
         h2d = 4 * (8 * M * G + M * G * G + 3 * N) + N + 8 * NF  # tables the call uploads, once per run
         d2h = 4 * (G * N + N + K) + 64                           # flux, fission source, k, counters
         peak, peak_src = peaks()
         b_hist = RECORD_BYTES + 2 * RECORD_BYTES * coll_per_hist
-        if has_bank:
+        if head["bank"]:
             b_hist += 12 + 12 * res.counters["banked"] / max(1, res.counters["histories"])  # source read + bank write, SURVEY 8d
-        hist_per_launch = count
-        achieved = b_hist * hist_per_launch / (ms_kernel * 1e-3) / 1e9
+        ms_kernel, ms_total = head["ms_kernel"], head["ms_total"]
+        achieved = b_hist * count / (ms_kernel * 1e-3) / 1e9
+        kname = "woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel"
+        facts = ncu_facts(kname)
         line = {
             "metric": METRIC, "value": H * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "histories_per_generation": H, "histories_per_gpu": count, "generations_timed": K,
-                       "source_mode": source_mode, "tracking_mode": a.tracking, "kernel_variant": a.variant, "parallelism": f"history-sharded x{world}, int64 tally all-reduce per generation",
-                       "launch": info, "l2": "256 MiB device memset between steps inside the timed region (kernel inputs are ~12 KB of tables)"},
-            "clocks": clocks,
+            "config": workload_config(a.workload, world, a.tracking),
+            "details": {"histories_per_gpu": count, "generations_timed": K, "kernel_variant": a.variant,
+                        "parallelism": f"history-sharded x{world}; int64 tally all-reduce per generation on a side stream, overlapped with the next generation",
+                        "launch": info, "l2": "256 MiB device memset between steps inside the timed region (kernel inputs are ~12 KB of tables)"},
+            "clocks": head["clocks"],
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "wall_s": e2e_s, "device_s": float(getattr(e2e_res, "seconds_device", 0.0)),
                     "note": "one monte_carlo() call: context create + table upload + K generations + result download; bytes are per run / K"},
-            "gpu_launches": (3 + (5 if has_bank else 0)) * K,  # source + transport + finalize (+ bank compaction / entropy)
+            # births + transport + tally prefix sum + finalize (+ bank: 3 compaction kernels, histogram, entropy)
+            "gpu_launches": ((4 if a.tracking == "surface" else 3) + (5 if head["bank"] else 0)) * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel"),
-                         "peak_source": peak_src, "kernel": ("block_event_kernel<4>" if a.variant == "block_event" else ("woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel") + "<4,false,%s>" % ("true" if has_bank else "false")), "kernel_ms": ms_kernel,
+                         "traffic": facts.get("bytes"), "peak_source": peak_src,
+                         "kernel": kname + "<4,false,%s>" % ("true" if head["bank"] else "false"), "kernel_ms": ms_kernel,
+                         "kernel_ms_note": "births + transport + tally prefix sum of one generation (CUDA events on the launching stream); "
+                                           "the transport kernel is > 98 % of it (profiles/ launch list)",
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
-                         "actual_limiter": {"what": "instruction issue (ncu, profiles/)", **{k: v for k, v in ncu_facts(
-                             "woodcock_kernel" if a.tracking == "woodcock" else "transport_kernel").items() if k not in ("bytes", "source")}},
+                         "actual_limiter": {"what": "instruction issue (ncu, profiles/)", **{k: v for k, v in facts.items() if k not in ("bytes", "source")}},
                          "note": "algorithmic bytes = 24 + 48*collisions/history (SURVEY 8d bank model); the fused kernel keeps "
                                  "particles in registers, so measured DRAM traffic (the 32-byte birth records) is ~2 % of that: "
                                  "the kernel is instruction-issue bound (profiles/)"},
@@ -340,19 +456,59 @@ def run_ours(a):
                 "note": "same workload, same timing rules, other tracking mode: 'surface' follows the reference cell by cell "
                         "(bit-comparable with the CPU restatement); 'woodcock' is delta tracking with a collision-estimator tally "
                         "(statistically equivalent, 3 sigma / chi-square tested)"}}
+        if configs:
+            line["configs"] = configs
+            line["multi_gpu_bit_identical"] = bool(identical and all(identical.values()))
+            line["multi_gpu_bit_identical_detail"] = {
+                **(identical or {}), "what": "k, flux and bank sizes of a 4-generation 50 001-history TestCaseC run through this launch's "
+                                            f"{world}-rank generation-level route against nraps_mc_run on one GPU, compared bit for bit"}
+        if world == 1 and not a.no_cold:
+            line["e2e_cold"] = cold_runs(local)
         if world == 1 and not a.no_cpu:
+            from tests.util import oracle_inputs
+
             cores = os.cpu_count() or 2
             threads = max(1, cores - 1)
-            sample_h, sample_g = min(H, 1_000_000), 3
-            cpu_sample(args, 50_000, 1, threads)
-            r = cpu_sample(args, sample_h, sample_g, threads)
-            line["cpu_baseline"] = {
-                "value": sample_h * sample_g / r.seconds_transport, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"{sample_g} generations x {sample_h} histories of the same workload, C restatement of src/mc_code.rs "
-                          f"threaded like the reference ({threads} workers of {cores} cores, per-worker f32 tallies)"}
+            problem = oracle_inputs(v, xs, dx, mesh, fuel)
+            t0 = time.perf_counter()
+            cpu_run(problem, 50_000, 1, threads)
+            per_history = (time.perf_counter() - t0) / 50_000
+            sample_h, sample_g = H, 3
+            while sample_h > 100_000 and per_history * sample_h * sample_g > 30.0:
+                sample_h //= 2
+            t0 = time.perf_counter()
+            cpu_run(problem, sample_h, sample_g, threads)
+            wall = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": sample_h * sample_g / wall, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": cpu_sample_text(sample_g, sample_h, H, threads, cores)}
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def cold_runs(device: int) -> dict:
+    """Fresh-process runs of the drop-in binary on the three decks as shipped (BASELINE configs 1 and 2): wall clock of
+    the whole process against the device time of its generations, with nraps_mc_run's own split of the difference."""
+    exe = os.path.join(ROOT, "nraps_b200", "lib", "nraps")
+    out = {}
+    for case in "abc":
+        deck = os.path.join(ROOT, "tests", "golden", "decks", f"case_{case}.txt")
+        with tempfile.TemporaryDirectory() as d:
+            t0 = time.perf_counter()
+            run = subprocess.run([exe, deck, "--out", d, "--quiet", "--device", str(device)], capture_output=True, text=True,
+                                 env=dict(os.environ, NRAPS_TIMING="1"), timeout=300)
+            wall = time.perf_counter() - t0
+        entry = {"process_wall_s": wall, "rc": run.returncode}
+        for ln in run.stderr.splitlines():
+            try:
+                entry.update(json.loads(ln))
+            except ValueError:
+                pass
+        out[f"deck_{case}"] = entry
+    out["note"] = ("`nraps <deck>` as a new process per deck (generations x histories as the deck says: A 100 x 1e5, B and C 100 x 1e6): "
+                   "process start, CUDA context, tables, 100 generations, CSV files.  nraps_mc_run_ms is the library call's own wall-clock split")
+    return out
 
 
 def main():
@@ -362,20 +518,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"])
-    ap.add_argument("--histories", type=int, default=0, help="override histories per generation (total)")
+    ap.add_argument("--histories", type=int, default=0, help="override histories per generation (total) of the headline workload")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--spawn-batch", type=int, default=0)
     ap.add_argument("--walk-cap", type=int, default=0)
-    ap.add_argument("--slots-per-thread", type=int, default=0, help="block_event variant: neutrons banked per thread")
     ap.add_argument("--tracking", default="surface", choices=["surface", "woodcock"],
                     help="surface = the reference's cell-by-cell tracking (headline, bit-comparable); woodcock = delta tracking")
-    ap.add_argument("--variant", default="fused", choices=["fused", "event", "block_event"],
-                    help="kernel variant (event = SoA-bank pipeline in HBM, woodcock only; block_event = experimental on-chip bank, surface only)")
+    ap.add_argument("--variant", default="fused", choices=["fused", "event"],
+                    help="kernel variant (event = SoA-bank pipeline in HBM, woodcock only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other-tracking-mode measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 4 / 5 and the bit-identity check")
+    ap.add_argument("--no-cold", action="store_true", help="skip the fresh-process runs of the shipped decks")
+    ap.add_argument("--quick", action="store_true", help="headline only: --no-cpu --no-variants --no-configs --no-cold")
     a = ap.parse_args()
+    if a.quick:
+        a.no_cpu = a.no_variants = a.no_configs = a.no_cold = True
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference(a)

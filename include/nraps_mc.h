@@ -85,7 +85,13 @@ typedef struct nraps_options {
     int32_t walk_cap;              /* surface tracking: crossings per lane before the warp regroups; 0 or -1 = to the end of the segment */
     int32_t slots_per_thread;      /* block_event variant: neutrons banked per thread of a block; 0 = 3 (was reserved1) */
     uint64_t max_flights;          /* per-history safety cap; 0 = 1<<24               */
+    int32_t profile_phases;        /* 1 = time the phases of every generation with CUDA events (nraps_mc_phase_ms); the host
+                                    * then waits for generation g's kernels before it launches g+1 */
+    int32_t reserved0;
 } nraps_options;
+
+/* phases timed by profile_phases (milliseconds, summed over the generations since creation / nraps_mc_reset) */
+enum { NRAPS_PH_SOURCE = 0, NRAPS_PH_TRANSPORT, NRAPS_PH_PREFIX, NRAPS_PH_COMPACT, NRAPS_PH_FINALIZE, NRAPS_PH_WORDS };
 
 enum {
     NRAPS_CT_HISTORIES = 0, NRAPS_CT_COLLISIONS, NRAPS_CT_CROSSINGS, NRAPS_CT_FLIGHTS,
@@ -145,7 +151,8 @@ int nraps_mc_trim(int32_t device);
 int nraps_mc_reset(nraps_mc_ctx *ctx, float k0, void *stream);
 int nraps_mc_transport(nraps_mc_ctx *ctx, uint64_t gen, uint64_t hist_begin, uint64_t hist_count, void *stream);
 int nraps_mc_finalize_generation(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
-/* device buffer of G*N tally words followed by NRAPS_CT_WORDS counter words (uint64) */
+/* device buffer of G*N tally words followed by NRAPS_CT_WORDS counter words (uint64); in fission_bank mode N more words
+ * follow (cell histogram of the generation's bank).  n_words is what a multi-GPU host all-reduces. */
 int nraps_mc_tally_buffer(nraps_mc_ctx *ctx, void **device_ptr, uint64_t *n_words);
 int nraps_mc_set_tally_buffer(nraps_mc_ctx *ctx, void *device_ptr); /* caller-owned, same size */
 int nraps_mc_read_tally(nraps_mc_ctx *ctx, uint64_t *host_words, void *stream);      /* synchronous */
@@ -154,15 +161,36 @@ int nraps_mc_fetch(nraps_mc_ctx *ctx, nraps_results *r, void *stream);          
 int nraps_mc_trace(nraps_mc_ctx *ctx, uint64_t gen, uint64_t hist_begin, uint64_t hist_count,
                    uint32_t *host_records, void *stream);
 /*
- * fission_bank source mode (power iteration; no reference counterpart).  After transport of generation g:
- *   bank_compact    -> this rank's sites in canonical (history, site) order, (cell << 32 | x bits) each
- *   bank_local      -> device pointer + count of that dense local bank (synchronous)
- *   bank_set_source -> the bank generation g+1 samples from: NULL = the local bank (single GPU), or the
- *                      caller's all-gathered bank (rank order); also records bank size and entropy of `gen`
+ * fission_bank source mode (power iteration; no reference counterpart).  Per generation g, on every rank:
+ *   nraps_mc_transport(g)            births from the bank of g-1 (uniform source for g = 0), then transport
+ *   nraps_mc_bank_compact(g)         this rank's sites of g in canonical (history, site) order, (cell << 32 | x bits)
+ *                                    each, into one of its two bank buffers; the bank's cell histogram is added to
+ *                                    the N words behind the counters of the tally buffer
+ *   [all-reduce of the tally buffer] multi-GPU only; it also orders every rank's compaction before any rank's next births
+ *   nraps_mc_finalize_generation(g)
+ *   nraps_mc_bank_advance(g)         records size and entropy of the bank of g; generation g+1 samples from it
+ * (finalize may also come before compact: it does not touch the bank.)
+ *
+ * Several GPUs: no gathered copy of the bank exists.  Each rank keeps its bank where it compacted it and the source
+ * kernel of every rank resolves a site index to (rank, offset) from the ranks' site counts -- word 0 of each bank buffer
+ * -- and loads the 8-byte site from the rank that banked it, over NVLink.  Set up once, before generation 0:
+ *   nraps_mc_bank_reserve   allocate the two buffers peer-mappable, for shards up to `shard_histories` histories
+ *   one process per GPU:    nraps_mc_bank_export (2 IPC handles) -> exchange them -> nraps_mc_bank_import on every rank
+ *   one process, N devices: enable peer access, pass every rank's two buffer pointers to nraps_mc_bank_peers
  */
+#define NRAPS_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
+#define NRAPS_MAX_RANKS 8         /* GPUs of one NVSwitch box */
 int nraps_mc_bank_compact(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
+int nraps_mc_bank_advance(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
+/* device pointer + count of the dense local bank of the last compaction (synchronous; tests) */
 int nraps_mc_bank_local(nraps_mc_ctx *ctx, void **device_sites, uint64_t *count, void *stream);
-int nraps_mc_bank_set_source(nraps_mc_ctx *ctx, uint64_t gen, const void *device_sites, uint64_t count, void *stream);
+int nraps_mc_bank_reserve(nraps_mc_ctx *ctx, uint64_t shard_histories, void **device_buffers /* [2] out, may be NULL */);
+int nraps_mc_bank_export(nraps_mc_ctx *ctx, void *handles /* [2][NRAPS_IPC_HANDLE_BYTES] out */);
+int nraps_mc_bank_import(nraps_mc_ctx *ctx, int32_t world, int32_t rank, const void *handles /* [world][2][NRAPS_IPC_HANDLE_BYTES] */);
+int nraps_mc_bank_peers(nraps_mc_ctx *ctx, int32_t world, int32_t rank, const void *const *device_buffers /* [world][2] */);
+/* profile_phases = 1: milliseconds spent in {births, transport kernel, tally prefix sum, bank compaction + histogram,
+ * finalize} since creation / reset (synchronizes the device) */
+int nraps_mc_phase_ms(nraps_mc_ctx *ctx, double out[NRAPS_PH_WORDS]);
 /* launch geometry chosen for this context: {grid, block, dynamic smem bytes, blocks/SM, SM count, chunk} */
 int nraps_mc_launch_info(nraps_mc_ctx *ctx, uint32_t out[6]);
 

@@ -17,6 +17,8 @@ CT_NAMES = ["histories", "collisions", "crossings", "flights", "reflections", "l
 TR_WORDS = 10
 TR_NAMES = ["collisions", "crossings", "flights", "reflections", "rng_lo", "rng_hi", "cell", "xbits", "fate", "group"]
 TALLY_FRAC_BITS = 28
+IPC_HANDLE_BYTES = 64
+PH_NAMES = ["source", "transport", "prefix", "compact", "finalize"]
 ABI_VERSION = 4  # NRAPS_ABI_VERSION of include/nraps_mc.h this binding was written against
 
 _fp = C.POINTER(C.c_float)
@@ -44,6 +46,7 @@ class Options(C.Structure):
         ("tracking_mode", C.c_int32), ("kernel_variant", C.c_int32), ("threads_per_block", C.c_int32),
         ("blocks_per_sm", C.c_int32), ("chunk", C.c_int32), ("quiet", C.c_int32), ("bank_cap", C.c_int32),
         ("spawn_batch", C.c_int32), ("walk_cap", C.c_int32), ("slots_per_thread", C.c_int32), ("max_flights", C.c_uint64),
+        ("profile_phases", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -82,7 +85,8 @@ EXPORTS = [
     "nraps_mc_run", "nraps_mc_create", "nraps_mc_destroy", "nraps_mc_trim", "nraps_mc_reset", "nraps_mc_transport",
     "nraps_mc_finalize_generation", "nraps_mc_tally_buffer", "nraps_mc_set_tally_buffer", "nraps_mc_read_tally",
     "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_mc_bank_compact", "nraps_mc_bank_local",
-    "nraps_mc_bank_set_source", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
+    "nraps_mc_bank_advance", "nraps_mc_bank_reserve", "nraps_mc_bank_export", "nraps_mc_bank_import", "nraps_mc_bank_peers",
+    "nraps_mc_phase_ms", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
     "nraps_strerror", "nraps_last_cuda_error", "nraps_abi_version", "nraps_options_default",
     "nraps_process_input", "nraps_deck_free", "nraps_mesh_gen", "nraps_mesh_free", "nraps_problem_from",
     "nraps_format_f32", "nraps_format_f64", "nraps_plot_solution", "nraps_average_assembly", "nraps_k_fund",
@@ -118,9 +122,14 @@ def lib() -> C.CDLL:
     L.nraps_mc_fetch.argtypes = [vp, C.POINTER(Results), vp]
     L.nraps_mc_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, vp]
     L.nraps_mc_launch_info.argtypes = [vp, _u32p]
+    L.nraps_mc_phase_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.nraps_mc_bank_compact.argtypes = [vp, C.c_uint64, vp]
     L.nraps_mc_bank_local.argtypes = [vp, C.POINTER(vp), _u64p, vp]
-    L.nraps_mc_bank_set_source.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp]
+    L.nraps_mc_bank_advance.argtypes = [vp, C.c_uint64, vp]
+    L.nraps_mc_bank_reserve.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.nraps_mc_bank_export.argtypes = [vp, vp]
+    L.nraps_mc_bank_import.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.nraps_mc_bank_peers.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.nraps_dev_logf.argtypes = [_fp, _fp, C.c_uint32, C.c_int32]
     L.nraps_dev_div.argtypes = [_fp, _fp, _fp, _fp, C.c_uint32, C.c_int32]
     L.nraps_dev_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _u32p, _fp, C.c_int32]

@@ -201,14 +201,14 @@ class _Marshalled:
 def make_options(*, seed=0, stream=0, stride=0, device=0, scatter_mode="single_xi", stale_xs=True,
                  source_mode="uniform_fuel", tracking_mode="surface", kernel_variant="fused", threads_per_block=0,
                  blocks_per_sm=0, chunk=0, quiet=True, max_flights=0, bank_cap=0, spawn_batch=0, walk_cap=0,
-                 slots_per_thread=0) -> Options:
+                 slots_per_thread=0, profile_phases=False) -> Options:
     return Options(
         seed=seed, stream=stream, stride=stride, device=device, scatter_mode=SCATTER_MODES[scatter_mode],
         stale_xs=int(bool(stale_xs)), source_mode=SOURCE_MODES[source_mode], tracking_mode=TRACKING_MODES[tracking_mode],
         kernel_variant=KERNEL_VARIANTS[kernel_variant], threads_per_block=threads_per_block,
         blocks_per_sm=blocks_per_sm, chunk=chunk, quiet=int(bool(quiet)), bank_cap=bank_cap, spawn_batch=spawn_batch, walk_cap=walk_cap,
         slots_per_thread=slots_per_thread,
-        max_flights=max_flights,
+        max_flights=max_flights, profile_phases=int(bool(profile_phases)),
     )
 
 
@@ -273,8 +273,8 @@ class MonteCarloContext:
         self._h = C.c_void_p()
         check(lib().nraps_mc_create(C.byref(self._m.problem), C.byref(self._o), C.byref(self._h)), "nraps_mc_create")
         self.G, self.N, self.generations, self.histories = self._m.G, self._m.N, self._m.generations, self._m.histories
-        self.n_words = self.G * self.N + CT_WORDS
         self._ext = None
+        self.n_words = self.tally_buffer()[1]  # G*N tally words + counters (+ N histogram words in fission_bank mode)
 
     def close(self):
         if self._h:
@@ -337,15 +337,24 @@ class MonteCarloContext:
         check(lib().nraps_mc_bank_local(self._h, C.byref(ptr), C.byref(n), C.c_void_p(stream)), "nraps_mc_bank_local")
         return ptr.value, n.value
 
-    def bank_set_source(self, gen: int, tensor=None, stream=None):
-        """Bank that generation gen+1 samples from: None = the local bank, else an int64 CUDA tensor of sites."""
-        if tensor is None:
-            ptr, n = None, 0
-        else:
-            assert tensor.is_cuda and tensor.element_size() == 8 and tensor.is_contiguous()
-            self._src = tensor  # keep alive until replaced
-            ptr, n = tensor.data_ptr(), tensor.numel()
-        check(lib().nraps_mc_bank_set_source(self._h, gen, C.c_void_p(ptr), n, C.c_void_p(stream)), "nraps_mc_bank_set_source")
+    def bank_advance(self, gen: int, stream=None):
+        """Record size / entropy of the bank of `gen`; generation gen+1 samples from it."""
+        check(lib().nraps_mc_bank_advance(self._h, gen, C.c_void_p(stream)), "nraps_mc_bank_advance")
+
+    def bank_reserve(self, shard_histories: int):
+        """Allocate the two bank buffers peer-mappable (multi-GPU), sized for shards of up to `shard_histories`."""
+        check(lib().nraps_mc_bank_reserve(self._h, shard_histories, None), "nraps_mc_bank_reserve")
+
+    def bank_export(self) -> bytes:
+        """CUDA IPC handles of this rank's two bank buffers (2 x 64 bytes)."""
+        buf = C.create_string_buffer(2 * _lib.IPC_HANDLE_BYTES)
+        check(lib().nraps_mc_bank_export(self._h, buf), "nraps_mc_bank_export")
+        return buf.raw
+
+    def bank_import(self, world: int, rank: int, handles: bytes):
+        """Map the peers' bank buffers from every rank's exported handles (rank order, 2 x 64 bytes each)."""
+        assert len(handles) == world * 2 * _lib.IPC_HANDLE_BYTES
+        check(lib().nraps_mc_bank_import(self._h, world, rank, C.c_char_p(handles)), "nraps_mc_bank_import")
 
     def read_bank(self, stream=None) -> np.ndarray:
         """Host copy of the local dense bank (tests)."""
@@ -361,6 +370,12 @@ class MonteCarloContext:
         rb = _ResultBuffers(self.G, self.N, self.generations)
         check(lib().nraps_mc_fetch(self._h, C.byref(rb.c), C.c_void_p(stream)), "nraps_mc_fetch")
         return rb.solution()
+
+    def phase_ms(self) -> dict:
+        """profile_phases=True: milliseconds per phase summed over the generations run so far (synchronizes)."""
+        out = (C.c_double * len(_lib.PH_NAMES))()
+        check(lib().nraps_mc_phase_ms(self._h, out), "nraps_mc_phase_ms")
+        return dict(zip(_lib.PH_NAMES, [float(v) for v in out]))
 
     def launch_info(self) -> dict:
         out = (C.c_uint32 * 6)()

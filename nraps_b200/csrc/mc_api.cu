@@ -12,7 +12,9 @@
 //   per-crossing matid compare of src/mc_code.rs:175-181)
 //   PCG32 jump table (A_b, C_b): the affine map of stride*2^b LCG steps
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -175,16 +177,26 @@ struct nraps_mc_ctx {
     bool bank_mode = false;
     uint32_t bank_cap = 8;
     uint64_t bank_hist_cap = 0, dense_cap = 0; // histories / sites the buffers below are sized for
-    unsigned long long *d_slots = nullptr, *d_block_sums = nullptr, *d_dense[2] = {nullptr, nullptr};
-    unsigned long long *d_bank_count = nullptr;  // [3]: count of dense[0], dense[1], external source
+    unsigned long long *d_slots = nullptr, *d_block_sums = nullptr;
+    // the two bank buffers of this rank ([kBankHeader words: site count first][sites]), written alternately
+    unsigned long long *d_bank[2] = {nullptr, nullptr};
+    bool bank_shared = false;                    // buffers came from cudaMalloc (mappable by peers), not from the pool
+    int bank_world = 1, bank_rank = 0;           // ranks whose banks together feed a generation
+    const unsigned long long *peer_bank[2][kMaxPeers] = {}; // [buffer][rank]; own entries point at d_bank
+    void *ipc_opened[2][kMaxPeers] = {};         // peers' buffers opened from IPC handles (closed in free_ctx)
     unsigned long long *d_bank_sizes = nullptr;  // [generations]
     double *d_entropy = nullptr;                 // [generations]
     uint8_t *d_counts = nullptr;
-    uint32_t *d_hist = nullptr;
-    int bank_which = 0;                          // dense buffer the next compaction writes
-    const unsigned long long *src_bank = nullptr, *src_count_ptr = nullptr;
-    uint64_t ext_count_host = 0;
+    int bank_which = 0;                          // buffer the next compaction writes
+    int bank_src = -1;                           // buffer generation g+1 samples from (-1: no bank yet, uniform source)
+    int bank_last = -1;                          // buffer of the last compaction (nraps_mc_bank_local)
     uint64_t last_shard = 0;
+
+    // profile_phases: event pairs around each phase of the generation in flight, folded into phase_ms when the next
+    // generation (or a query) comes along
+    cudaEvent_t ph_ev[2 * NRAPS_PH_WORDS] = {};
+    bool ph_armed[NRAPS_PH_WORDS] = {};
+    double phase_ms[NRAPS_PH_WORDS] = {};
 
     // event-based pipeline (kernel_variant = NRAPS_KERNEL_EVENT)
     EventBank ev{};
@@ -243,6 +255,47 @@ int validate(const nraps_problem *p, const nraps_options *o)
     return NRAPS_OK;
 }
 
+// phase timing (nraps_options.profile_phases): begin/end record an event pair on the stream, fold() waits for the
+// pairs recorded so far and adds their elapsed times
+void phase_fold(nraps_mc_ctx *c)
+{
+    for (int p = 0; p < NRAPS_PH_WORDS; ++p) {
+        if (!c->ph_armed[p]) continue;
+        float ms = 0.0f;
+        if (cudaEventSynchronize(c->ph_ev[2 * p + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ph_ev[2 * p], c->ph_ev[2 * p + 1]) == cudaSuccess)
+            c->phase_ms[p] += (double)ms;
+        c->ph_armed[p] = false;
+    }
+}
+void phase_begin(nraps_mc_ctx *c, int p, cudaStream_t s)
+{
+    if (!c->opt.profile_phases) return;
+    if (c->ph_armed[p]) phase_fold(c);
+    if (!c->ph_ev[2 * p]) { cudaEventCreate(&c->ph_ev[2 * p]); cudaEventCreate(&c->ph_ev[2 * p + 1]); }
+    cudaEventRecord(c->ph_ev[2 * p], s);
+}
+void phase_end(nraps_mc_ctx *c, int p, cudaStream_t s)
+{
+    if (!c->opt.profile_phases) return;
+    cudaEventRecord(c->ph_ev[2 * p + 1], s);
+    c->ph_armed[p] = true;
+}
+
+void free_bank_buffers(nraps_mc_ctx *c)
+{
+    for (int w = 0; w < 2; ++w) {
+        for (int r = 0; r < kMaxPeers; ++r) {
+            if (c->ipc_opened[w][r]) cudaIpcCloseMemHandle(c->ipc_opened[w][r]);
+            c->ipc_opened[w][r] = nullptr;
+            c->peer_bank[w][r] = nullptr;
+        }
+        if (c->bank_shared) { cudaDeviceSynchronize(); cudaFree(c->d_bank[w]); }
+        else dev_free(c->d_bank[w]);
+        c->d_bank[w] = nullptr;
+    }
+    c->bank_shared = false;
+}
+
 void free_ctx(nraps_mc_ctx *c)
 {
     if (!c) return;
@@ -252,10 +305,13 @@ void free_ctx(nraps_mc_ctx *c)
     dev_free(c->d_tally_own); dev_free(c->d_work); dev_free(c->d_counters_total);
     dev_free(c->d_res_moments); dev_free(c->d_terms); dev_free(c->d_res_flux); dev_free(c->d_res_fission); dev_free(c->d_k_hist); dev_free(c->d_k_cur);
     dev_free(c->d_trace); dev_free(c->d_source);
-    dev_free(c->d_slots); dev_free(c->d_block_sums); dev_free(c->d_dense[0]); dev_free(c->d_dense[1]);
+    dev_free(c->d_slots); dev_free(c->d_block_sums);
+    free_bank_buffers(c);
+    for (cudaEvent_t e : c->ph_ev)
+        if (e) cudaEventDestroy(e);
     for (EventHalf &h : c->ev.half) { dev_free(h.x); dev_free(h.mu); dev_free(h.pack); dev_free(h.cnt); dev_free(h.ccnt); dev_free(h.rng); }
     dev_free(c->ev.n_alive);
-    dev_free(c->d_bank_count); dev_free(c->d_bank_sizes); dev_free(c->d_entropy); dev_free(c->d_counts); dev_free(c->d_hist);
+    dev_free(c->d_bank_sizes); dev_free(c->d_entropy); dev_free(c->d_counts);
     delete c;
 }
 
@@ -280,29 +336,35 @@ int ensure_event_bank(nraps_mc_ctx *c, uint64_t count)
     return NRAPS_OK;
 }
 
-// (re)size the per-history slot rows and the dense banks for a shard of `count` histories
-int ensure_bank(nraps_mc_ctx *c, uint64_t count, cudaStream_t s)
+// Size the per-history slot rows and the two bank buffers for a shard of `count` histories.  shared = the buffers must
+// be mappable by other ranks (cudaMalloc: IPC handles and peer access work on those, not on pool memory).
+int alloc_bank(nraps_mc_ctx *c, uint64_t count, bool shared, cudaStream_t s)
 {
-    if (count <= c->bank_hist_cap) return NRAPS_OK;
     const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
     // every history keeps at most bank_cap sites, so this bound is exact: no generation can overflow the dense bank
     // (a tighter guess of 3 sites per history truncated the first generations of problems with k / k0 > 3, found by
     // the GPU fuzz in round 2)
     const uint64_t dense_cap = count * c->bank_cap + 1024;
-    unsigned long long *dense[2] = {nullptr, nullptr};
-    CU(dev_malloc((void **)&dense[0], dense_cap * sizeof(unsigned long long)));
-    CU(dev_malloc((void **)&dense[1], dense_cap * sizeof(unsigned long long)));
-    // the bank the next generation samples from may live in the buffers about to be replaced: carry it over
+    const size_t bytes = (kBankHeader + dense_cap) * sizeof(unsigned long long);
+    unsigned long long *fresh[2] = {nullptr, nullptr};
     for (int w = 0; w < 2; ++w) {
-        if (!c->d_dense[w]) continue;
-        CU(cudaMemcpyAsync(dense[w], c->d_dense[w], c->dense_cap * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-        if (c->src_bank == c->d_dense[w]) c->src_bank = dense[w];
+        if (shared) CU(cudaMalloc((void **)&fresh[w], bytes));
+        else CU(dev_malloc((void **)&fresh[w], bytes));
+        CU(cudaMemsetAsync(fresh[w], 0, kBankHeader * sizeof(unsigned long long), s));
     }
+    // the bank the next generation samples from may live in the buffers about to be replaced: carry it over
+    for (int w = 0; w < 2; ++w)
+        if (c->d_bank[w]) CU(cudaMemcpyAsync(fresh[w], c->d_bank[w], (kBankHeader + c->dense_cap) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
     CU(cudaStreamSynchronize(s));
-    dev_free(c->d_slots); dev_free(c->d_counts); dev_free(c->d_block_sums); dev_free(c->d_dense[0]); dev_free(c->d_dense[1]);
+    dev_free(c->d_slots); dev_free(c->d_counts); dev_free(c->d_block_sums);
     c->d_slots = c->d_block_sums = nullptr;
     c->d_counts = nullptr;
-    c->d_dense[0] = dense[0]; c->d_dense[1] = dense[1];
+    free_bank_buffers(c);
+    for (int w = 0; w < 2; ++w) {
+        c->d_bank[w] = fresh[w];
+        c->peer_bank[w][c->bank_rank] = fresh[w];
+    }
+    c->bank_shared = shared;
     c->dense_cap = dense_cap;
     c->bank_hist_cap = 0;
     CU(dev_malloc((void **)&c->d_slots, padded * c->bank_cap * sizeof(unsigned long long)));
@@ -310,6 +372,13 @@ int ensure_bank(nraps_mc_ctx *c, uint64_t count, cudaStream_t s)
     CU(dev_malloc((void **)&c->d_block_sums, (padded / kBankTile) * sizeof(unsigned long long)));
     c->bank_hist_cap = count;
     return NRAPS_OK;
+}
+
+int ensure_bank(nraps_mc_ctx *c, uint64_t count, cudaStream_t s)
+{
+    if (count <= c->bank_hist_cap) return NRAPS_OK;
+    if (c->bank_world > 1) return NRAPS_ERR_STATE; // peers hold mappings of the current buffers: reserve for the largest shard first
+    return alloc_bank(c, count, c->bank_shared, s);
 }
 
 // Transport generations gen .. gen+nb-1 (shard [begin, begin+count) of each) in one launch.  nb > 1 only for the
@@ -325,7 +394,8 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
         if (padded) CU(cudaMemsetAsync(c->d_counts, 0, padded, s));
     }
-    const uint64_t words = (uint64_t)nb * c->G * c->N + NRAPS_CT_WORDS;
+    // bank mode: the cell histogram of the generation's bank rides behind the counters (one all-reduce for all of it)
+    const uint64_t words = (uint64_t)nb * c->G * c->N + NRAPS_CT_WORDS + (c->bank_mode ? c->N : 0u);
     CU(cudaMemsetAsync(c->d_tally, 0, words * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
     if (count == 0) return NRAPS_OK;
@@ -350,7 +420,8 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)std::min(c->opt.spawn_batch, 32) : (c->woodcock ? 2u : 1u);
     P.walk_cap = c->opt.walk_cap > 0 ? (uint32_t)c->opt.walk_cap : 0x7fffffffu;
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
-    P.src_bank = c->src_bank; P.src_count_ptr = c->src_count_ptr;
+    P.n_peers = (c->bank_mode && c->bank_src >= 0) ? (uint32_t)c->bank_world : 0u;
+    for (uint32_t r = 0; r < P.n_peers; ++r) P.peer_bank[r] = c->peer_bank[c->bank_src][r];
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
     if (c->opt.kernel_variant != NRAPS_KERNEL_EVENT) { // births first, every lane busy; the transport lanes adopt them
         const uint64_t births = (uint64_t)nb * count;
@@ -361,7 +432,9 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
             c->source_cap = births;
         }
         P.source = c->d_source;
+        phase_begin(c, NRAPS_PH_SOURCE, s);
         CU(launch_source(P, c->bank_mode, c->d_source, s));
+        phase_end(c, NRAPS_PH_SOURCE, s);
     }
     if (c->opt.kernel_variant == NRAPS_KERNEL_EVENT) {
         if (trace) return NRAPS_ERR_OPTION;
@@ -400,11 +473,15 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         c->geo_grid[ti] = (uint32_t)c->sm_count * bps;
         c->prepared |= 1u << ti;
     }
+    phase_begin(c, NRAPS_PH_TRANSPORT, s);
     if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
-    else {
-        CU(launch_transport(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
+    else CU(launch_transport(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
+    phase_end(c, NRAPS_PH_TRANSPORT, s);
+    if (!c->woodcock) {
         // the cells a flight crossed completely were booked as range updates: fold their prefix sums into the tally
+        phase_begin(c, NRAPS_PH_PREFIX, s);
         CU(launch_tally_prefix(c->d_diff, c->d_tally, nb * c->G, c->N, s));
+        phase_end(c, NRAPS_PH_PREFIX, s);
     }
     return NRAPS_OK;
 }
@@ -659,7 +736,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     ok(dev_malloc((void **)&c->d_diff, batch * GN * sizeof(unsigned long long)));
     ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump)); ok(upload(&c->d_bucket, bucket));
     ok(upload(&c->d_dx, dx)); ok(upload(&c->d_nut, nut)); ok(upload(&c->d_sigf, sigf));
-    ok(dev_malloc((void **)&c->d_tally_own, (batch * GN + NRAPS_CT_WORDS) * sizeof(unsigned long long)));
+    ok(dev_malloc((void **)&c->d_tally_own, (batch * GN + NRAPS_CT_WORDS + N) * sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_work, sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_counters_total, NRAPS_CT_WORDS * sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_terms, GN * sizeof(float)));
@@ -668,10 +745,8 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     ok(dev_malloc((void **)&c->d_res_fission, N * sizeof(float)));
     ok(dev_malloc((void **)&c->d_k_hist, c->generations * sizeof(float)));
     ok(dev_malloc((void **)&c->d_k_cur, sizeof(float)));
-    ok(dev_malloc((void **)&c->d_bank_count, 3 * sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_bank_sizes, c->generations * sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_entropy, c->generations * sizeof(double)));
-    ok(dev_malloc((void **)&c->d_hist, N * sizeof(uint32_t)));
     c->NB = NB; c->woodcock = woodcock; c->big = big;
     c->inv_h = NB ? (float)((double)NB / (double)p->right[N - 1]) : 0.0f;
     if (e != cudaSuccess) {
@@ -706,7 +781,9 @@ int finalize_slice(nraps_mc_ctx *c, uint64_t gen, uint32_t slice, uint32_t nb, c
     // 1 / (generations - (skip - 1)) in wrapping usize arithmetic, src/mc_code.rs:340
     F.fund = 1.0f / (float)(uint64_t)(c->generations - (c->skip - 1));
     F.gen = gen; F.skip = c->skip;
+    phase_begin(c, NRAPS_PH_FINALIZE, s);
     CU(launch_finalize(F, s));
+    phase_end(c, NRAPS_PH_FINALIZE, s);
     return NRAPS_OK;
 }
 
@@ -736,10 +813,11 @@ extern "C" int nraps_mc_reset(nraps_mc_ctx *c, float k0, void *stream)
     CU(cudaMemsetAsync(c->d_res_fission, 0, c->N * sizeof(float), s));
     CU(cudaMemsetAsync(c->d_k_hist, 0, c->generations * sizeof(float), s));
     CU(cudaMemsetAsync(c->d_counters_total, 0, NRAPS_CT_WORDS * sizeof(unsigned long long), s));
-    CU(cudaMemsetAsync(c->d_bank_count, 0, 3 * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_bank_sizes, 0, c->generations * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_entropy, 0, c->generations * sizeof(double), s));
-    c->src_bank = nullptr; c->src_count_ptr = nullptr; c->bank_which = 0;
+    c->bank_src = -1; c->bank_last = -1; c->bank_which = 0;
+    phase_fold(c);
+    for (double &v : c->phase_ms) v = 0.0;
     CU(cudaMemcpyAsync(c->d_k_cur, &k0, sizeof(float), cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s)); // k0 lives on the caller's stack
     return NRAPS_OK;
@@ -764,7 +842,7 @@ extern "C" int nraps_mc_tally_buffer(nraps_mc_ctx *c, void **device_ptr, uint64_
 {
     if (!c || !device_ptr || !n_words) return NRAPS_ERR_NULL;
     *device_ptr = c->d_tally;
-    *n_words = (uint64_t)c->G * c->N + NRAPS_CT_WORDS;
+    *n_words = (uint64_t)c->G * c->N + NRAPS_CT_WORDS + (c->bank_mode ? c->N : 0u);
     return NRAPS_OK;
 }
 
@@ -847,49 +925,125 @@ extern "C" int nraps_mc_trace(nraps_mc_ctx *c, uint64_t gen, uint64_t hist_begin
 extern "C" int nraps_mc_bank_compact(nraps_mc_ctx *c, uint64_t gen, void *stream)
 {
     if (!c) return NRAPS_ERR_NULL;
-    if (!c->bank_mode || gen >= c->generations) return NRAPS_ERR_STATE;
+    if (!c->bank_mode || gen >= c->generations || !c->d_bank[c->bank_which]) return NRAPS_ERR_STATE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU(cudaSetDevice(c->device));
     BankParams B{};
     const uint64_t padded = (c->last_shard + kBankTile - 1) / kBankTile * kBankTile;
-    B.counts = c->d_counts; B.slots = c->d_slots; B.dense = c->d_dense[c->bank_which];
-    B.block_sums = c->d_block_sums; B.count_out = c->d_bank_count + c->bank_which;
+    unsigned long long *buf = c->d_bank[c->bank_which];
+    B.counts = c->d_counts; B.slots = c->d_slots; B.dense = buf + kBankHeader;
+    B.block_sums = c->d_block_sums; B.count_out = buf; // word 0 of the buffer: where the peers read the count
     B.n_hist = c->last_shard; B.dense_cap = c->dense_cap; B.cap = c->bank_cap; B.n_tiles = (uint32_t)(padded / kBankTile);
-    CU(launch_bank_compact(B, static_cast<cudaStream_t>(stream)));
+    phase_begin(c, NRAPS_PH_COMPACT, s);
+    CU(launch_bank_compact(B, s));
+    // this rank's share of the bank's cell histogram, into the words behind the counters of the tally buffer
+    CU(launch_bank_histogram(buf + kBankHeader, buf, c->d_tally + (uint64_t)c->G * c->N + NRAPS_CT_WORDS, c->N, s));
+    phase_end(c, NRAPS_PH_COMPACT, s);
+    c->bank_last = c->bank_which;
     return NRAPS_OK;
 }
 
 extern "C" int nraps_mc_bank_local(nraps_mc_ctx *c, void **device_sites, uint64_t *count, void *stream)
 {
     if (!c || !device_sites || !count) return NRAPS_ERR_NULL;
-    if (!c->bank_mode) return NRAPS_ERR_STATE;
+    if (!c->bank_mode || c->bank_last < 0) return NRAPS_ERR_STATE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU(cudaSetDevice(c->device));
     unsigned long long n = 0;
-    CU(cudaMemcpyAsync(&n, c->d_bank_count + c->bank_which, sizeof(n), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&n, c->d_bank[c->bank_last], sizeof(n), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    *device_sites = c->d_dense[c->bank_which];
+    *device_sites = c->d_bank[c->bank_last] + kBankHeader;
     *count = n;
     return NRAPS_OK;
 }
 
-extern "C" int nraps_mc_bank_set_source(nraps_mc_ctx *c, uint64_t gen, const void *device_sites, uint64_t count, void *stream)
+extern "C" int nraps_mc_bank_advance(nraps_mc_ctx *c, uint64_t gen, void *stream)
 {
     if (!c) return NRAPS_ERR_NULL;
-    if (!c->bank_mode || gen >= c->generations) return NRAPS_ERR_STATE;
+    if (!c->bank_mode || gen >= c->generations || c->bank_last != c->bank_which) return NRAPS_ERR_STATE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU(cudaSetDevice(c->device));
-    if (device_sites) { // caller-owned (all-gathered) bank; must stay valid until the next transport has finished
-        if (count >> 32) return NRAPS_ERR_TOO_LARGE; // site index = (u32 * count) >> 32
-        c->ext_count_host = count;
-        CU(cudaMemcpyAsync(c->d_bank_count + 2, &c->ext_count_host, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-        c->src_bank = static_cast<const unsigned long long *>(device_sites);
-        c->src_count_ptr = c->d_bank_count + 2;
-    } else {
-        c->src_bank = c->d_dense[c->bank_which];
-        c->src_count_ptr = c->d_bank_count + c->bank_which;
-    }
+    // size and entropy of the whole bank from the histogram words (summed across ranks by the caller's all-reduce)
+    CU(launch_bank_entropy(c->d_tally + (uint64_t)c->G * c->N + NRAPS_CT_WORDS, c->N, c->d_entropy + gen, c->d_bank_sizes + gen, s));
+    c->bank_src = c->bank_which;
     c->bank_which ^= 1;
-    CU(launch_bank_entropy(c->src_bank, c->src_count_ptr, c->d_hist, c->N, c->d_entropy + gen, c->d_bank_sizes + gen, s));
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_bank_reserve(nraps_mc_ctx *c, uint64_t shard_histories, void **device_buffers)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    if (!c->bank_mode || c->bank_world > 1 || shard_histories == 0) return NRAPS_ERR_STATE;
+    CU(cudaSetDevice(c->device));
+    if (!c->bank_shared || shard_histories > c->bank_hist_cap) {
+        int rc = alloc_bank(c, std::max<uint64_t>(shard_histories, c->bank_hist_cap), true, nullptr);
+        if (rc != NRAPS_OK) return rc;
+    }
+    if (device_buffers) { device_buffers[0] = c->d_bank[0]; device_buffers[1] = c->d_bank[1]; }
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_bank_export(nraps_mc_ctx *c, void *handles)
+{
+    if (!c || !handles) return NRAPS_ERR_NULL;
+    if (!c->bank_mode || !c->bank_shared) return NRAPS_ERR_STATE;
+    CU(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == NRAPS_IPC_HANDLE_BYTES, "handle size is part of the ABI");
+    for (int w = 0; w < 2; ++w) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->d_bank[w]));
+        std::memcpy(static_cast<unsigned char *>(handles) + w * NRAPS_IPC_HANDLE_BYTES, &h, NRAPS_IPC_HANDLE_BYTES);
+    }
+    return NRAPS_OK;
+}
+
+namespace {
+int set_peers(nraps_mc_ctx *c, int32_t world, int32_t rank)
+{
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return NRAPS_ERR_OPTION;
+    if (!c->bank_mode || !c->bank_shared || c->bank_src >= 0) return NRAPS_ERR_STATE; // before the first bank is advanced to
+    return NRAPS_OK;
+}
+} // namespace
+
+extern "C" int nraps_mc_bank_import(nraps_mc_ctx *c, int32_t world, int32_t rank, const void *handles)
+{
+    if (!c || !handles) return NRAPS_ERR_NULL;
+    int rc = set_peers(c, world, rank);
+    if (rc != NRAPS_OK) return rc;
+    CU(cudaSetDevice(c->device));
+    for (int r = 0; r < world; ++r)
+        for (int w = 0; w < 2; ++w) {
+            if (r == rank) { c->peer_bank[w][r] = c->d_bank[w]; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const unsigned char *>(handles) + ((size_t)r * 2 + w) * NRAPS_IPC_HANDLE_BYTES, NRAPS_IPC_HANDLE_BYTES);
+            void *p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened[w][r] = p;
+            c->peer_bank[w][r] = static_cast<const unsigned long long *>(p);
+        }
+    c->bank_world = world; c->bank_rank = rank;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_bank_peers(nraps_mc_ctx *c, int32_t world, int32_t rank, const void *const *device_buffers)
+{
+    if (!c || !device_buffers) return NRAPS_ERR_NULL;
+    int rc = set_peers(c, world, rank);
+    if (rc != NRAPS_OK) return rc;
+    for (int r = 0; r < world; ++r)
+        for (int w = 0; w < 2; ++w)
+            c->peer_bank[w][r] = r == rank ? c->d_bank[w] : static_cast<const unsigned long long *>(device_buffers[(size_t)r * 2 + w]);
+    c->bank_world = world; c->bank_rank = rank;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_phase_ms(nraps_mc_ctx *c, double out[NRAPS_PH_WORDS])
+{
+    if (!c || !out) return NRAPS_ERR_NULL;
+    CU(cudaSetDevice(c->device));
+    phase_fold(c);
+    for (int p = 0; p < NRAPS_PH_WORDS; ++p) out[p] = c->phase_ms[p];
     return NRAPS_OK;
 }
 
@@ -908,9 +1062,16 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
 {
     if (!p || !o || !r) return NRAPS_ERR_NULL;
     if (!r->flux || !r->assembly_average || !r->fission_source || !r->k || !r->k_fund) return NRAPS_ERR_NULL;
+    // NRAPS_TIMING=1: host wall-clock split of this call on stderr (where a cold process spends its time)
+    const bool timing = std::getenv("NRAPS_TIMING") != nullptr;
+    const auto w0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+    if (timing) cudaFree(nullptr); // bring the CUDA context up on its own line of the split
+    const double ms_context = since(w0);
     nraps_mc_ctx *c = nullptr;
     int rc = create_ctx(p, o, &c, true);
     if (rc != NRAPS_OK) return rc;
+    const double ms_create = since(w0) - ms_context;
     if (!o->quiet) { std::printf("running MC code\n"); std::fflush(stdout); } // src/mc_code.rs:292
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -941,15 +1102,23 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
         gen += nb;
         if (c->bank_mode) {
             if ((rc = nraps_mc_bank_compact(c, gen - 1, s)) != NRAPS_OK) return bail(rc);
-            if ((rc = nraps_mc_bank_set_source(c, gen - 1, nullptr, 0, s)) != NRAPS_OK) return bail(rc);
+            if ((rc = nraps_mc_bank_advance(c, gen - 1, s)) != NRAPS_OK) return bail(rc);
         }
     }
     cudaEventRecord(e1, s);
+    const double ms_enqueue = since(w0) - ms_context - ms_create;
     if ((rc = nraps_mc_fetch(c, r, s)) != NRAPS_OK) return bail(rc);
+    const double ms_fetch = since(w0) - ms_context - ms_create - ms_enqueue;
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
     r->seconds_device = 1e-3 * (double)ms;
-    return bail(NRAPS_OK);
+    const auto w1 = std::chrono::steady_clock::now();
+    rc = bail(NRAPS_OK);
+    if (timing)
+        std::fprintf(stderr, "{\"nraps_mc_run_ms\": {\"cuda_context\": %.1f, \"create_tables_buffers\": %.1f, \"enqueue_generations\": %.1f, "
+                             "\"wait_and_fetch\": %.1f, \"destroy\": %.1f, \"device_generations\": %.1f, \"batch\": %u}}\n",
+                     ms_context, ms_create, ms_enqueue, ms_fetch, since(w1), (double)ms, 0u);
+    return rc;
 }
 
 // device scratch of the unit probes below: released on every return path

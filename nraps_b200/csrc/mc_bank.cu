@@ -124,10 +124,12 @@ __global__ void __launch_bounds__(1024) bank_scatter(const BankParams P)
     }
 }
 
-// cell histogram of the bank; bins privatised in shared memory when they fit (sites cluster on a few hundred
-// fuel cells, so global atomics would serialise: 180 ms for 1e9 sites before this was privatised)
-__global__ void __launch_bounds__(1024) bank_histogram(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist,
-                                                       uint32_t N, int use_smem)
+// Cell histogram of this rank's dense bank, added to the N words behind the tally and the counters of the generation's
+// tally buffer: the buffer is summed across ranks once per generation anyway, so the histogram of the whole bank --
+// what the entropy diagnostic needs -- comes with it.  Bins are privatised in shared memory when they fit (sites
+// cluster on a few hundred fuel cells, so global atomics would serialise: 180 ms for 1e9 sites before).
+__global__ void __launch_bounds__(1024) bank_histogram(const unsigned long long *bank, const unsigned long long *count_ptr,
+                                                       unsigned long long *hist, uint32_t N, int use_smem)
 {
     extern __shared__ uint32_t s_hist[];
     const unsigned long long n = *count_ptr;
@@ -135,24 +137,35 @@ __global__ void __launch_bounds__(1024) bank_histogram(const unsigned long long 
         for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) s_hist[i] = 0u;
         __syncthreads();
     }
-    uint32_t *dst = use_smem ? s_hist : hist;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
-        atomicAdd(&dst[(uint32_t)(bank[i] >> 32)], 1u);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t cell = (uint32_t)(bank[i] >> 32);
+        if (use_smem) atomicAdd(&s_hist[cell], 1u);
+        else atomicAdd(&hist[cell], 1ull);
+    }
     if (use_smem) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < N; i += blockDim.x)
-            if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+            if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
     }
 }
 
-__global__ void __launch_bounds__(1024) bank_entropy(const uint32_t *hist, uint32_t N, const unsigned long long *count_ptr,
-                                                     double *entropy_out, unsigned long long *size_out)
+// Shannon entropy (bits) of the bank over mesh cells and the bank's size, from the summed histogram
+__global__ void __launch_bounds__(1024) bank_entropy(const unsigned long long *hist, uint32_t N, double *entropy_out, unsigned long long *size_out)
 {
     __shared__ double part[32];
-    const double n = (double)*count_ptr;
+    __shared__ unsigned long long tot[32];
+    unsigned long long cnt = 0ull;
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) cnt += hist[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+    if ((threadIdx.x & 31) == 0) tot[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    unsigned long long total = 0ull;
+    for (int w = 0; w < 32; ++w) total += tot[w];
+    const double n = (double)total;
     double e = 0.0;
     for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
-        const uint32_t h = hist[i];
+        const unsigned long long h = hist[i];
         if (h) {
             const double p = (double)h / n;
             e -= p * log2(p);
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(1024) bank_entropy(const uint32_t *hist, uint3
         double t = 0.0;
         for (int w = 0; w < 32; ++w) t += part[w];
         *entropy_out = t;
-        *size_out = *count_ptr;
+        *size_out = total;
     }
 }
 
@@ -181,19 +194,22 @@ cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
-                                double *entropy_out, unsigned long long *size_out, cudaStream_t s)
+cudaError_t launch_bank_histogram(const unsigned long long *bank, const unsigned long long *count_ptr, unsigned long long *hist, uint32_t N,
+                                  cudaStream_t s)
 {
-    cudaError_t e = cudaMemsetAsync(hist, 0, N * sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
     const int use_smem = N * sizeof(uint32_t) <= 96 * 1024;
     const size_t smem = use_smem ? N * sizeof(uint32_t) : 0;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(bank_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bank_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     bank_histogram<<<148 * 2, 1024, smem, s>>>(bank, count_ptr, hist, N, use_smem);
-    bank_entropy<<<1, 1024, 0, s>>>(hist, N, count_ptr, entropy_out, size_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bank_entropy(const unsigned long long *hist, uint32_t N, double *entropy_out, unsigned long long *size_out, cudaStream_t s)
+{
+    bank_entropy<<<1, 1024, 0, s>>>(hist, N, entropy_out, size_out);
     return cudaGetLastError();
 }
 

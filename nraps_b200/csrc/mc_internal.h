@@ -93,6 +93,9 @@ __host__ __device__ inline SurfLayout make_surface_layout(uint32_t M, uint32_t G
     return L;
 }
 
+constexpr int kMaxPeers = 8;        // GPUs of one NVSwitch box
+constexpr uint32_t kBankHeader = 16; // 64-bit words in front of the sites of a bank buffer (word 0: site count)
+
 struct TransportParams {
     // read-only tables in global memory (device pointers)
     const float *edges;
@@ -122,9 +125,11 @@ struct TransportParams {
     uint32_t walk_cap;    // surface kernel: crossings a lane walks before the warp regroups (0xffffffff = never)
     uint32_t spawn_batch; // dead lanes a warp waits for before it refills (amortises the divergent spawn path)
     int32_t scatter_mode, stale_xs;
-    // fission_bank source mode
-    const unsigned long long *src_bank;      // dense sites (cell << 32 | x bits) feeding this generation, or nullptr
-    const unsigned long long *src_count_ptr; // device scalar: number of sites in src_bank
+    // fission_bank source mode: the bank of the previous generation, one dense buffer per rank (this rank's own and,
+    // over NVLink, the peers'); word 0 of a buffer is its site count, the sites (cell << 32 | x bits) start at word
+    // kBankHeader.  Canonical order = rank order, history order inside a rank.  n_peers = 0: no bank yet (uniform source)
+    const unsigned long long *peer_bank[kMaxPeers];
+    uint32_t n_peers;
     unsigned long long *slots;               // [hist_end-hist_begin][bank_cap] sites produced, by history
     uint8_t *counts;                         // [hist_end-hist_begin]
     const float *k_cur;                      // device scalar: k of the previous generation
@@ -184,8 +189,9 @@ cudaError_t run_event_generation(const TransportParams &p, const EventBank &b, u
 uint32_t block_event_smem(const TransportParams &p, uint32_t slots);
 cudaError_t launch_block_event(const TransportParams &p, dim3 grid, dim3 block, uint32_t smem, uint32_t slots, cudaStream_t s);
 cudaError_t launch_bank_compact(const BankParams &p, cudaStream_t s);
-cudaError_t launch_bank_entropy(const unsigned long long *bank, const unsigned long long *count_ptr, uint32_t *hist, uint32_t N,
-                                double *entropy_out, unsigned long long *size_out, cudaStream_t s);
+cudaError_t launch_bank_histogram(const unsigned long long *bank, const unsigned long long *count_ptr, unsigned long long *hist, uint32_t N,
+                                  cudaStream_t s);
+cudaError_t launch_bank_entropy(const unsigned long long *hist, uint32_t N, double *entropy_out, unsigned long long *size_out, cudaStream_t s);
 cudaError_t prepare_transport(uint32_t smem_bytes, uint32_t G, uint32_t surf_mode, bool trace, bool bank);
 cudaError_t launch_finalize(const FinalizeParams &p, cudaStream_t s);
 cudaError_t launch_probe_logf(const float *x, float *out, uint32_t n, cudaStream_t s);

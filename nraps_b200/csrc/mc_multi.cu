@@ -1,7 +1,10 @@
 // Single-process multi-GPU driver over the generation-level C ABI (include/nraps_multi.h).
 // One host thread per device; NCCL over NVLink for the per-generation exchange:
-//   tally:  ncclAllReduce(sum) on uint64[G*N + 8]   (mirrors the ordered thread join, src/mc_code.rs:331-338)
-//   bank :  ncclAllGather of counts, then of the padded local banks, compacted in rank order
+//   tally:  ncclAllReduce(sum) on the uint64 tally buffer (mirrors the ordered thread join, src/mc_code.rs:331-338)
+//   bank :  nothing is exchanged.  Every device keeps the bank it compacted, peer access is enabled between all pairs,
+//           and the source kernel of the next generation loads each site from the device that banked it (NVLink);
+//           the all-reduce, issued after the local compaction, is the barrier in between and carries the bank's
+//           cell histogram along.
 #include <nccl.h>
 
 #include <algorithm>
@@ -41,10 +44,8 @@ struct Job {
 // device scratch and the stream of one rank, released on every return path
 struct RankScratch {
     cudaStream_t s = nullptr;
-    unsigned long long *d_counts = nullptr, *d_stage = nullptr, *d_gathered = nullptr, *d_global[2] = {nullptr, nullptr};
     ~RankScratch()
     {
-        cudaFree(d_counts); cudaFree(d_stage); cudaFree(d_gathered); cudaFree(d_global[0]); cudaFree(d_global[1]);
         if (s) cudaStreamDestroy(s);
     }
 };
@@ -83,52 +84,12 @@ void rank_main(Rank &me, Job &job, int rank, int world, const nraps_problem *p, 
     const uint64_t begin = H * (uint64_t)rank / (uint64_t)world, end = H * (uint64_t)(rank + 1) / (uint64_t)world;
     const bool bank = o->source_mode == NRAPS_SOURCE_FISSION_BANK;
 
-    uint64_t stage_cap = 0, global_cap[2] = {0, 0};
-    std::vector<unsigned long long> counts((size_t)world);
-    if (bank) RCU(cudaMalloc((void **)&sc.d_counts, (size_t)(world + 1) * sizeof(unsigned long long)));
-
     for (uint64_t gen = 0; gen < p->generations; ++gen) {
         RK(nraps_mc_transport(me.ctx, gen, begin, end - begin, s));
+        if (bank) RK(nraps_mc_bank_compact(me.ctx, gen, s)); // before the all-reduce: it orders every bank before any reader
         RNC(ncclAllReduce(tally, tally, words, ncclUint64, ncclSum, me.comm, s));
         RK(nraps_mc_finalize_generation(me.ctx, gen, s));
-        if (!bank) continue;
-        RK(nraps_mc_bank_compact(me.ctx, gen, s));
-        void *local = nullptr;
-        uint64_t n_local = 0;
-        RK(nraps_mc_bank_local(me.ctx, &local, &n_local, s));
-        RCU(cudaMemcpyAsync(sc.d_counts + world, &n_local, sizeof(n_local), cudaMemcpyHostToDevice, s));
-        RNC(ncclAllGather(sc.d_counts + world, sc.d_counts, 1, ncclUint64, me.comm, s));
-        RCU(cudaMemcpyAsync(counts.data(), sc.d_counts, (size_t)world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        RCU(cudaStreamSynchronize(s));
-        unsigned long long max_n = 0, total = 0;
-        for (unsigned long long c : counts) { max_n = std::max(max_n, c); total += c; }
-        if (total == 0) { RK(nraps_mc_bank_set_source(me.ctx, gen, nullptr, 0, s)); continue; }
-        if (max_n > stage_cap) { // padded staging: NCCL all-gather wants equal contributions
-            cudaFree(sc.d_stage); cudaFree(sc.d_gathered);
-            sc.d_stage = sc.d_gathered = nullptr;
-            stage_cap = 0;
-            RCU(cudaMalloc((void **)&sc.d_stage, max_n * sizeof(unsigned long long)));
-            RCU(cudaMalloc((void **)&sc.d_gathered, max_n * (size_t)world * sizeof(unsigned long long)));
-            stage_cap = max_n;
-        }
-        const int w = (int)(gen & 1u); // the bank read by generation gen+1 must outlive the next gather
-        if (total > global_cap[w]) {
-            cudaFree(sc.d_global[w]);
-            sc.d_global[w] = nullptr;
-            global_cap[w] = 0;
-            RCU(cudaMalloc((void **)&sc.d_global[w], total * sizeof(unsigned long long)));
-            global_cap[w] = total;
-        }
-        if (n_local) RCU(cudaMemcpyAsync(sc.d_stage, local, n_local * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-        RNC(ncclAllGather(sc.d_stage, sc.d_gathered, max_n, ncclUint64, me.comm, s));
-        unsigned long long off = 0;
-        for (int q = 0; q < world; ++q) { // rank order == canonical history order
-            if (counts[(size_t)q])
-                RCU(cudaMemcpyAsync(sc.d_global[w] + off, sc.d_gathered + (size_t)q * max_n, counts[(size_t)q] * sizeof(unsigned long long),
-                                    cudaMemcpyDeviceToDevice, s));
-            off += counts[(size_t)q];
-        }
-        RK(nraps_mc_bank_set_source(me.ctx, gen, sc.d_global[w], total, s));
+        if (bank) RK(nraps_mc_bank_advance(me.ctx, gen, s));
     }
     if (rank == 0) RK(nraps_mc_fetch(me.ctx, r, s));
     RCU(cudaStreamSynchronize(s));
@@ -154,6 +115,22 @@ extern "C" int nraps_mc_run_multi(const nraps_problem *p, const nraps_options *o
         oo.quiet = 1;
         ranks[(size_t)i].device = devs[(size_t)i];
         rc = nraps_mc_create(p, &oo, &ranks[(size_t)i].ctx);
+    }
+    if (rc == NRAPS_OK && o->source_mode == NRAPS_SOURCE_FISSION_BANK) {
+        // every device keeps its own bank; the others read it in place
+        const uint64_t shard_max = (p->histories + (uint64_t)num_gpus - 1) / (uint64_t)num_gpus;
+        std::vector<void *> bufs((size_t)num_gpus * 2, nullptr);
+        for (int i = 0; i < num_gpus && rc == NRAPS_OK; ++i) rc = nraps_mc_bank_reserve(ranks[(size_t)i].ctx, shard_max, &bufs[(size_t)i * 2]);
+        for (int i = 0; i < num_gpus && rc == NRAPS_OK; ++i) {
+            if (cudaSetDevice(devs[(size_t)i]) != cudaSuccess) { rc = NRAPS_ERR_CUDA; break; }
+            for (int j = 0; j < num_gpus; ++j) {
+                if (j == i) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devs[(size_t)j], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) { rc = NRAPS_ERR_CUDA; break; }
+            }
+        }
+        for (int i = 0; i < num_gpus && rc == NRAPS_OK; ++i) rc = nraps_mc_bank_peers(ranks[(size_t)i].ctx, num_gpus, i, bufs.data());
     }
     Job job;
     job.comms.assign((size_t)num_gpus, nullptr);

@@ -18,12 +18,22 @@ template <int TG, bool BANK>
 __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, uint4 *out)
 {
     __shared__ ulonglong2 s_jump[64];
+    __shared__ unsigned long long s_first[kMaxPeers + 1]; // first global site index of each rank's bank; [n_peers] = bank size
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_jump[i] = P.jump[i];
+    if (BANK && threadIdx.x == 0) {
+        // every rank's site count sits in word 0 of its bank buffer: read them where they are (NVLink for the peers)
+        unsigned long long acc = 0ull;
+        for (uint32_t r = 0; r < P.n_peers; ++r) {
+            s_first[r] = acc;
+            acc += *reinterpret_cast<const volatile unsigned long long *>(P.peer_bank[r]);
+        }
+        s_first[P.n_peers] = acc;
+    }
     __syncthreads();
     const int G = TG ? TG : (int)P.G, MG = (int)P.M * G;
     const float *chi = P.xs + 2 * MG;
     const uint64_t n = (uint64_t)(P.rows / P.G) * P.hist_shard;
-    const unsigned long long src_count = (BANK && P.src_bank) ? *P.src_count_ptr : 0ull;
+    const unsigned long long src_count = (BANK && P.n_peers) ? s_first[P.n_peers] : 0ull;
     const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRun;
     if (first >= n) return;
     // record i belongs to generation i / hist_shard of the launch and history hist_begin + i % hist_shard of it;
@@ -46,7 +56,12 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
         int cell;
         float x, mu;
         if (BANK && src_count) {
-            const unsigned long long site = __ldg(P.src_bank + (((unsigned long long)u * src_count) >> 32));
+            // site index -> (rank, offset): no gathered copy of the bank exists, the site is loaded from the rank that
+            // banked it (8 bytes over NVLink for 7 of 8 histories on a full box)
+            const unsigned long long idx = ((unsigned long long)u * src_count) >> 32;
+            uint32_t r = 0;
+            while (r + 1 < P.n_peers && idx >= s_first[r + 1]) ++r;
+            const unsigned long long site = __ldg(P.peer_bank[r] + kBankHeader + (idx - s_first[r]));
             cell = (int)(site >> 32);
             x = __uint_as_float((uint32_t)site);
             mu = fsub(fmul(2.0f, pcg32_unit(rng, P.rng_inc)), 1.0f);

@@ -7,6 +7,17 @@ summed across ranks with one ``all_reduce`` (NCCL over NVLink on GPUs), and
 every rank then runs the same finalize, so all ranks hold identical k / flux.
 Because history streams depend only on the global history index and the tally
 is an integer sum, the result is bit-identical for any world size.
+
+Two refinements (round 2):
+
+* uniform source: generations are independent (k cancels, src/mc_code.rs:346-351), so the all-reduce and the
+  finalize of generation g run on a side stream while generation g+1 is already transporting into a second tally
+  buffer (``run_generations_overlapped``): the collective leaves the critical path.
+* fission_bank source: nothing is gathered.  Every rank keeps the bank it compacted in a peer-mapped buffer, the
+  source kernel of generation g+1 turns a site index into (rank, offset) from the ranks' site counts and loads the
+  site over NVLink (``setup_bank_peers`` exchanges the CUDA IPC handles once).  The per-generation all-reduce --
+  issued after the local compaction -- is the only collective and doubles as the barrier between "every rank has
+  compacted bank g" and "any rank samples from it"; the bank's cell histogram rides in the same buffer.
 """
 from __future__ import annotations
 
@@ -20,6 +31,19 @@ def shard_range(histories: int, rank: int, world: int) -> tuple[int, int]:
     return begin, end - begin
 
 
+def resolve_site(index: int, counts: list[int]) -> tuple[int, int]:
+    """(rank, offset) of global site `index` of a bank held as one dense list per rank, canonical order = rank order.
+
+    Host mirror of the lookup in source_kernel (nraps_b200/csrc/mc_source.cu): the first rank r whose cumulative
+    count exceeds `index`; ranks with an empty bank are skipped."""
+    first = 0
+    for rank, n in enumerate(counts):
+        if index < first + n:
+            return rank, index - first
+        first += n
+    raise IndexError(f"site {index} of a bank of {first}")
+
+
 class GenerationEngine(Protocol):
     generations: int
     histories: int
@@ -28,76 +52,96 @@ class GenerationEngine(Protocol):
     def finalize_generation(self, gen: int, stream=None) -> None: ...
 
 
-def gather_bank(local_sites, world: int, all_gather_counts, all_gather_padded):
-    """All-gather variable-length site lists into one bank in rank order (= canonical history order).
-
-    `local_sites`: 1-D int64 tensor of this rank's sites; `all_gather_counts(n) -> list[int]`;
-    `all_gather_padded(padded_tensor, max_n) -> [world, max_n] tensor`.  NCCL all-gather needs equal
-    sizes, so every rank pads to the largest count and the valid prefixes are concatenated afterwards.
-    """
-    import torch
-
-    counts = all_gather_counts(int(local_sites.numel()))
-    max_n = max(counts)
-    if max_n == 0:
-        return local_sites[:0], counts
-    padded = torch.zeros(max_n, dtype=local_sites.dtype, device=local_sites.device)
-    padded[: local_sites.numel()] = local_sites
-    gathered = all_gather_padded(padded, max_n)
-    return torch.cat([gathered[r, : counts[r]] for r in range(world)]), counts
-
-
 def run_generations(engine: GenerationEngine, tally, rank: int, world: int, *, all_reduce=None, stream=None,
-                    first_gen: int = 0, n_gens: int | None = None, bank=None) -> None:
-    """Drive `n_gens` generations of `engine` for this rank.
+                    first_gen: int = 0, n_gens: int | None = None, bank: bool = False) -> None:
+    """Drive `n_gens` generations of `engine` for this rank, one after the other.
 
-    `tally` is the buffer the engine accumulates into (an int64 tensor);
-    `all_reduce(tally)` sums it in place across ranks (skipped when world == 1).
-    `bank(gen)`, when given (fission_bank source mode), compacts / gathers the
-    fission bank and installs it as the source of generation gen+1.
+    `tally` is the buffer the engine accumulates into (an int64 tensor); `all_reduce(tally)` sums it in place across
+    ranks (skipped when world == 1).  With ``bank`` (fission_bank source mode) the local bank is compacted *before*
+    the all-reduce -- the collective is then also the point after which every rank's bank of this generation is
+    complete -- and becomes the source of generation gen+1 after the finalize.
     """
     begin, count = shard_range(engine.histories, rank, world)
     last = engine.generations if n_gens is None else first_gen + n_gens
     for gen in range(first_gen, last):
         engine.transport(gen, begin, count, stream)
+        if bank:
+            engine.bank_compact(gen, stream)
         if world > 1:
             all_reduce(tally)
         engine.finalize_generation(gen, stream)
-        if bank is not None:
-            bank(gen)
+        if bank:
+            engine.bank_advance(gen, stream)
 
 
-def make_bank_callback(ctx, world: int, device: int, stream):
-    """bank(gen) for run_generations on GPUs: compact locally, all-gather over NCCL, install as next source."""
-    import torch
+class OverlappedReducer:
+    """Uniform source on GPUs: all-reduce + finalize of generation g on a side stream while g+1 transports.
+
+    Two tally tensors alternate.  Main stream: transport(g) into tally[g & 1].  Side stream: waits for that transport,
+    all-reduces the tensor, finalizes g.  Before transport(g+2) reuses tally[g & 1] the main stream waits for the
+    side stream's finalize of g.  Finalizes stay in generation order (one side stream), as k and the running flux
+    sums are sequential f32 accumulations."""
+
+    def __init__(self, ctx, world: int, device: int, main_stream=None):
+        import torch
+
+        self.torch, self.ctx, self.world = torch, ctx, world
+        dev = f"cuda:{device}"
+        self.tallies = [torch.zeros(ctx.n_words, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.main = main_stream if main_stream is not None else torch.cuda.current_stream()
+        self.side = torch.cuda.Stream(device=dev)
+        self.done = [None, None]   # side-stream events: finalize of the generation that last used the tensor
+        self.launched = 0
+
+    def step(self, gen: int, hist_begin: int, hist_count: int, before_transport=None, after_transport=None):
+        torch = self.torch
+        import torch.distributed as dist
+
+        t = self.tallies[gen & 1]
+        if self.done[gen & 1] is not None:
+            self.main.wait_event(self.done[gen & 1])
+        self.ctx.use_tally_tensor(t)
+        if before_transport is not None:
+            before_transport()
+        self.ctx.transport(gen, hist_begin, hist_count, self.main.cuda_stream)
+        if after_transport is not None:
+            after_transport()
+        ready = torch.cuda.Event()
+        ready.record(self.main)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            if self.world > 1:
+                dist.all_reduce(t)
+            # the context reads its current tally pointer at launch time: point it at this generation's tensor
+            self.ctx.use_tally_tensor(t)
+            self.ctx.finalize_generation(gen, self.side.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[gen & 1] = ev
+        self.launched += 1
+
+    def drain(self):
+        """Main stream waits for everything the side stream still owes."""
+        for ev in self.done:
+            if ev is not None:
+                self.main.wait_event(ev)
+
+
+def setup_bank_peers(ctx, rank: int, world: int, shard_max: int) -> None:
+    """fission_bank mode on several GPUs: make every rank's two bank buffers readable by every other rank.
+
+    Allocates the buffers peer-mappable, exchanges their CUDA IPC handles through the default process group and maps
+    the peers' buffers; afterwards no bank data moves except the 8-byte sites the source kernel asks for."""
     import torch.distributed as dist
 
-    from .api import _DevArray
-
-    dev = f"cuda:{device}"
-
-    def counts_fn(n):
-        t = torch.tensor([n], dtype=torch.int64, device=dev)
-        out = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(out, t)
-        return [int(v) for v in out.tolist()]
-
-    def padded_fn(padded, max_n):
-        out = torch.empty(world * max_n, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(out, padded)
-        return out.view(world, max_n)
-
-    def bank(gen):
-        ctx.bank_compact(gen, stream)
-        if world == 1:
-            ctx.bank_set_source(gen, None, stream)
-            return
-        ptr, n = ctx.bank_local(stream)
-        local = torch.as_tensor(_DevArray(ptr, n), device=dev) if n else torch.zeros(0, dtype=torch.int64, device=dev)
-        full, _ = gather_bank(local, world, counts_fn, padded_fn)
-        ctx.bank_set_source(gen, full.contiguous() if full.numel() else None, stream)
-
-    return bank
+    ctx.bank_reserve(shard_max)
+    if world == 1:
+        return
+    mine = ctx.bank_export()
+    handles: list = [None] * world
+    dist.all_gather_object(handles, mine)
+    ctx.bank_import(world, rank, b"".join(handles))
+    dist.barrier()  # nobody starts generation 0 before every mapping exists
 
 
 def monte_carlo_distributed(variables, xsdata, delta_x, meshid, fuel_indices, k_new: float = 1.0, *, generations=None,
@@ -110,15 +154,26 @@ def monte_carlo_distributed(variables, xsdata, delta_x, meshid, fuel_indices, k_
 
     rank, world = dist.get_rank(), dist.get_world_size()
     device = options.pop("device", torch.cuda.current_device())
+    bank = options.get("source_mode") == "fission_bank"
     with torch.cuda.device(device):
         ctx = MonteCarloContext(variables, xsdata, delta_x, meshid, fuel_indices, k_new, generations=generations,
                                 histories=histories, skip=skip, device=device, **options)
         try:
-            tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{device}")
-            ctx.use_tally_tensor(tally)
-            stream = torch.cuda.current_stream().cuda_stream
-            bank = make_bank_callback(ctx, world, device, stream) if options.get("source_mode") == "fission_bank" else None
-            run_generations(ctx, tally, rank, world, all_reduce=lambda t: dist.all_reduce(t), stream=stream, bank=bank)
-            return ctx.fetch(stream)
+            stream = torch.cuda.current_stream()
+            begin, count = shard_range(ctx.histories, rank, world)
+            if bank:
+                setup_bank_peers(ctx, rank, world, max(shard_range(ctx.histories, r, world)[1] for r in range(world)))
+                tally = torch.zeros(ctx.n_words, dtype=torch.int64, device=f"cuda:{device}")
+                ctx.use_tally_tensor(tally)
+                run_generations(ctx, tally, rank, world, all_reduce=lambda t: dist.all_reduce(t), stream=stream.cuda_stream, bank=True)
+            else:
+                red = OverlappedReducer(ctx, world, device, stream)
+                for gen in range(ctx.generations):
+                    red.step(gen, begin, count)
+                red.drain()
+            res = ctx.fetch(stream.cuda_stream)
+            if world > 1:
+                dist.barrier()  # peers may still be reading this rank's bank buffers: close nothing before all are done
+            return res
         finally:
             ctx.close()

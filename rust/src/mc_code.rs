@@ -24,6 +24,7 @@ struct NrapsOptions {
     kernel_variant: i32, threads_per_block: i32, blocks_per_sm: i32, chunk: i32, quiet: i32,
     bank_cap: i32, spawn_batch: i32, walk_cap: i32, slots_per_thread: i32,
     max_flights: u64,
+    profile_phases: i32, reserved0: i32,
 }
 
 #[repr(C)]

@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-from nraps_b200.dist import gather_bank, run_generations, shard_range  # noqa: E402
+from nraps_b200.dist import resolve_site, run_generations, shard_range  # noqa: E402
 
 
 def test_shard_ranges_tile_the_generation():
@@ -24,30 +24,36 @@ def test_shard_ranges_tile_the_generation():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
 
 
-def test_gather_bank_concatenates_in_rank_order():
-    """Variable-length site lists -> one bank in rank (= history) order; simulated 3-rank all-gather."""
-    import torch
+def test_site_lookup_is_the_rank_ordered_concatenation():
+    """The source kernel never sees a gathered bank: it maps a global site index to (rank, offset) from the ranks'
+    site counts.  That map must be exactly the rank-ordered concatenation of the local banks -- what makes generation
+    g+1 independent of the number of GPUs -- including ragged and empty local banks."""
+    for counts in ([5, 0, 3], [0, 4], [7, 0], [1, 1, 1, 1, 1, 1, 1, 1], [0, 0, 9, 0]):
+        flat = [(r, i) for r, n in enumerate(counts) for i in range(n)]
+        assert [resolve_site(s, counts) for s in range(len(flat))] == flat
+        with pytest.raises(IndexError):
+            resolve_site(len(flat), counts)
+    # the device's index draw: site = (u32 * B) >> 32 covers [0, B) and nothing else
+    B = sum([5, 0, 3])
+    assert {(u * B) >> 32 for u in (0, 1, 2**31, 2**32 - 1)} <= set(range(B)) and ((2**32 - 1) * B) >> 32 == B - 1
 
-    locals_ = [torch.arange(5, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), torch.arange(100, 103, dtype=torch.int64)]
-    counts = [t.numel() for t in locals_]
-    pads = {}
 
-    def counts_fn(n):
-        return counts
+def test_bank_protocol_order():
+    """fission_bank mode: the local compaction comes before the all-reduce (the collective is the barrier after which
+    every rank's bank is complete) and the bank becomes the next source only after the finalize."""
+    calls = []
 
-    def make_padded_fn(rank):
-        def fn(padded, max_n):
-            pads[rank] = padded
-            rows = [torch.zeros(max_n, dtype=torch.int64) for _ in range(3)]
-            for r, t in enumerate(locals_):
-                rows[r][: t.numel()] = t
-            return torch.stack(rows)
-        return fn
+    class Engine:
+        generations, histories = 2, 10
 
-    for rank in range(3):
-        full, got_counts = gather_bank(locals_[rank], 3, counts_fn, make_padded_fn(rank))
-        assert got_counts == counts and full.tolist() == [0, 1, 2, 3, 4, 100, 101, 102]
-        assert pads[rank].numel() == 5 and pads[rank][: counts[rank]].tolist() == locals_[rank].tolist()
+        def transport(self, gen, b, n, stream=None): calls.append(("transport", gen, b, n))
+        def bank_compact(self, gen, stream=None): calls.append(("compact", gen))
+        def finalize_generation(self, gen, stream=None): calls.append(("finalize", gen))
+        def bank_advance(self, gen, stream=None): calls.append(("advance", gen))
+
+    run_generations(Engine(), None, 1, 2, all_reduce=lambda t: calls.append(("all_reduce",)), bank=True)
+    assert calls == [("transport", 0, 5, 5), ("compact", 0), ("all_reduce",), ("finalize", 0), ("advance", 0),
+                     ("transport", 1, 5, 5), ("compact", 1), ("all_reduce",), ("finalize", 1), ("advance", 1)]
 
 
 class OracleEngine:
@@ -123,47 +129,3 @@ def test_two_rank_gloo_equals_single_rank(tmp_path):
     run_generations(eng, tally, 0, 1)
     assert np.array_equal(np.stack(eng.per_gen), r0)  # and it is the single-rank tally, bit for bit
     assert r0.any()
-
-
-def _bank_worker(rank, world, port, out_dir):
-    import torch
-    import torch.distributed as dist
-
-    sys.path.insert(0, ROOT)
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-
-    def counts_fn(n):  # same shape of exchange as make_bank_callback's NCCL version
-        out = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(out, torch.tensor([n], dtype=torch.int64))
-        return [int(t.item()) for t in out]
-
-    def padded_fn(padded, max_n):
-        out = [torch.zeros(max_n, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(out, padded)
-        return torch.stack(out)
-
-    banks = []
-    for gen, sizes in enumerate([(5, 3), (0, 4), (7, 0), (0, 0)]):  # ragged, one side empty, both empty
-        local = torch.arange(sizes[rank], dtype=torch.int64) + 1000 * rank + 100 * gen
-        full, counts = gather_bank(local, world, counts_fn, padded_fn)
-        assert counts == list(sizes)
-        banks.append(full.numpy().copy())
-    np.save(os.path.join(out_dir, f"bank{rank}.npy"), np.concatenate(banks))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-@pytest.mark.timeout(300)
-def test_two_rank_gloo_bank_gather_is_rank_ordered_and_identical_everywhere(tmp_path):
-    """The fission-bank exchange of nraps_b200.dist over real collectives (gloo, world size 2): every rank ends with
-    the same bank, rank 0's sites first -- what makes generation g+1 independent of the number of GPUs."""
-    import torch.multiprocessing as mp
-
-    port = _free_port()
-    mp.spawn(_bank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    b0, b1 = np.load(tmp_path / "bank0.npy"), np.load(tmp_path / "bank1.npy")
-    assert np.array_equal(b0, b1)
-    want = np.r_[np.arange(5), 1000 + np.arange(3), 1100 + np.arange(4), 200 + np.arange(7)]
-    assert np.array_equal(b0, want)

@@ -352,7 +352,7 @@ def test_fission_bank_contents_and_sharding():
             ctx.bank_compact(gen)
             if gen == 1:
                 bank = ctx.read_bank()
-            ctx.bank_set_source(gen)
+            ctx.bank_advance(gen)
         res = ctx.fetch()
     assert np.array_equal(bank, want.bank_sites)
     assert np.array_equal(res.bank_sizes, want.bank_sizes)
@@ -390,7 +390,8 @@ def _dist_worker(rank, world, port, out_dir, mode):
 
 @pytest.mark.parametrize("mode", ["uniform_fuel", "fission_bank"])
 def test_two_gpus_equal_one_gpu_bit_for_bit(tmp_path, mode):
-    """History sharding + NCCL all-reduce (+ bank all-gather): identical to the single-GPU run on every rank."""
+    """History sharding + NCCL all-reduce (uniform source: overlapped with the next generation; fission bank: sites
+    loaded from the peers' banks over NVLink, nothing gathered): identical to the single-GPU run on every rank."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -536,8 +537,8 @@ def test_synthetic_shapes_bit_exact(M, G, pins, mpfr, mpwr, bl, br, tracking):
 
 @pytest.mark.parametrize("extra", [[], ["--source", "fission_bank"], ["--tracking", "woodcock", "--source", "fission_bank"]])
 def test_native_nccl_driver_two_gpus_equals_one(tmp_path, extra):
-    """`nraps --gpus 2` (single process, one host thread per GPU, ncclAllReduce / ncclAllGather inside the C ABI
-    library) writes byte-identical CSV files to the single-GPU run."""
+    """`nraps --gpus 2` (single process, one host thread per GPU, ncclAllReduce inside the C ABI library, fission bank
+    read in place through peer access) writes byte-identical CSV files to the single-GPU run."""
     import subprocess
 
     import torch

@@ -150,6 +150,7 @@ struct nraps_mc_ctx {
     SmemLayout layout{};
     uint32_t smem_total = 0;       // dynamic shared memory of the transport launch
     uint32_t surf_mode = SURF_SPLIT; // tally placement of the surface kernel (mc_internal.h)
+    uint32_t skip_walk = 0;          // closed-form strides through long segments (set when the mean segment is >= 16 cells)
     uint32_t grid = 0, block = 0, blocks_per_sm = 0, chunk = 0, max_flights = 0;
     uint32_t geo_grid[2] = {0, 0}, geo_block[2] = {0, 0}; // launch geometry of the plain / trace instantiation
 
@@ -403,7 +404,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     if (surface_fused) CU(cudaMemsetAsync(c->d_diff, 0, (uint64_t)nb * c->G * c->N * sizeof(unsigned long long), s));
 
     TransportParams P{};
-    P.segw = c->d_segw; P.diff = c->d_diff; P.surf_mode = c->surf_mode;
+    P.segw = c->d_segw; P.diff = c->d_diff; P.surf_mode = c->surf_mode; P.skip_walk = c->skip_walk; P.length = c->length;
     P.edges = c->d_edges; P.runb = c->d_runb; P.matid = c->d_matid; P.fuel = c->d_fuel; P.xs = c->d_xs; P.jump = c->d_jump;
     P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF; P.NB = c->NB; P.bucket = c->d_bucket; P.inv_h = c->inv_h; P.big = c->big;
     P.boundl = c->boundl; P.boundr = c->boundr; P.dx_fuel = c->dx_fuel;
@@ -418,7 +419,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;
     P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)std::min(c->opt.spawn_batch, 32) : (c->woodcock ? 2u : 1u);
-    P.walk_cap = c->opt.walk_cap > 0 ? (uint32_t)c->opt.walk_cap : 0x7fffffffu;
+    P.walk_cap = 0x7fffffffu; // round 1's regrouping cap; the surface kernel walks to the end of the segment now
     P.scatter_mode = c->opt.scatter_mode; P.stale_xs = c->opt.stale_xs;
     P.n_peers = (c->bank_mode && c->bank_src >= 0) ? (uint32_t)c->bank_world : 0u;
     for (uint32_t r = 0; r < P.n_peers; ++r) P.peer_bank[r] = c->peer_bank[c->bank_src][r];
@@ -459,7 +460,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
             // maximum, so that a second live context with a smaller image cannot lower it under this one
             CU(c->woodcock ? prepare_woodcock(kMaxSmem, c->G, trace, c->bank_mode)
                            : prepare_transport(kMaxSmem, c->G, c->surf_mode, trace, c->bank_mode));
-        // auto geometry: 2 x 576 threads per SM (36 warps) when the instantiation's registers allow it, else 2 x 512;
+        // auto geometry: 2 x 640 threads per SM (40 warps) when the instantiation's registers allow it, else 2 x 576 or 2 x 512;
         // ncu: the kernels are issue bound and the extra warps buy ~3 % (gpurun sweep, profiles/r1_sweeps.txt)
         uint32_t block = c->block, bps = c->blocks_per_sm;
         if (c->opt.threads_per_block <= 0 && c->opt.blocks_per_sm <= 0 && bps == 2) {
@@ -467,7 +468,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
                 return c->woodcock ? occupancy_woodcock(c->G, c->big, trace, c->bank_mode, b, c->smem_total)
                                    : occupancy_transport(c->G, c->surf_mode, trace, c->bank_mode, b, c->smem_total);
             };
-            block = occ(576) >= 2 ? 576u : 512u;
+            block = occ(640) >= 2 ? 640u : (occ(576) >= 2 ? 576u : 512u);
         }
         c->geo_block[ti] = block;
         c->geo_grid[ti] = (uint32_t)c->sm_count * bps;
@@ -661,6 +662,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     // changes by an ulp where the position crosses a power of two: a material run is one segment, or two around such a
     // point.  Inside a segment x - edge is the same number for every cell crossed completely (mc_transport.cu).
     std::vector<uint2> segw(N);
+    uint32_t n_segments = 0;
     for (uint32_t i = 0; i < N;) {
         const float w = edges[i + 1] - edges[i];
         uint32_t wbits;
@@ -671,9 +673,16 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
             if (std::memcmp(&wj, &w, sizeof(float)) != 0) break;
             ++j;
         }
-        for (uint32_t q = i; q < j; ++q) segw[q] = make_uint2(i | (j << 16), wbits);
+        // what the kernel needs of the segment [i, j): the edge reference at which a walk through it stops -- the neutron
+        // has then entered cell j (going right: the edge ahead of it is j + 1) or cell i - 1 (going left: edge i - 1).
+        // The domain's boundary cells are never entered by the walk loop (the wall logic runs before it), so a segment
+        // that contains one stops there: entering cell N - 1 means edge N ahead, entering cell 0 means edge 0.
+        const uint32_t stop_right = std::min(j, N - 1) + 1, stop_left = i > 0 ? i - 1 : 0;
+        for (uint32_t q = i; q < j; ++q) segw[q] = make_uint2(stop_left | (stop_right << 16), wbits);
+        ++n_segments;
         i = j;
     }
+    c->skip_walk = (o->walk_cap != -2 && N >= 16u * n_segments) ? 1u : 0u; // walk_cap = -2: never stride (tests, comparisons)
     std::vector<float> xs(xs_floats(M, G));
     float *inv_sigtr = xs.data(), *p_abs = inv_sigtr + MG, *chi_cdf = p_abs + MG, *nusigf = chi_cdf + MG, *sigtr = nusigf + MG,
           *scat_cdf = sigtr + MG, *inv_maj = scat_cdf + MG * G * G;

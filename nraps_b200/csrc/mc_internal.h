@@ -109,6 +109,8 @@ struct TransportParams {
     const uint2 *segw;       // [N] surface kernel: {segment lo | hi << 16, width bits} of each cell
     unsigned long long *diff; // [rows*N] surface kernel: difference array of the full-cell scores (global, summed over blocks)
     uint32_t surf_mode;      // SURF_SPLIT / SURF_UNIFIED / SURF_GLOBAL
+    uint32_t skip_walk;      // surface kernel: stride over the surely-crossed cells of a segment in closed form (fine meshes)
+    float length;            // right edge of the slab (bounds the rounding of x + ds)
     uint32_t M, G, N, NF, NB, big;
     uint32_t rows;       // tally rows of this launch = batch * G: generations gen .. gen+batch-1 share the launch
     uint64_t hist_shard; // histories of one generation in this launch (hist_end - hist_begin = batch * hist_shard)

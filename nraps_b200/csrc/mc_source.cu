@@ -43,6 +43,39 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
     uint64_t base = jump_ahead(P.rng_state, (uint64_t)gen_local * P.hist_total + P.hist_begin + in_gen, s_jump);
     const ulonglong2 J1 = s_jump[0];
     const uint64_t last = first + kRun < n ? first + kRun : n;
+    if (BANK && src_count) {
+        // Bank source (never batched: one generation per launch).  No gathered copy of the bank exists: a site index is
+        // resolved to (rank, offset) and the 8-byte site is loaded from the rank that banked it -- over NVLink for 7 of
+        // 8 histories on a full box.  The loads of the thread's kRun histories are issued together, before anything is
+        // done with them: a remote load takes microseconds, and the kernel is bound by how many are in flight.
+        unsigned long long site[kRun];
+        uint64_t b = base;
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) {
+            uint64_t rng = b;
+            b = J1.x * b + J1.y;
+            const uint32_t u = pcg32_next(rng, P.rng_inc);
+            const unsigned long long idx = ((unsigned long long)u * src_count) >> 32;
+            uint32_t r = 0;
+            while (r + 1 < P.n_peers && idx >= s_first[r + 1]) ++r;
+            site[j] = first + j < last ? __ldg(P.peer_bank[r] + kBankHeader + (idx - s_first[r])) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) {
+            const uint64_t i = first + j;
+            if (i >= last) break;
+            uint64_t rng = base;
+            base = J1.x * base + J1.y;
+            (void)pcg32_next(rng, P.rng_inc); // the site draw, already used above
+            const int cell = (int)(site[j] >> 32);
+            const float x = __uint_as_float((uint32_t)site[j]);
+            const float mu = fsub(fmul(2.0f, pcg32_unit(rng, P.rng_inc)), 1.0f);
+            const int g = search_cdf_global<TG>(chi + __ldg(P.matid + cell) * G, G, pcg32_unit(rng, P.rng_inc));
+            out[2 * i] = make_uint4(__float_as_uint(x), __float_as_uint(mu), (uint32_t)cell | ((uint32_t)g << 16), gen_local * P.G);
+            out[2 * i + 1] = make_uint4((uint32_t)rng, (uint32_t)(rng >> 32), 0u, 0u);
+        }
+        return;
+    }
     for (uint64_t i = first; i < last; ++i) {
         if (in_gen == P.hist_shard) { // the run crosses into the next generation of the batch
             in_gen = 0;
@@ -53,24 +86,10 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
         uint64_t rng = base;
         base = J1.x * base + J1.y; // stream of the next history
         const uint32_t u = pcg32_next(rng, P.rng_inc);
-        int cell;
-        float x, mu;
-        if (BANK && src_count) {
-            // site index -> (rank, offset): no gathered copy of the bank exists, the site is loaded from the rank that
-            // banked it (8 bytes over NVLink for 7 of 8 histories on a full box)
-            const unsigned long long idx = ((unsigned long long)u * src_count) >> 32;
-            uint32_t r = 0;
-            while (r + 1 < P.n_peers && idx >= s_first[r + 1]) ++r;
-            const unsigned long long site = __ldg(P.peer_bank[r] + kBankHeader + (idx - s_first[r]));
-            cell = (int)(site >> 32);
-            x = __uint_as_float((uint32_t)site);
-            mu = fsub(fmul(2.0f, pcg32_unit(rng, P.rng_inc)), 1.0f);
-        } else {
-            cell = __ldg(P.fuel + __umulhi(u, P.NF));
-            const float xi_pos = pcg32_unit(rng, P.rng_inc);
-            mu = fsub(fmul(2.0f, pcg32_unit(rng, P.rng_inc)), 1.0f);
-            x = fadd(__ldg(P.edges + cell), fmul(xi_pos, P.dx_fuel));
-        }
+        const int cell = __ldg(P.fuel + __umulhi(u, P.NF));
+        const float xi_pos = pcg32_unit(rng, P.rng_inc);
+        const float mu = fsub(fmul(2.0f, pcg32_unit(rng, P.rng_inc)), 1.0f);
+        const float x = fadd(__ldg(P.edges + cell), fmul(xi_pos, P.dx_fuel));
         const int g = search_cdf_global<TG>(chi + __ldg(P.matid + cell) * G, G, pcg32_unit(rng, P.rng_inc));
         out[2 * i] = make_uint4(__float_as_uint(x), __float_as_uint(mu), (uint32_t)cell | ((uint32_t)g << 16), gen_local * P.G);
         out[2 * i + 1] = make_uint4((uint32_t)rng, (uint32_t)(rng >> 32), 0u, 0u);

@@ -58,6 +58,45 @@ static __device__ __forceinline__ void bin_sub(uint32_t ref, uint32_t hi_off, un
     if (borrow | wide) reds_add(ref + hi_off, 0u - (h + (borrow ? 1u : 0u)));
 }
 
+// Cells of a segment that can be taken in one stride.  The walk changes ds by fl(ds -+ w) per cell; with a = |ds| in
+// the binade [2^e, 2^(e+1)), grid U = 2^(e-23), and w not a rounding tie on that grid, every such step subtracts the
+// same multiple q U from a (w rounded to the grid) as long as the exact difference stays inside the binade, so after j
+// steps the mantissa is m - j q -- bit for bit what j sequential subtractions give.  j is limited to the cells whose
+// |ds| stays >= lim (their collision test cannot fail), to the binade and to nmax; it is deliberately rounded down
+// (a shorter stride is still exact).  Checked against the cell-by-cell loop on 3.6e7 random walks over six meshes
+// before it went into the kernel (tools/closed_form_walk.c).
+static __device__ __forceinline__ uint32_t skip_cells(float a, uint32_t mw, int ewb, float lim, uint32_t nmax, float &out)
+{
+    const uint32_t ia = __float_as_uint(a);
+    const int eb = (int)(ia >> 23);
+    const uint32_t m = (ia & 0x7fffffu) | 0x800000u;
+    const int sh = eb - ewb;
+    out = a;
+    if (sh < 0 || sh > 24 || m <= 0x800000u) return 0u;
+    uint32_t q = mw >> sh;
+    const uint32_t rem = mw & ((1u << sh) - 1u), half = (1u << sh) >> 1;
+    if (sh && rem == half) {
+        // tie: round to even.  Once the mantissa is even it stays even and every step subtracts the even one of
+        // {q, q + 1}; an odd mantissa is left to the caller's one exact subtraction, which makes it even
+        if (m & 1u) return 0u;
+        q += q & 1u;
+    } else if (rem > half) q += 1u;
+    const float ls = fmul(lim, __uint_as_float((uint32_t)(277 - eb) << 23)); // lim / U
+    if (!(ls < 16777216.0f)) return 0u;
+    const uint32_t mt = (uint32_t)__float2uint_ru(ls);
+    if (m < mt) return 0u;
+    float rq; // ~1/q, biased low by far more than the error of the approximate reciprocal
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(__uint2float_rn(q)));
+    rq = fmul(rq, 0.99999f);
+    const uint32_t j1 = __float2uint_rz(fmul(__uint2float_rn(m - mt), rq)) + 1u;
+    const uint32_t j2 = __float2uint_rz(fmul(__uint2float_rn(m - 0x800001u), rq));
+    uint32_t j = j1 < j2 ? j1 : j2;
+    if (j > nmax) j = nmax;
+    const uint32_t mr = m - j * q;
+    out = __uint_as_float(((uint32_t)eb << 23) | (mr & 0x7fffffu));
+    return j;
+}
+
 // Where the tallies of this block live (see SurfLayout, mc_internal.h).
 template <int MODE> struct Tally {
     uint32_t diff_base, direct_base, diff_hi_off, direct_hi_off; // shared byte addresses / offsets
@@ -102,6 +141,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool BIG = (MODE == SURF_GLOBAL);
+    constexpr bool kSkip = (MODE != SURF_SPLIT); // meshes fine enough to leave SURF_SPLIT have segments worth striding over
     const int G = TG ? TG : (int)P.G;
     const int M = (int)P.M, N = (int)P.N;
     const SurfLayout L = make_surface_layout(P.M, P.G, P.N, MODE, P.rows);
@@ -223,7 +263,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
             if (!fate) {
                 // ------------ WALK: cell by cell inside one segment
                 rc = make_recip(mu);
-                // {first cell | one past the last cell << 16, width bits} of the segment `cell` lies in
+                // {stop edge going left | stop edge going right << 16, width bits} of the segment `cell` lies in
                 const uint2 sw = BIG ? __ldg(P.segw + cell) : make_uint2(lds_u32(segw_base + 8u * (uint32_t)cell), lds_u32(segw_base + 8u * (uint32_t)cell + 4u));
                 int fwd = mu >= 0.0f ? 1 : 0;
                 int dir = 2 * fwd - 1;
@@ -267,13 +307,6 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     }
                 }
                 if (in_loop) {
-                    // crossings this trip: to the end of the segment, at most `walk_cap` (a longer walk is suspended --
-                    // pending -- and resumed on the next trip, so that the lanes that finished early do not wait for
-                    // the longest flight of the warp), and not into the boundary cell
-                    const int seg_exit = fwd ? (int)(sw.x >> 16) : (int)(sw.x & 0xffffu) - 1;
-                    int steps = min((seg_exit - cell) * dir, (int)P.walk_cap);
-                    const int to_wall = (wall - cell) * dir;
-                    if (to_wall < steps) steps = to_wall;
                     // the cell the flight starts in: an arbitrary part of it is crossed (src/mc_code.rs:171-181)
                     end = fadd(x, ds);
                     const float edge0 = ld_edge(e_addr);
@@ -284,10 +317,14 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                         T.direct(row0 + g, cell, fabsf(fast_div(t0, rc)));
                         ds = fadd(ds, t0);
                         const int stride = kStep * dir;
-                        const uint32_t e_first = e_addr;
-                        const uint32_t e_stop = e_first + (uint32_t)(stride * steps); // e_addr once `steps` edges are crossed
+                        // where this walk stops if no collision does: the edge reference once the neutron has entered
+                        // the first cell that is not its segment's -- or the boundary cell, which the block above handles
+                        // on the next trip (both folded into one per-cell table entry by the host)
+                        const uint32_t e_stop = edges_base + (uint32_t)kStep * (fwd ? (sw.x >> 16) : (sw.x & 0xffffu));
+                        const int cell0 = cell;
                         float xc = edge0;
                         e_addr += (uint32_t)stride;
+                        bool hit = false;
                         if (e_addr != e_stop) {
                             // Cells crossed completely: x - edge is -+w for every one of them, w the segment's width,
                             // so the loop carries ds, the position and the edge address only.  One step = the
@@ -296,26 +333,55 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                             const float tn = fwd ? -w : w;
                             auto step = [&]() -> bool {
                                 end = fadd(xc, ds);
-                                if (!(fabsf(fsub(end, xc)) > w)) return false; // collision at `end` inside this cell
+                                if (!(fabsf(fsub(end, xc)) > w)) { hit = true; return false; } // collision at `end` inside this cell
                                 ds = fadd(ds, tn);
                                 xc = ld_edge(e_addr);
                                 e_addr += (uint32_t)stride;
                                 return e_addr != e_stop;
                             };
-                            while (step() && step() && step() && step()) {} // one back branch per four crossings
-                            const int n_full = (int)((uint32_t)((int)(e_addr - e_first) * dir) / (uint32_t)kStep) - 1; // cells crossed completely
-                            if (n_full > 0) // [cell+1, cell+n_full] going right, [cell-n_full, cell-1] going left
-                                T.range(row0 + g, fwd ? cell + 1 : cell - n_full, n_full, fabsf(fast_div(tn, rc)));
+                            if (kSkip && P.skip_walk) {
+                                // Fine meshes: a flight crosses tens of cells of one segment.  While |ds| is surely large
+                                // enough for the collision test to pass (|ds| >= w + the rounding of x + ds), the only
+                                // thing a crossing changes is ds <- fl(ds -+ w), and inside one binade of |ds| that is an
+                                // exact integer recurrence on the mantissa (skip_cells above): those cells are taken in
+                                // one stride, in registers.  One real subtraction carries |ds| over what the recurrence
+                                // does not cover (the change of binade, an odd mantissa under a rounding tie), then the
+                                // next stride; the position is read once at the end and the exact loop finishes the walk.
+                                const uint32_t mw = (sw.y & 0x7fffffu) | 0x800000u;
+                                const int ewb = (int)(sw.y >> 23);
+                                float a = fabsf(ds);
+                                const float lim = fadd(w, fmul(fadd(P.length, a), 4.76837158203125e-07f)); // w + 2^-21 (L + |ds|)
+                                const float w4 = fmul(w, 4.0f);
+                                const uint32_t total = (uint32_t)((int)(e_stop - e_addr) * dir) / (uint32_t)kStep; // cells to the stop
+                                uint32_t done = 0u;
+#pragma unroll 1
+                                for (int round = 0; round < 8; ++round) {
+                                    const uint32_t rem = total - done;
+                                    if (rem < 4u || !(a > w4)) break; // a handful of cells left: the exact loop is cheaper
+                                    float an;
+                                    done += skip_cells(a, mw, ewb, lim, rem, an);
+                                    a = an;
+                                    if (done == total || !(a >= lim)) break;
+                                    a = fsub(a, w); // |fl(ds -+ w)|: this cell too is surely crossed
+                                    done += 1u;
+                                }
+                                if (done) {
+                                    ds = copysignf(a, ds);
+                                    e_addr += (uint32_t)(stride * (int)done);
+                                    xc = ld_edge(e_addr - (uint32_t)stride);
+                                }
+                            }
+                            if (!hit && e_addr != e_stop)
+                                while (step() && step() && step() && step()) {} // one back branch per four crossings
                         }
-                        const int n_cross = (int)((uint32_t)((int)(e_addr - e_first) * dir) / (uint32_t)kStep);
-                        if (e_addr != e_stop) ev = EV_COLLIDE;
+                        // the cell the neutron is in now: the edge ahead of it is e_addr
+                        cell = (int)((e_addr - edges_base) / (uint32_t)kStep) - fwd;
+                        const int n_full = (cell - cell0) * dir - 1; // cells crossed completely
+                        if (n_full > 0) // [cell0+1, cell-1] going right, [cell+1, cell0-1] going left
+                            T.range(row0 + g, fwd ? cell0 + 1 : cell + 1, n_full, fabsf(fast_div(fwd ? -__uint_as_float(sw.y) : __uint_as_float(sw.y), rc)));
+                        ev = hit ? EV_COLLIDE : EV_SEGEXIT;
                         x = xc; // x after a crossing is the edge just crossed (src/mc_code.rs:72,77)
-                        cell += n_cross * dir;
-                        if (TRACE) h_cross += (uint32_t)n_cross;
-                        if (ev == EV_NONE) {
-                            if (cell == seg_exit) ev = EV_SEGEXIT;
-                            else pending = true;
-                        }
+                        if (TRACE) h_cross += (uint32_t)(n_full + 1);
                     }
                 }
             }
@@ -330,7 +396,9 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                         mat = m2;
                         xsg = g;
                     } else {
-                        pending = true; // next segment of the same material run (the cell width changed): the flight goes on
+                        // same material: the next segment of the run (the cell width changed by an ulp), or the
+                        // boundary cell, which the walk never enters on its own: the flight goes on next trip
+                        pending = true;
                     }
                 }
             }

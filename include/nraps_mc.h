@@ -82,8 +82,10 @@ typedef struct nraps_options {
     int32_t bank_cap;              /* fission_bank: sites kept per history, 1..255; 0 = 8 */
     int32_t spawn_batch;           /* refill a warp's dead lanes only once this many are dead (0 = auto); block_event variant:
                                     * walks predicted to cross >= this many cells form the "long" list (0 = split by run length) */
-    int32_t walk_cap;              /* accepted and ignored since round 2 (round 1 regrouped a warp after this many crossings;
-                                    * with range-update tallies a lane walks to the end of its segment) */
+    int32_t walk_cap;              /* tuning knob of the surface kernel's walk.  Round 1: crossings before a warp regroups (gone:
+                                    * with range-update tallies a lane walks to the end of its segment).  Round 2, fine meshes:
+                                    * > 0 = closed-form strides only while |ds| > walk_cap cell widths (0 = auto, 6);
+                                    * -2 = never stride (cell-by-cell loop only).  No value changes a result bit. */
     int32_t slots_per_thread;      /* block_event variant: neutrons banked per thread of a block; 0 = 3 (was reserved1) */
     uint64_t max_flights;          /* per-history safety cap; 0 = 1<<24               */
     int32_t profile_phases;        /* 1 = time the phases of every generation with CUDA events (nraps_mc_phase_ms); the host

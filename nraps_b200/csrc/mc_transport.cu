@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                                 const int ewb = (int)(sw.y >> 23);
                                 float a = fabsf(ds);
                                 const float lim = fadd(w, fmul(fadd(P.length, a), 4.76837158203125e-07f)); // w + 2^-21 (L + |ds|)
-                                const float w4 = fmul(w, 4.0f);
+                                const float w4 = fmul(w, P.stride_min);
                                 const uint32_t total = (uint32_t)((int)(e_stop - e_addr) * dir) / (uint32_t)kStep; // cells to the stop
                                 uint32_t done = 0u;
 #pragma unroll 1

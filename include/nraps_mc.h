@@ -177,18 +177,20 @@ int nraps_mc_trace(nraps_mc_ctx *ctx, uint64_t gen, uint64_t hist_begin, uint64_
  * Several GPUs: no gathered copy of the bank exists.  Each rank keeps its bank where it compacted it and the source
  * kernel of every rank resolves a site index to (rank, offset) from the ranks' site counts -- word 0 of each bank buffer
  * -- and loads the 8-byte site from the rank that banked it, over NVLink.  Set up once, before generation 0:
- *   nraps_mc_bank_reserve   allocate the two buffers peer-mappable, for shards up to `shard_histories` histories
- *   one process per GPU:    nraps_mc_bank_export (2 IPC handles) -> exchange them -> nraps_mc_bank_import on every rank
- *   one process, N devices: enable peer access, pass every rank's two buffer pointers to nraps_mc_bank_peers
+ *   nraps_mc_bank_reserve   allocate the two buffers mappable by the other ranks, for shards up to `shard_histories`
+ *   one process per GPU:    reserve(.., NULL) -> nraps_mc_bank_export (2 tickets) -> exchange them -> nraps_mc_bank_import
+ *                           (cuMemCreate allocations shared as file descriptors, 2 MB pages on both sides; the legacy
+ *                           cudaIpc mappings of round 2's first version thrashed the TLB under random reads)
+ *   one process, N devices: reserve(.., buffers) -> enable peer access -> every rank's two pointers to nraps_mc_bank_peers
  */
-#define NRAPS_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
+#define NRAPS_IPC_HANDLE_BYTES 64 /* one exported bank buffer: {magic, pid, fd, size}, padded */
 #define NRAPS_MAX_RANKS 8         /* GPUs of one NVSwitch box */
 int nraps_mc_bank_compact(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
 int nraps_mc_bank_advance(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
 /* device pointer + count of the dense local bank of the last compaction (synchronous; tests) */
 int nraps_mc_bank_local(nraps_mc_ctx *ctx, void **device_sites, uint64_t *count, void *stream);
-int nraps_mc_bank_reserve(nraps_mc_ctx *ctx, uint64_t shard_histories, void **device_buffers /* [2] out, may be NULL */);
-int nraps_mc_bank_export(nraps_mc_ctx *ctx, void *handles /* [2][NRAPS_IPC_HANDLE_BYTES] out */);
+int nraps_mc_bank_reserve(nraps_mc_ctx *ctx, uint64_t shard_histories, void **device_buffers /* [2] out; NULL = for other processes */);
+int nraps_mc_bank_export(nraps_mc_ctx *ctx, void *handles /* [2][NRAPS_IPC_HANDLE_BYTES] out; valid while the context lives */);
 int nraps_mc_bank_import(nraps_mc_ctx *ctx, int32_t world, int32_t rank, const void *handles /* [world][2][NRAPS_IPC_HANDLE_BYTES] */);
 int nraps_mc_bank_peers(nraps_mc_ctx *ctx, int32_t world, int32_t rank, const void *const *device_buffers /* [world][2] */);
 /* profile_phases = 1: milliseconds spent in {births, transport kernel, tally prefix sum, bank compaction + histogram,

@@ -342,17 +342,18 @@ class MonteCarloContext:
         check(lib().nraps_mc_bank_advance(self._h, gen, C.c_void_p(stream)), "nraps_mc_bank_advance")
 
     def bank_reserve(self, shard_histories: int):
-        """Allocate the two bank buffers peer-mappable (multi-GPU), sized for shards of up to `shard_histories`."""
+        """Allocate the two bank buffers so that other processes can map them (one process per GPU), sized for shards
+        of up to `shard_histories`."""
         check(lib().nraps_mc_bank_reserve(self._h, shard_histories, None), "nraps_mc_bank_reserve")
 
     def bank_export(self) -> bytes:
-        """CUDA IPC handles of this rank's two bank buffers (2 x 64 bytes)."""
+        """Tickets of this rank's two bank buffers (2 x 64 bytes: pid + exported file descriptor + size)."""
         buf = C.create_string_buffer(2 * _lib.IPC_HANDLE_BYTES)
         check(lib().nraps_mc_bank_export(self._h, buf), "nraps_mc_bank_export")
         return buf.raw
 
     def bank_import(self, world: int, rank: int, handles: bytes):
-        """Map the peers' bank buffers from every rank's exported handles (rank order, 2 x 64 bytes each)."""
+        """Map the peers' bank buffers from every rank's exported tickets (rank order, 2 x 64 bytes each)."""
         assert len(handles) == world * 2 * _lib.IPC_HANDLE_BYTES
         check(lib().nraps_mc_bank_import(self._h, world, rank, C.c_char_p(handles)), "nraps_mc_bank_import")
 

@@ -21,6 +21,10 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "mc_internal.h"
 
 using namespace nraps;
@@ -129,6 +133,113 @@ cudaError_t dev_free(void *p)
     return cudaFreeAsync(p, nullptr);
 }
 
+// ---- Bank buffers other PROCESSES map (one process per GPU).  Legacy CUDA IPC (cudaIpcOpenMemHandle) maps the peer's
+// memory with small pages: random 8-byte reads over a few GB of it thrash the TLB -- measured on 8 B200s, births of
+// 1.25e8 histories per GPU took 1.3 s with IPC mappings against 10 ms through plain peer pointers in one process
+// (profiles/r2_bank8_ipc_vs_vmm.txt).  So the buffers are created with the virtual memory management API (cuMemCreate,
+// 2 MB granularity on both sides), exported as POSIX file descriptors and duplicated into the importing process with
+// pidfd_getfd.  The driver API is reached through cudaGetDriverEntryPoint: the library keeps no link-time dependency on
+// libcuda and still loads on a host without a driver.
+struct DriverApi {
+    decltype(&cuMemCreate) memCreate = nullptr;
+    decltype(&cuMemRelease) memRelease = nullptr;
+    decltype(&cuMemAddressReserve) addressReserve = nullptr;
+    decltype(&cuMemAddressFree) addressFree = nullptr;
+    decltype(&cuMemMap) memMap = nullptr;
+    decltype(&cuMemUnmap) memUnmap = nullptr;
+    decltype(&cuMemSetAccess) setAccess = nullptr;
+    decltype(&cuMemGetAllocationGranularity) granularity = nullptr;
+    decltype(&cuMemExportToShareableHandle) exportHandle = nullptr;
+    decltype(&cuMemImportFromShareableHandle) importHandle = nullptr;
+    bool ok = false;
+};
+
+const DriverApi &driver_api()
+{
+    static DriverApi api = [] {
+        DriverApi a;
+        auto get = [](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        a.ok = get("cuMemCreate", (void **)&a.memCreate) && get("cuMemRelease", (void **)&a.memRelease) &&
+               get("cuMemAddressReserve", (void **)&a.addressReserve) && get("cuMemAddressFree", (void **)&a.addressFree) &&
+               get("cuMemMap", (void **)&a.memMap) && get("cuMemUnmap", (void **)&a.memUnmap) && get("cuMemSetAccess", (void **)&a.setAccess) &&
+               get("cuMemGetAllocationGranularity", (void **)&a.granularity) && get("cuMemExportToShareableHandle", (void **)&a.exportHandle) &&
+               get("cuMemImportFromShareableHandle", (void **)&a.importHandle);
+        return a;
+    }();
+    return api;
+}
+
+struct VmmBuffer { // one mapping of one physical allocation in this process
+    CUmemGenericAllocationHandle handle = 0;
+    CUdeviceptr ptr = 0;
+    size_t size = 0;
+    bool mapped = false;
+};
+
+int vmm_fail(CUresult r, const char *what)
+{
+    g_cuda_error = std::string(what) + ": CUresult " + std::to_string((int)r);
+    return NRAPS_ERR_CUDA;
+}
+
+void vmm_release(VmmBuffer &b)
+{
+    const DriverApi &d = driver_api();
+    if (!d.ok) return;
+    if (b.mapped) d.memUnmap(b.ptr, b.size);
+    if (b.ptr) d.addressFree(b.ptr, b.size);
+    if (b.handle) d.memRelease(b.handle);
+    b = VmmBuffer{};
+}
+
+// map `b.handle` (created here or imported) read-write for `device`
+int vmm_map(VmmBuffer &b, int device)
+{
+    const DriverApi &d = driver_api();
+    CUresult r;
+    if ((r = d.addressReserve(&b.ptr, b.size, 0, 0, 0)) != CUDA_SUCCESS) return vmm_fail(r, "cuMemAddressReserve");
+    if ((r = d.memMap(b.ptr, b.size, 0, b.handle, 0)) != CUDA_SUCCESS) return vmm_fail(r, "cuMemMap");
+    b.mapped = true;
+    CUmemAccessDesc acc{};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if ((r = d.setAccess(b.ptr, b.size, &acc, 1)) != CUDA_SUCCESS) return vmm_fail(r, "cuMemSetAccess");
+    return NRAPS_OK;
+}
+
+int vmm_create(VmmBuffer &b, size_t bytes, int device)
+{
+    const DriverApi &d = driver_api();
+    if (!d.ok) return cuda_fail(cudaErrorNotSupported, "CUDA virtual memory management API unavailable");
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    CUresult r;
+    if ((r = d.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED)) != CUDA_SUCCESS) return vmm_fail(r, "cuMemGetAllocationGranularity");
+    b.size = (bytes + gran - 1) / gran * gran;
+    if ((r = d.memCreate(&b.handle, b.size, &prop, 0)) != CUDA_SUCCESS) return vmm_fail(r, "cuMemCreate");
+    int rc = vmm_map(b, device);
+    if (rc != NRAPS_OK) vmm_release(b);
+    return rc;
+}
+
+// what one rank publishes per bank buffer (NRAPS_IPC_HANDLE_BYTES each): enough for another process to duplicate the fd
+struct BankTicket {
+    uint32_t magic;
+    int32_t pid, fd;
+    uint32_t pad;
+    uint64_t size;
+};
+static_assert(sizeof(BankTicket) <= NRAPS_IPC_HANDLE_BYTES, "ticket fits the handle slot");
+constexpr uint32_t kTicketMagic = 0x4b4e4142u;
+
 template <typename T> cudaError_t upload(T **dst, const std::vector<T> &src)
 {
     cudaError_t e = dev_malloc(reinterpret_cast<void **>(dst), std::max<size_t>(1, src.size()) * sizeof(T));
@@ -181,10 +292,13 @@ struct nraps_mc_ctx {
     unsigned long long *d_slots = nullptr, *d_block_sums = nullptr;
     // the two bank buffers of this rank ([kBankHeader words: site count first][sites]), written alternately
     unsigned long long *d_bank[2] = {nullptr, nullptr};
-    bool bank_shared = false;                    // buffers came from cudaMalloc (mappable by peers), not from the pool
+    int bank_kind = 0;                           // 0: pool memory; 1: cudaMalloc (peer access inside one process); 2: cuMemCreate
+                                                 // (mapped by other processes through exported file descriptors)
+    VmmBuffer bank_vmm[2];                       // kind 2: this rank's allocations
+    VmmBuffer peer_vmm[2][kMaxPeers];            // kind 2: the peers' allocations mapped here
+    int bank_fd[2] = {-1, -1};                   // kind 2: exported file descriptors (peers duplicate them)
     int bank_world = 1, bank_rank = 0;           // ranks whose banks together feed a generation
     const unsigned long long *peer_bank[2][kMaxPeers] = {}; // [buffer][rank]; own entries point at d_bank
-    void *ipc_opened[2][kMaxPeers] = {};         // peers' buffers opened from IPC handles (closed in free_ctx)
     unsigned long long *d_bank_sizes = nullptr;  // [generations]
     double *d_entropy = nullptr;                 // [generations]
     uint8_t *d_counts = nullptr;
@@ -284,17 +398,20 @@ void phase_end(nraps_mc_ctx *c, int p, cudaStream_t s)
 
 void free_bank_buffers(nraps_mc_ctx *c)
 {
+    if (c->bank_kind != 0) cudaDeviceSynchronize();
     for (int w = 0; w < 2; ++w) {
         for (int r = 0; r < kMaxPeers; ++r) {
-            if (c->ipc_opened[w][r]) cudaIpcCloseMemHandle(c->ipc_opened[w][r]);
-            c->ipc_opened[w][r] = nullptr;
+            vmm_release(c->peer_vmm[w][r]);
             c->peer_bank[w][r] = nullptr;
         }
-        if (c->bank_shared) { cudaDeviceSynchronize(); cudaFree(c->d_bank[w]); }
+        if (c->bank_kind == 2) vmm_release(c->bank_vmm[w]);
+        else if (c->bank_kind == 1) cudaFree(c->d_bank[w]);
         else dev_free(c->d_bank[w]);
+        if (c->bank_fd[w] >= 0) close(c->bank_fd[w]);
+        c->bank_fd[w] = -1;
         c->d_bank[w] = nullptr;
     }
-    c->bank_shared = false;
+    c->bank_kind = 0;
 }
 
 void free_ctx(nraps_mc_ctx *c)
@@ -337,9 +454,9 @@ int ensure_event_bank(nraps_mc_ctx *c, uint64_t count)
     return NRAPS_OK;
 }
 
-// Size the per-history slot rows and the two bank buffers for a shard of `count` histories.  shared = the buffers must
-// be mappable by other ranks (cudaMalloc: IPC handles and peer access work on those, not on pool memory).
-int alloc_bank(nraps_mc_ctx *c, uint64_t count, bool shared, cudaStream_t s)
+// Size the per-history slot rows and the two bank buffers for a shard of `count` histories.  kind: 0 = pool memory
+// (one GPU), 1 = cudaMalloc (peer access from the other devices of this process), 2 = cuMemCreate (other processes).
+int alloc_bank(nraps_mc_ctx *c, uint64_t count, int kind, cudaStream_t s)
 {
     const uint64_t padded = (count + kBankTile - 1) / kBankTile * kBankTile;
     // every history keeps at most bank_cap sites, so this bound is exact: no generation can overflow the dense bank
@@ -348,8 +465,13 @@ int alloc_bank(nraps_mc_ctx *c, uint64_t count, bool shared, cudaStream_t s)
     const uint64_t dense_cap = count * c->bank_cap + 1024;
     const size_t bytes = (kBankHeader + dense_cap) * sizeof(unsigned long long);
     unsigned long long *fresh[2] = {nullptr, nullptr};
+    VmmBuffer fresh_vmm[2];
     for (int w = 0; w < 2; ++w) {
-        if (shared) CU(cudaMalloc((void **)&fresh[w], bytes));
+        if (kind == 2) {
+            int rc = vmm_create(fresh_vmm[w], bytes, c->device);
+            if (rc != NRAPS_OK) { vmm_release(fresh_vmm[0]); return rc; }
+            fresh[w] = reinterpret_cast<unsigned long long *>(fresh_vmm[w].ptr);
+        } else if (kind == 1) CU(cudaMalloc((void **)&fresh[w], bytes));
         else CU(dev_malloc((void **)&fresh[w], bytes));
         CU(cudaMemsetAsync(fresh[w], 0, kBankHeader * sizeof(unsigned long long), s));
     }
@@ -363,9 +485,10 @@ int alloc_bank(nraps_mc_ctx *c, uint64_t count, bool shared, cudaStream_t s)
     free_bank_buffers(c);
     for (int w = 0; w < 2; ++w) {
         c->d_bank[w] = fresh[w];
+        c->bank_vmm[w] = fresh_vmm[w];
         c->peer_bank[w][c->bank_rank] = fresh[w];
     }
-    c->bank_shared = shared;
+    c->bank_kind = kind;
     c->dense_cap = dense_cap;
     c->bank_hist_cap = 0;
     CU(dev_malloc((void **)&c->d_slots, padded * c->bank_cap * sizeof(unsigned long long)));
@@ -379,7 +502,7 @@ int ensure_bank(nraps_mc_ctx *c, uint64_t count, cudaStream_t s)
 {
     if (count <= c->bank_hist_cap) return NRAPS_OK;
     if (c->bank_world > 1) return NRAPS_ERR_STATE; // peers hold mappings of the current buffers: reserve for the largest shard first
-    return alloc_bank(c, count, c->bank_shared, s);
+    return alloc_bank(c, count, c->bank_kind, s);
 }
 
 // Transport generations gen .. gen+nb-1 (shard [begin, begin+count) of each) in one launch.  nb > 1 only for the
@@ -985,8 +1108,11 @@ extern "C" int nraps_mc_bank_reserve(nraps_mc_ctx *c, uint64_t shard_histories, 
     if (!c) return NRAPS_ERR_NULL;
     if (!c->bank_mode || c->bank_world > 1 || shard_histories == 0) return NRAPS_ERR_STATE;
     CU(cudaSetDevice(c->device));
-    if (!c->bank_shared || shard_histories > c->bank_hist_cap) {
-        int rc = alloc_bank(c, std::max<uint64_t>(shard_histories, c->bank_hist_cap), true, nullptr);
+    // device_buffers given: the caller will hand the pointers to the other devices of this process (peer access);
+    // NULL: other processes will map the buffers through nraps_mc_bank_export / import
+    const int kind = device_buffers ? 1 : 2;
+    if (c->bank_kind != kind || shard_histories > c->bank_hist_cap) {
+        int rc = alloc_bank(c, std::max<uint64_t>(shard_histories, c->bank_hist_cap), kind, nullptr);
         if (rc != NRAPS_OK) return rc;
     }
     if (device_buffers) { device_buffers[0] = c->d_bank[0]; device_buffers[1] = c->d_bank[1]; }
@@ -996,22 +1122,28 @@ extern "C" int nraps_mc_bank_reserve(nraps_mc_ctx *c, uint64_t shard_histories, 
 extern "C" int nraps_mc_bank_export(nraps_mc_ctx *c, void *handles)
 {
     if (!c || !handles) return NRAPS_ERR_NULL;
-    if (!c->bank_mode || !c->bank_shared) return NRAPS_ERR_STATE;
+    if (!c->bank_mode || c->bank_kind != 2) return NRAPS_ERR_STATE;
     CU(cudaSetDevice(c->device));
-    static_assert(sizeof(cudaIpcMemHandle_t) == NRAPS_IPC_HANDLE_BYTES, "handle size is part of the ABI");
+    const DriverApi &d = driver_api();
+    std::memset(handles, 0, 2 * NRAPS_IPC_HANDLE_BYTES);
     for (int w = 0; w < 2; ++w) {
-        cudaIpcMemHandle_t h;
-        CU(cudaIpcGetMemHandle(&h, c->d_bank[w]));
-        std::memcpy(static_cast<unsigned char *>(handles) + w * NRAPS_IPC_HANDLE_BYTES, &h, NRAPS_IPC_HANDLE_BYTES);
+        if (c->bank_fd[w] < 0) {
+            int fd = -1;
+            const CUresult r = d.exportHandle(&fd, c->bank_vmm[w].handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+            if (r != CUDA_SUCCESS) return vmm_fail(r, "cuMemExportToShareableHandle");
+            c->bank_fd[w] = fd; // stays open until the buffers are freed: the peers duplicate it from this process
+        }
+        BankTicket t{kTicketMagic, (int32_t)getpid(), c->bank_fd[w], 0u, (uint64_t)c->bank_vmm[w].size};
+        std::memcpy(static_cast<unsigned char *>(handles) + w * NRAPS_IPC_HANDLE_BYTES, &t, sizeof(t));
     }
     return NRAPS_OK;
 }
 
 namespace {
-int set_peers(nraps_mc_ctx *c, int32_t world, int32_t rank)
+int set_peers(nraps_mc_ctx *c, int32_t world, int32_t rank, int kind)
 {
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return NRAPS_ERR_OPTION;
-    if (!c->bank_mode || !c->bank_shared || c->bank_src >= 0) return NRAPS_ERR_STATE; // before the first bank is advanced to
+    if (!c->bank_mode || c->bank_kind != kind || c->bank_src >= 0) return NRAPS_ERR_STATE; // before the first bank is advanced to
     return NRAPS_OK;
 }
 } // namespace
@@ -1019,18 +1151,29 @@ int set_peers(nraps_mc_ctx *c, int32_t world, int32_t rank)
 extern "C" int nraps_mc_bank_import(nraps_mc_ctx *c, int32_t world, int32_t rank, const void *handles)
 {
     if (!c || !handles) return NRAPS_ERR_NULL;
-    int rc = set_peers(c, world, rank);
+    int rc = set_peers(c, world, rank, 2);
     if (rc != NRAPS_OK) return rc;
     CU(cudaSetDevice(c->device));
+    const DriverApi &d = driver_api();
     for (int r = 0; r < world; ++r)
         for (int w = 0; w < 2; ++w) {
             if (r == rank) { c->peer_bank[w][r] = c->d_bank[w]; continue; }
-            cudaIpcMemHandle_t h;
-            std::memcpy(&h, static_cast<const unsigned char *>(handles) + ((size_t)r * 2 + w) * NRAPS_IPC_HANDLE_BYTES, NRAPS_IPC_HANDLE_BYTES);
-            void *p = nullptr;
-            CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-            c->ipc_opened[w][r] = p;
-            c->peer_bank[w][r] = static_cast<const unsigned long long *>(p);
+            BankTicket t;
+            std::memcpy(&t, static_cast<const unsigned char *>(handles) + ((size_t)r * 2 + w) * NRAPS_IPC_HANDLE_BYTES, sizeof(t));
+            if (t.magic != kTicketMagic) return NRAPS_ERR_OPTION;
+            // duplicate the exporter's file descriptor into this process (Linux >= 5.6; same user, as under torchrun)
+            const int pidfd = (int)syscall(SYS_pidfd_open, (pid_t)t.pid, 0);
+            if (pidfd < 0) return cuda_fail(cudaErrorOperatingSystem, "pidfd_open on the exporting rank");
+            const int fd = (int)syscall(SYS_pidfd_getfd, pidfd, t.fd, 0);
+            close(pidfd);
+            if (fd < 0) return cuda_fail(cudaErrorOperatingSystem, "pidfd_getfd of the exported bank buffer");
+            VmmBuffer &b = c->peer_vmm[w][r];
+            b.size = (size_t)t.size;
+            const CUresult cr = d.importHandle(&b.handle, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+            close(fd);
+            if (cr != CUDA_SUCCESS) { b = VmmBuffer{}; return vmm_fail(cr, "cuMemImportFromShareableHandle"); }
+            if ((rc = vmm_map(b, c->device)) != NRAPS_OK) { vmm_release(b); return rc; }
+            c->peer_bank[w][r] = reinterpret_cast<const unsigned long long *>(b.ptr);
         }
     c->bank_world = world; c->bank_rank = rank;
     return NRAPS_OK;
@@ -1039,7 +1182,7 @@ extern "C" int nraps_mc_bank_import(nraps_mc_ctx *c, int32_t world, int32_t rank
 extern "C" int nraps_mc_bank_peers(nraps_mc_ctx *c, int32_t world, int32_t rank, const void *const *device_buffers)
 {
     if (!c || !device_buffers) return NRAPS_ERR_NULL;
-    int rc = set_peers(c, world, rank);
+    int rc = set_peers(c, world, rank, 1);
     if (rc != NRAPS_OK) return rc;
     for (int r = 0; r < world; ++r)
         for (int w = 0; w < 2; ++w)

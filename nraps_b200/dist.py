@@ -15,7 +15,7 @@ Two refinements (round 2):
   buffer (``run_generations_overlapped``): the collective leaves the critical path.
 * fission_bank source: nothing is gathered.  Every rank keeps the bank it compacted in a peer-mapped buffer, the
   source kernel of generation g+1 turns a site index into (rank, offset) from the ranks' site counts and loads the
-  site over NVLink (``setup_bank_peers`` exchanges the CUDA IPC handles once).  The per-generation all-reduce --
+  site over NVLink (``setup_bank_peers`` shares the buffers once: cuMemCreate allocations, exported file descriptors).  The per-generation all-reduce --
   issued after the local compaction -- is the only collective and doubles as the barrier between "every rank has
   compacted bank g" and "any rank samples from it"; the bank's cell histogram rides in the same buffer.
 """
@@ -130,13 +130,14 @@ class OverlappedReducer:
 def setup_bank_peers(ctx, rank: int, world: int, shard_max: int) -> None:
     """fission_bank mode on several GPUs: make every rank's two bank buffers readable by every other rank.
 
-    Allocates the buffers peer-mappable, exchanges their CUDA IPC handles through the default process group and maps
-    the peers' buffers; afterwards no bank data moves except the 8-byte sites the source kernel asks for."""
+    Allocates the buffers shareable (cuMemCreate, 2 MB pages), exchanges their tickets (pid + exported file descriptor)
+    through the default process group and maps the peers' buffers; afterwards no bank data moves except the 8-byte
+    sites the source kernel asks for."""
     import torch.distributed as dist
 
-    ctx.bank_reserve(shard_max)
     if world == 1:
         return
+    ctx.bank_reserve(shard_max)
     mine = ctx.bank_export()
     handles: list = [None] * world
     dist.all_gather_object(handles, mine)

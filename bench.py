@@ -441,7 +441,7 @@ def run_ours(a):
                          "kernel_ms_note": "births + transport + tally prefix sum of one generation (CUDA events on the launching stream); "
                                            "the transport kernel is > 98 % of it (profiles/ launch list)",
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
-                         "actual_limiter": {"what": "instruction issue (ncu, profiles/)", **{k: v for k, v in facts.items() if k not in ("bytes", "source")}},
+                         "actual_limiter": {"what": "instruction issue (ncu, profiles/)", **{k: v for k, v in facts.items() if k not in ("bytes", "source", "round1")}},
                          "note": "algorithmic bytes = 24 + 48*collisions/history (SURVEY 8d bank model); the fused kernel keeps "
                                  "particles in registers, so measured DRAM traffic (the 32-byte birth records) is ~2 % of that: "
                                  "the kernel is instruction-issue bound (profiles/)"},

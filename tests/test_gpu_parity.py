@@ -215,6 +215,25 @@ def test_fine_mesh_bit_exact():
     _assert_identical(got, want)
 
 
+@pytest.mark.parametrize("case,mpfr,bl,br,source", [("c", 80, 1.0, 1.0, "uniform_fuel"), ("a", 160, 0.0, 0.5, "uniform_fuel"),
+                                                    ("b", 40, 1.0, 0.0, "fission_bank"), ("c", 320, 1.0, 1.0, "uniform_fuel")])
+def test_closed_form_strides_do_not_change_a_bit(case, mpfr, bl, br, source):
+    """Fine meshes: the surface kernel strides over the surely-crossed cells of a segment in closed form (DESIGN section
+    5).  With the strides switched off (walk_cap = -2: cell-by-cell loop only) every tally bin, k and counter must be
+    the same -- 2 and 4 groups, reflecting / vacuum / albedo walls, both source modes, tallies in shared memory (N = 2040,
+    4080) and in global memory (N = 8160, 16320) -- and equal to the oracle's."""
+    v, xs, dx, mesh, fuel = load_case(case, mpfr=mpfr, mpwr=mpfr // 2)
+    v.boundl, v.boundr = bl, br
+    kw = dict(generations=3, histories=40_000, skip=1, want_tally=True, source_mode=source)
+    on = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, **kw)
+    off = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, walk_cap=-2, **kw)
+    _assert_identical(on, off)
+    assert np.array_equal(on.bank_sizes, off.bank_sizes)
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=3, histories=40_000, skip=1, threads=8, want_tally=True, source_mode=source)
+    _assert_identical(on, want)
+
+
 def test_statistical_parity_independent_streams():
     """k within 3 sigma combined and per-bin chi-square between the GPU (seed 1) and the oracle (seed 2)."""
     v, xs, dx, mesh, fuel = load_case("c")

@@ -20,13 +20,17 @@ pytestmark = pytest.mark.gpu
 N_CASES = int(os.environ.get("NRAPS_GPU_FUZZ", "60"))
 
 
-def test_random_problems_bit_exact_on_the_gpu():
+@pytest.mark.parametrize("fine", [False, True])
+def test_random_problems_bit_exact_on_the_gpu(fine):
+    """fine = tens of cells per pin: the closed-form strides of the surface kernel, shared-memory images without the
+    direct-score array, the Woodcock bucket tables of long meshes (a quarter of the problems: the oracle is slower there)."""
     from tools.fuzz_restatements import random_case
 
-    rng = np.random.default_rng(int(os.environ.get("NRAPS_GPU_FUZZ_SEED", "11")))
+    rng = np.random.default_rng(int(os.environ.get("NRAPS_GPU_FUZZ_SEED", "11")) + (1000 if fine else 0))
     ran, failures = 0, []
-    while ran < N_CASES:
-        c = random_case(rng)
+    n_cases = N_CASES // 4 if fine else N_CASES
+    while ran < n_cases:
+        c = random_case(rng, fine=fine)
         try:
             args = synthetic_case(c["M"], c["G"], c["pins"], c["mpfr"], c["mpwr"], seed=c["seed"], boundl=c["bl"], boundr=c["br"],
                                   numass=c["numass"])
@@ -34,7 +38,7 @@ def test_random_problems_bit_exact_on_the_gpu():
             continue  # the reference panics on this layout (mesh_gen trims past the ends)
         if len(args[4]) == 0 or len(args[3].matid) < c["numass"]:
             continue
-        H, gens = 100 * c["H"], c["gens"]
+        H, gens = (30 if fine else 100) * c["H"], c["gens"]
         kw = dict(scatter_mode=c["scatter_mode"], stale_xs=c["stale_xs"], tracking_mode=c["tracking"], source_mode=c["source"],
                   seed=c["rng_seed"], stride=c["stride"])
         got = nb.monte_carlo(*args, 1.0, generations=gens, histories=H, skip=1, want_tally=True, stream=c["rng_seq"], **kw)

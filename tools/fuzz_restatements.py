@@ -23,8 +23,9 @@ from oracle import restatement_py as rp  # noqa: E402
 from tests.util import bits, oracle_inputs, synthetic_case  # noqa: E402
 
 
-def random_case(rng: np.random.Generator) -> dict:
-    """Parameters of one problem; everything needed to rebuild it is in the returned dict."""
+def random_case(rng: np.random.Generator, fine: bool = False) -> dict:
+    """Parameters of one problem; everything needed to rebuild it is in the returned dict.  fine = meshes with tens of
+    cells per pin (the surface kernel's closed-form strides and its larger shared-memory images)."""
     M = int(rng.integers(2, 6))
     G = int(rng.integers(2, 9))
     n_pins = int(rng.integers(1, 8))
@@ -33,6 +34,9 @@ def random_case(rng: np.random.Generator) -> dict:
         pins[int(rng.integers(0, n_pins))] = int(rng.integers(0, 2))
     mpfr = int(rng.choice([1, 2, 3, 5, 8, 17]))
     mpwr = int(rng.choice([0, 1, 2, 4, 7])) if n_pins == 1 else int(rng.choice([1, 2, 4, 7]))
+    if fine:
+        mpfr = int(rng.choice([24, 40, 64, 100, 257]))
+        mpwr = int(rng.choice([12, 20, 33, 50, 128]))
     walls = [0.0, 0.3, 1.0]
     tracking = str(rng.choice(["surface", "surface", "woodcock"]))
     source = str(rng.choice(["uniform_fuel", "uniform_fuel", "fission_bank"]))

@@ -548,8 +548,15 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.n_peers = (c->bank_mode && c->bank_src >= 0) ? (uint32_t)c->bank_world : 0u;
     for (uint32_t r = 0; r < P.n_peers; ++r) P.peer_bank[r] = c->peer_bank[c->bank_src][r];
     P.slots = c->d_slots; P.counts = c->d_counts; P.k_cur = c->d_k_cur; P.bank_cap = c->bank_cap;
+    // The fused kernels take a shard in sub-shards of at most `sub` histories: births of a sub-shard (32 bytes per
+    // history) -> its transport -> the next one, all into the same tallies (integer sums) with the streams still keyed by
+    // the global history index, so the split changes nothing but the size of the birth-record buffer (4 GiB at most
+    // instead of 32 bytes x histories; NRAPS_SUBSHARD overrides the size for tests).
+    uint64_t sub = 1ull << 27;
+    if (const char *e = std::getenv("NRAPS_SUBSHARD")) sub = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
+    if (nb > 1 || c->opt.kernel_variant != NRAPS_KERNEL_FUSED) sub = (uint64_t)nb * count; // batched generations / other variants: one piece
     if (c->opt.kernel_variant != NRAPS_KERNEL_EVENT) { // births first, every lane busy; the transport lanes adopt them
-        const uint64_t births = (uint64_t)nb * count;
+        const uint64_t births = std::min<uint64_t>((uint64_t)nb * count, sub);
         if (births > c->source_cap) {
             CU(dev_free(c->d_source));
             c->d_source = nullptr; c->source_cap = 0;
@@ -557,10 +564,13 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
             c->source_cap = births;
         }
         P.source = c->d_source;
-        phase_begin(c, NRAPS_PH_SOURCE, s);
-        CU(launch_source(P, c->bank_mode, c->d_source, s));
-        phase_end(c, NRAPS_PH_SOURCE, s);
     }
+    auto births_of = [&](TransportParams &Q) -> int {
+        phase_begin(c, NRAPS_PH_SOURCE, s);
+        CU(launch_source(Q, c->bank_mode, c->d_source, s));
+        phase_end(c, NRAPS_PH_SOURCE, s);
+        return NRAPS_OK;
+    };
     if (c->opt.kernel_variant == NRAPS_KERNEL_EVENT) {
         if (trace) return NRAPS_ERR_OPTION;
         int rc = ensure_event_bank(c, count);
@@ -573,6 +583,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         if (trace || nb != 1) return NRAPS_ERR_OPTION;
         P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)c->opt.spawn_batch : 0u; // walk-class threshold, 0 = by run length
         if (count >> 32) return NRAPS_ERR_TOO_LARGE; // the block's source cursor is 32-bit
+        { int rc = births_of(P); if (rc != NRAPS_OK) return rc; }
         CU(launch_block_event(P, dim3(c->bev_grid), dim3(c->bev_block), c->bev_smem, c->bev_slots, s));
         return NRAPS_OK;
     }
@@ -598,10 +609,23 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         c->geo_grid[ti] = (uint32_t)c->sm_count * bps;
         c->prepared |= 1u << ti;
     }
-    phase_begin(c, NRAPS_PH_TRANSPORT, s);
-    if (c->woodcock) CU(launch_woodcock(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
-    else CU(launch_transport(P, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
-    phase_end(c, NRAPS_PH_TRANSPORT, s);
+    const uint64_t total = (uint64_t)nb * count;
+    for (uint64_t off = 0; off < total; off += sub) {
+        TransportParams Q = P;
+        const uint64_t n = std::min<uint64_t>(sub, total - off);
+        if (sub < total) { // a sub-shard of one generation (nb == 1): everything indexed by history moves along
+            Q.hist_begin = begin + off; Q.hist_end = begin + off + n; Q.hist_shard = n;
+            Q.slots = P.slots ? P.slots + off * c->bank_cap : nullptr;
+            Q.counts = P.counts ? P.counts + off : nullptr;
+            Q.trace = P.trace ? P.trace + off * NRAPS_TR_WORDS : nullptr;
+            if (off) CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
+        }
+        { int rc = births_of(Q); if (rc != NRAPS_OK) return rc; }
+        phase_begin(c, NRAPS_PH_TRANSPORT, s);
+        if (c->woodcock) CU(launch_woodcock(Q, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
+        else CU(launch_transport(Q, trace, c->bank_mode, dim3(c->geo_grid[ti]), dim3(c->geo_block[ti]), c->smem_total, s));
+        phase_end(c, NRAPS_PH_TRANSPORT, s);
+    }
     if (!c->woodcock) {
         // the cells a flight crossed completely were booked as range updates: fold their prefix sums into the tally
         phase_begin(c, NRAPS_PH_PREFIX, s);

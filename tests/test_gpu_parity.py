@@ -199,6 +199,24 @@ def test_launch_geometry_and_sharding_do_not_change_a_bit():
             assert np.array_equal(tally, ref), kw
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(source_mode="fission_bank"), dict(tracking_mode="woodcock", source_mode="fission_bank")])
+def test_shards_taken_in_sub_shards_bit_exact(monkeypatch, kw):
+    """A shard larger than 2^27 histories is transported in sub-shards (births of a piece, its transport, the next piece)
+    so that the birth-record buffer stays bounded.  NRAPS_SUBSHARD shrinks the piece to 7001 histories: tallies, k, bank
+    and per-history replay records must not notice."""
+    monkeypatch.setenv("NRAPS_SUBSHARD", "7001")
+    got, want = _both("c", generations=3, histories=50_000, **kw)
+    _assert_identical(got, want)
+    assert np.array_equal(got.bank_sizes, want.bank_sizes)
+    if not kw:
+        v, xs, dx, mesh, fuel = load_case("c")
+        with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=2, histories=30_000, skip=0) as ctx:
+            rec = ctx.trace(1, 100, 29_000)
+        deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+        ref = orc.monte_carlo(deck, m, generations=2, histories=30_000, skip=0, threads=8, trace_gen=1, hist_begin=100, hist_count=29_000)
+        assert np.array_equal(rec, ref.trace)
+
+
 def test_single_history_and_flight_cap():
     got, want = _both("a", generations=2, histories=1, skip=1)
     _assert_identical(got, want)

@@ -5,7 +5,10 @@
 //              [--seed S --stream Q --stride T] [--device D] [--scatter single_xi|rust_pre182|rust_182]
 //              [--generation-log]  (one JSON line per generation on stderr: k, k_fund, bank size, source entropy)
 //              [--fix-stale-xs] [--quiet] [--gpus N] [--tracking surface|woodcock] [--source uniform_fuel|fission_bank]
-//              [--solution mc|diffusion]  (diffusion = the reference's finite-difference solver, host code, cross-check only)
+//              [--solution mc|diffusion|deck]  (diffusion = the reference's finite-difference solver, host code, cross-check
+//              only; deck = what the deck's `Solution` key says, 1 = Monte Carlo, anything else diffusion, the dispatch the
+//              reference's commented-out main intends (src/main.rs:336-346).  Default mc: the shipped decks say Solution = 0
+//              and BASELINE's configurations are Monte Carlo runs of them)
 // The deck defaults to ./TestCaseC.txt like the reference (src/process_input.rs:86).
 #include <chrono>
 #include <cstdio>
@@ -26,7 +29,7 @@ int main(int argc, char **argv)
     opt.stale_xs = 1;
     long long gens = -1, hist = -1, skip = -1;
     int gpus = 1;
-    bool gen_log = false, diffusion = false;
+    bool gen_log = false, diffusion = false, solution_from_deck = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&](const char *what) -> const char * {
@@ -47,7 +50,11 @@ int main(int argc, char **argv)
         else if (a == "--gpus") gpus = std::atoi(next("--gpus"));
         else if (a == "--tracking") opt.tracking_mode = std::string(next("--tracking")) == "woodcock" ? NRAPS_TRACK_WOODCOCK : NRAPS_TRACK_SURFACE;
         else if (a == "--source") opt.source_mode = std::string(next("--source")) == "fission_bank" ? NRAPS_SOURCE_FISSION_BANK : NRAPS_SOURCE_UNIFORM_FUEL;
-        else if (a == "--solution") diffusion = std::string(next("--solution")) == "diffusion";
+        else if (a == "--solution") {
+            const std::string m = next("--solution");
+            diffusion = m == "diffusion";
+            solution_from_deck = m == "deck";
+        }
         else if (a == "--scatter") {
             const std::string m = next("--scatter");
             opt.scatter_mode = m == "rust_pre182" ? NRAPS_SCATTER_RUST_PRE182 : m == "rust_182" ? NRAPS_SCATTER_RUST_182 : NRAPS_SCATTER_SINGLE_XI;
@@ -59,6 +66,7 @@ int main(int argc, char **argv)
     nraps_deck deck;
     int rc = nraps_process_input(deck_path.c_str(), &deck);
     if (rc != NRAPS_OK) { std::fprintf(stderr, "process_input(%s): %s\n", deck_path.c_str(), nraps_strerror(rc)); return 1; }
+    if (solution_from_deck) diffusion = deck.solution != 1;
     if (gens >= 0) deck.generations = (uint64_t)gens;
     if (hist >= 0) deck.histories = (uint64_t)hist;
     if (skip >= 0) deck.skip = (uint64_t)skip;

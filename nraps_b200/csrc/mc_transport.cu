@@ -199,9 +199,12 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     uint32_t h_coll = 0, h_cross = 0, h_flight = 0, h_refl = 0, h_bank = 0; // this history
     uint32_t c_hist = 0, c_coll = 0, c_cross = 0, c_flight = 0, c_refl = 0, c_leak = 0, c_trunc = 0, c_bank = 0;
 
+    // set by the walk of a trip, read by its collision stage only: declared out here so that they are not re-initialised
+    // every trip (4 instructions of ~410; measured +0.6 %)
+    float end = 0.f;
+    Recip rc{1.f, 1.f};
     for (;;) {
-        __syncwarp();
-        // ---------------- SPAWN: hand fresh history indices to dead lanes
+        // ---------------- SPAWN: hand fresh history indices to dead lanes (the ballot is the warp's convergence point)
         const unsigned need = __ballot_sync(kFull, !alive);
         if (need && ((uint32_t)__popc(need) >= P.spawn_batch || need == kFull)) {
             if (w_next == w_end && !exhausted) {
@@ -248,8 +251,6 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
 
         uint32_t fate = 0;
         int ev = EV_NONE;
-        float end = 0.f;
-        Recip rc{1.f, 1.f};
         if (alive) {
             if (!pending) {
                 if (h_flight >= P.max_flights) {

@@ -555,6 +555,10 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     uint64_t sub = 1ull << 27;
     if (const char *e = std::getenv("NRAPS_SUBSHARD")) sub = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
     if (nb > 1 || c->opt.kernel_variant != NRAPS_KERNEL_FUSED) sub = (uint64_t)nb * count; // batched generations / other variants: one piece
+    if (sub > 0xffffffffull) { // the fused kernels index a launch's histories with 32 bits
+        if (nb > 1 || c->opt.kernel_variant != NRAPS_KERNEL_FUSED) return NRAPS_ERR_TOO_LARGE;
+        sub = 1ull << 31;
+    }
     if (c->opt.kernel_variant != NRAPS_KERNEL_EVENT) { // births first, every lane busy; the transport lanes adopt them
         const uint64_t births = std::min<uint64_t>((uint64_t)nb * count, sub);
         if (births > c->source_cap) {

@@ -136,8 +136,13 @@ template <int MODE> struct Tally {
     }
 };
 
+// Register budget per instantiation.  Blocks of up to 1024 threads must be launchable (64 registers); the instantiations
+// that share an SM between two blocks (SURF_SPLIT) are asked for 56, which lets 2 x 576 threads reside -- left to itself
+// ptxas gives the fission-bank one anything from 55 to 64 depending on unrelated edits.
+template <bool TRACE, int MODE> struct RegCap { static constexpr int k = (MODE == SURF_SPLIT && !TRACE) ? 56 : 64; };
+
 template <int TG, bool TRACE, bool BANK, int MODE>
-__global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParams P)
+__global__ void __maxnreg__((RegCap<TRACE, MODE>::k)) transport_kernel(const TransportParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool BIG = (MODE == SURF_GLOBAL);
@@ -187,13 +192,16 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
     const unsigned lane = tid & 31;
     const uint64_t inc = P.rng_inc;
 
-    // warp-uniform cursor over the chunk of history indices this warp owns
-    uint64_t w_next = 0, w_end = 0;
+    // warp-uniform cursor over the chunk of histories this warp owns, relative to hist_begin (a launch never covers
+    // 2^32 histories: the host hands larger shards over in sub-shards)
+    uint32_t w_next = 0, w_end = 0;
+    const uint32_t span = (uint32_t)(P.hist_end - P.hist_begin);
     bool exhausted = false;
 
     // lane state: one neutron
     bool alive = false, pending = false;
-    uint64_t rng = 0, y = 0;
+    uint64_t rng = 0;
+    uint32_t y = 0; // history index relative to hist_begin
     float x = 0.f, mu = 1.f, ds = 0.f;
     int cell = 0, g = 0, xsg = 0, mat = 0, row0 = 0;
     uint32_t h_coll = 0, h_cross = 0, h_flight = 0, h_refl = 0, h_bank = 0; // this history
@@ -211,20 +219,19 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(P.work, (unsigned long long)P.chunk);
                 base = __shfl_sync(kFull, base, 0);
-                const uint64_t b = P.hist_begin + base;
-                if (b >= P.hist_end) exhausted = true;
+                if (base >= span) exhausted = true;
                 else {
-                    w_next = b;
-                    w_end = (b + P.chunk < P.hist_end) ? b + P.chunk : P.hist_end;
+                    w_next = (uint32_t)base;
+                    w_end = (base + P.chunk < span) ? (uint32_t)base + P.chunk : span;
                 }
             }
-            const uint32_t avail = (uint32_t)(w_end - w_next);
+            const uint32_t avail = w_end - w_next;
             if (avail) {
                 const uint32_t rank = __popc(need & ((1u << lane) - 1u));
                 if (!alive && rank < avail) {
                     y = w_next + rank;
                     // adopt the neutron source_kernel gave birth to (mc_source.cu)
-                    const uint4 *rec = P.source + 2 * (y - P.hist_begin);
+                    const uint4 *rec = P.source + 2 * (size_t)y;
                     const uint4 r0 = __ldg(rec);
                     const uint2 r1 = __ldg(reinterpret_cast<const uint2 *>(rec + 1));
                     x = __uint_as_float(r0.x);
@@ -390,20 +397,16 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                 }
             }
             if (ev == EV_SEGEXIT) { // ------------ end of the segment
+                // (the stop-edge table keeps the walk inside [0, N-1]: the boundary cells are never left through the loop)
                 ev = EV_NONE;
-                if ((unsigned)cell >= (unsigned)N) {
-                    fate = NRAPS_FATE_TRUNCATED; // unreachable for validated input
-                    cell = cell < 0 ? 0 : N - 1;
+                const int m2 = ld_mat(cell);
+                if (m2 != mat) { // material change: the flight ends here, alive (src/mc_code.rs:175-181)
+                    mat = m2;
+                    xsg = g;
                 } else {
-                    const int m2 = ld_mat(cell);
-                    if (m2 != mat) { // material change: the flight ends here, alive (src/mc_code.rs:175-181)
-                        mat = m2;
-                        xsg = g;
-                    } else {
-                        // same material: the next segment of the run (the cell width changed by an ulp), or the
-                        // boundary cell, which the walk never enters on its own: the flight goes on next trip
-                        pending = true;
-                    }
+                    // same material: the next segment of the run (the cell width changed by an ulp), or the
+                    // boundary cell, which the walk never enters on its own: the flight goes on next trip
+                    pending = true;
                 }
             }
         }
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
                     const uint32_t n = (uint32_t)__float2int_rz(fadd(wgt, pcg32_unit(rng, inc)));
                     const unsigned long long site = ((unsigned long long)(uint32_t)cell << 32) | __float_as_uint(end);
                     for (uint32_t j = 0; j < n; ++j) {
-                        if (h_bank < P.bank_cap) P.slots[(y - P.hist_begin) * P.bank_cap + h_bank] = site;
+                        if (h_bank < P.bank_cap) P.slots[(size_t)y * P.bank_cap + h_bank] = site;
                         ++h_bank;
                     }
                 }
@@ -448,13 +451,13 @@ __global__ void __launch_bounds__(1024, 1) transport_kernel(const TransportParam
             c_trunc += (fate == NRAPS_FATE_TRUNCATED);
             if (BANK) {
                 const uint32_t kept = h_bank < P.bank_cap ? h_bank : P.bank_cap;
-                P.counts[y - P.hist_begin] = (uint8_t)kept;
+                P.counts[y] = (uint8_t)kept;
                 c_bank += kept;
             }
             if (TRACE) {
                 c_cross += h_cross; c_refl += h_refl;
                 if (P.trace) {
-                    uint32_t *t = P.trace + (y - P.hist_begin) * NRAPS_TR_WORDS;
+                    uint32_t *t = P.trace + (size_t)y * NRAPS_TR_WORDS;
                     t[NRAPS_TR_COLLISIONS] = h_coll;
                     t[NRAPS_TR_CROSSINGS] = h_cross;
                     t[NRAPS_TR_FLIGHTS] = h_flight;

@@ -24,7 +24,7 @@
 // practically a whole material run -- that is one and the same value v for every
 // cell.  So the walk loop only replays what decides the trajectory (the two
 // additions and the compare of the reference's collision test and the running
-// ds += t, all in the reference's operation order, 9 instructions per
+// ds += t, all in the reference's operation order, 10 instructions per
 // crossing), and the scores of the n cells crossed completely are booked as ONE
 // range update of a difference array: diff[first] += fx(v), diff[last+1] -=
 // fx(v).  fx() is the same float -> 2^-28 fixed-point conversion as before and
@@ -32,6 +32,8 @@
 // only), so tally = direct + prefix_sum(diff) (tally_prefix_kernel) equals the
 // cell-by-cell sums of the oracle bit for bit, for any scheduling.  Only the
 // partial cells at the two ends of a flight are still scored one by one.
+// On fine meshes the surely-crossed cells of a segment are not even walked:
+// skip_cells() takes them in closed-form strides (see there).
 #include "mc_lane.cuh"
 
 namespace nraps {

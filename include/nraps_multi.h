@@ -2,8 +2,10 @@
  * nraps_multi.h -- optional single-process multi-GPU driver of the Monte Carlo path (library
  * libnraps_b200_nccl.so, links NCCL).  One host thread and one nraps_mc_ctx per device; histories shard
  * across devices (the reference's thread fork / ordered join, src/mc_code.rs:302-338, at GPU granularity);
- * per generation one ncclAllReduce(sum, uint64) of the tally buffer and, in fission_bank mode, an
- * ncclAllGather of the bank.  Results are bit-identical to nraps_mc_run on one GPU.
+ * per generation one ncclAllReduce(sum, uint64) of the tally buffer -- nothing else: in fission_bank mode every
+ * device keeps the bank it compacted and the births of the next generation load each site from the device that
+ * banked it (peer access over NVLink; nraps_mc_bank_reserve / nraps_mc_bank_peers of nraps_mc.h).  Results are
+ * bit-identical to nraps_mc_run on one GPU.
  *
  * The one-process-per-GPU route (torchrun + nraps_b200.monte_carlo_distributed) needs none of this; this entry
  * point exists so that a host without Python (the `nraps` driver, the Rust shim) gets all GPUs of a box

@@ -381,17 +381,27 @@ def run_ours(a):
     configs = {}
     if not a.no_configs:
         kc, wc = max(2, min(4, K)), 2
-        configs["config4_strong"] = config_entry("config4", "surface", kc, wc)
-        configs["config4_strong_woodcock"] = config_entry("config4", "woodcock", kc, wc)
-        configs["config5_weak"] = config_entry("config5", "surface", kc, wc)
-        configs["config5_weak_woodcock"] = config_entry("config5", "woodcock", kc, wc)
+        for key, name, tracking in (("config4_strong", "config4", "surface"), ("config4_strong_woodcock", "config4", "woodcock"),
+                                    ("config5_weak", "config5", "surface"), ("config5_weak_woodcock", "config5", "woodcock")):
+            try:
+                configs[key] = config_entry(name, tracking, kc, wc)
+            except Exception as e:  # noqa: BLE001 -- the headline must still be printed; a failure is reported in its place
+                # (a setup failure -- e.g. the bank buffers cannot be shared between processes on this host -- hits every
+                # rank alike, before any collective of the run)
+                configs[key] = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.synchronize()
     identical = None
     if not a.no_configs:
         vs, xss, dxs, meshs, fuels = product_problem("config3")
         identical = {}
         for mode in ("uniform_fuel", "fission_bank"):
             kw = dict(generations=4, histories=50_001, skip=1, source_mode=mode)
-            many = nb.monte_carlo_distributed(vs, xss, dxs, meshs, fuels, 1.0, device=local, **kw) if world > 1 else None
+            try:
+                many = nb.monte_carlo_distributed(vs, xss, dxs, meshs, fuels, 1.0, device=local, **kw) if world > 1 else None
+            except Exception as e:  # noqa: BLE001 -- reported as "not identical" with the reason
+                identical[mode] = False
+                identical[mode + "_error"] = f"{type(e).__name__}: {e}"
+                continue
             if rank == 0:
                 one = nb.monte_carlo(vs, xss, dxs, meshs, fuels, 1.0, device=local, **kw)
                 if world == 1:  # the generation-level route (what the multi-GPU launcher drives) against the batched call
@@ -458,7 +468,7 @@ def run_ours(a):
                         "(statistically equivalent, 3 sigma / chi-square tested)"}}
         if configs:
             line["configs"] = configs
-            line["multi_gpu_bit_identical"] = bool(identical and all(identical.values()))
+            line["multi_gpu_bit_identical"] = bool(identical and all(v for k, v in identical.items() if not k.endswith("_error")))
             line["multi_gpu_bit_identical_detail"] = {
                 **(identical or {}), "what": "k, flux and bank sizes of a 4-generation 50 001-history TestCaseC run through this launch's "
                                             f"{world}-rank generation-level route against nraps_mc_run on one GPU, compared bit for bit"}

@@ -765,7 +765,7 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     // the event pipeline packs the flight count of a record into 20 bits (mc_event.cu): a cap it cannot count to would
     // never fire and the host-driven round loop would spin on a runaway history
     if (o->kernel_variant == NRAPS_KERNEL_EVENT) c->max_flights = std::min<uint32_t>(c->max_flights, 0xfffffu); // validate(): <= 2^20-1 if given
-    c->chunk = o->chunk > 0 ? (uint32_t)o->chunk : 64u;
+    c->chunk = o->chunk > 0 ? (uint32_t)o->chunk : 32u; // histories a warp claims per global atomic (swept on config 3: 16-32 best, 64 -0.4 %, 256 -3 %)
     c->bank_mode = (o->source_mode == NRAPS_SOURCE_FISSION_BANK);
     c->bank_cap = o->bank_cap > 0 ? (uint32_t)o->bank_cap : 8u;
 

@@ -4,6 +4,7 @@
  *
  *   nraps_process_input ... src/process_input.rs:85-175 (+ scanner :44-83)
  *   nraps_mesh_gen ........ src/main.rs:85-143
+ *   nraps_walk_segments ... (no counterpart) segments of equal-width cells the surface kernel walks and scores by range
  *   nraps_plot_solution ... src/plot_solution.rs:7-58 (without spawning plot.py)
  *   nraps_average_assembly  src/mc_code.rs:259-274
  *   nraps_k_fund .......... src/mc_code.rs:368-376
@@ -59,6 +60,17 @@ size_t nraps_format_f64(double v, char *buf, size_t cap);
  * vars.csv and the 2G flux rows of interface.csv, which is what the reference's writer leaves behind in that case */
 int nraps_plot_solution(const nraps_results *r, uint32_t G, uint64_t generations, uint32_t N,
                         double assembly_length, const char *dir);
+
+/* Walk segments of the surface-tracking kernel (no reference counterpart: it is how the kernel books the scores of
+ * src/mc_code.rs:163,173 as range updates).  A segment = a maximal range of cells of one material run whose widths
+ * right[i] - left[i] are the same binary32 number.  Per cell i of segment [a, b):
+ *   stops[i]      = (edge index at which a walk to the left stops) | (the same to the right) << 16: the neutron has then
+ *                   entered cell a-1 (edge a-1 ahead) / cell b (edge b+1 ahead); the domain's boundary cells are not
+ *                   entered by the walk loop, so a segment holding cell 0 stops at edge 0 and one holding cell N-1 at edge N
+ *   width_bits[i] = the bits of that width
+ * Returns the number of segments through *n_segments (optional). */
+int nraps_walk_segments(const uint8_t *matid, const float *left, const float *right, uint32_t N, uint32_t *stops,
+                        uint32_t *width_bits, uint32_t *n_segments);
 
 void nraps_average_assembly(const float *flux, uint32_t G, uint32_t N, uint32_t numass, float *out);
 void nraps_k_fund(const float *k, uint64_t generations, uint64_t skip, float *out);

@@ -89,7 +89,7 @@ EXPORTS = [
     "nraps_mc_phase_ms", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
     "nraps_strerror", "nraps_last_cuda_error", "nraps_abi_version", "nraps_options_default",
     "nraps_process_input", "nraps_deck_free", "nraps_mesh_gen", "nraps_mesh_free", "nraps_problem_from",
-    "nraps_format_f32", "nraps_format_f64", "nraps_plot_solution", "nraps_average_assembly", "nraps_k_fund",
+    "nraps_walk_segments", "nraps_format_f32", "nraps_format_f64", "nraps_plot_solution", "nraps_average_assembly", "nraps_k_fund",
     "nraps_diffusion_run",
 ]
 
@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
     L.nraps_mesh_gen.argtypes = [_u8p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_float, C.c_float, C.POINTER(Mesh)]
     L.nraps_mesh_free.argtypes = [C.POINTER(Mesh)]
     L.nraps_mesh_free.restype = None
+    L.nraps_walk_segments.argtypes = [_u8p, _fp, _fp, C.c_uint32, _u32p, _u32p, _u32p]
     L.nraps_problem_from.argtypes = [C.POINTER(Deck), C.POINTER(Mesh), C.c_float, C.POINTER(Problem)]
     L.nraps_format_f32.argtypes = [C.c_float, C.c_char_p, C.c_size_t]
     L.nraps_format_f32.restype = C.c_size_t

@@ -7,6 +7,7 @@
 //   nraps_k_fund ............. src/mc_code.rs:368-376
 #include "nraps_host.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -109,4 +110,34 @@ extern "C" void nraps_k_fund(const float *k, uint64_t gens, uint64_t skip, float
         for (uint64_t j = skip; j <= n; ++j) acc += k[j];
         out[n] = acc / (float)(uint64_t)(n - (skip - 1)); // usize arithmetic wraps for skip == 0
     }
+}
+
+extern "C" int nraps_walk_segments(const uint8_t *matid, const float *left, const float *right, uint32_t N, uint32_t *stops,
+                                   uint32_t *width_bits, uint32_t *n_segments)
+{
+    if (!matid || !left || !right || !stops || !width_bits) return NRAPS_ERR_NULL;
+    if (N == 0 || N > 65535) return NRAPS_ERR_SHAPE;
+    uint32_t count = 0;
+    for (uint32_t i = 0; i < N;) {
+        // Edges accumulate in f32 upstream (src/main.rs:119-140), so the width of a fuel or water cell changes by an ulp
+        // where the position crosses a power of two: a material run is one segment, or two around such a point.
+        const float w = right[i] - left[i];
+        uint32_t wbits;
+        std::memcpy(&wbits, &w, sizeof(wbits));
+        uint32_t j = i + 1;
+        while (j < N && matid[j] == matid[i]) {
+            const float wj = right[j] - left[j];
+            if (std::memcmp(&wj, &w, sizeof(float)) != 0) break;
+            ++j;
+        }
+        const uint32_t stop_right = std::min(j, N - 1) + 1, stop_left = i > 0 ? i - 1 : 0;
+        for (uint32_t q = i; q < j; ++q) {
+            stops[q] = stop_left | (stop_right << 16);
+            width_bits[q] = wbits;
+        }
+        ++count;
+        i = j;
+    }
+    if (n_segments) *n_segments = count;
+    return NRAPS_OK;
 }

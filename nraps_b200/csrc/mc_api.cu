@@ -25,6 +25,7 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 
+#include "../../include/nraps_host.h"
 #include "mc_internal.h"
 
 using namespace nraps;
@@ -815,24 +816,10 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     // point.  Inside a segment x - edge is the same number for every cell crossed completely (mc_transport.cu).
     std::vector<uint2> segw(N);
     uint32_t n_segments = 0;
-    for (uint32_t i = 0; i < N;) {
-        const float w = edges[i + 1] - edges[i];
-        uint32_t wbits;
-        std::memcpy(&wbits, &w, sizeof(wbits));
-        uint32_t j = i + 1;
-        while (j < (runb[i] >> 16)) {
-            const float wj = edges[j + 1] - edges[j];
-            if (std::memcmp(&wj, &w, sizeof(float)) != 0) break;
-            ++j;
-        }
-        // what the kernel needs of the segment [i, j): the edge reference at which a walk through it stops -- the neutron
-        // has then entered cell j (going right: the edge ahead of it is j + 1) or cell i - 1 (going left: edge i - 1).
-        // The domain's boundary cells are never entered by the walk loop (the wall logic runs before it), so a segment
-        // that contains one stops there: entering cell N - 1 means edge N ahead, entering cell 0 means edge 0.
-        const uint32_t stop_right = std::min(j, N - 1) + 1, stop_left = i > 0 ? i - 1 : 0;
-        for (uint32_t q = i; q < j; ++q) segw[q] = make_uint2(stop_left | (stop_right << 16), wbits);
-        ++n_segments;
-        i = j;
+    {
+        std::vector<uint32_t> stops(N), wbits(N);
+        nraps_walk_segments(p->matid, p->left, p->right, N, stops.data(), wbits.data(), &n_segments); // host_mesh.cpp
+        for (uint32_t i = 0; i < N; ++i) segw[i] = make_uint2(stops[i], wbits[i]);
     }
     c->skip_walk = (o->walk_cap != -2 && N >= 16u * n_segments) ? 1u : 0u; // walk_cap = -2: never stride (tests, comparisons)
     std::vector<float> xs(xs_floats(M, G));

@@ -502,3 +502,36 @@ def test_bindings_mirror_the_header_field_for_field(tmp_path):
         assert int(got[cname]) == C.sizeof(pycls)
         for (name, _), (pyname, _t) in zip(c_fields(cname), pycls._fields_):
             assert int(got[f"{cname}.{name}"]) == getattr(pycls, pyname).offset, (cname, name)
+
+
+def test_walk_segments_of_the_surface_kernel():
+    """nraps_walk_segments: the table the surface kernel walks by (include/nraps_host.h).  Against a numpy restatement on
+    the three decks and two refinements: segments tile the mesh, never span a material boundary, hold cells of one
+    binary32 width only and are maximal; the stop edges are the segment's outer neighbours, clipped so that the walk
+    never enters a boundary cell; and the counts the design quotes (deck C: 76 segments for 69 material runs)."""
+    import ctypes as C
+
+    L = _lib.lib()
+    for case, mpfr, mpwr in (("a", None, None), ("b", None, None), ("c", None, None), ("c", 80, 40), ("b", 17, 5)):
+        v, xs, dx, mesh, fuel = load_case(case, mpfr=mpfr, mpwr=mpwr) if mpfr else load_case(case)
+        N = len(mesh)
+        stops, wbits, nseg = np.zeros(N, np.uint32), np.zeros(N, np.uint32), C.c_uint32(0)
+        u32p = C.POINTER(C.c_uint32)
+        rc = L.nraps_walk_segments(mesh.matid.ctypes.data_as(_lib._u8p), mesh.mesh_left.ctypes.data_as(_lib._fp),
+                                   mesh.mesh_right.ctypes.data_as(_lib._fp), N, stops.ctypes.data_as(u32p), wbits.ctypes.data_as(u32p),
+                                   C.byref(nseg))
+        assert rc == 0
+        w = (mesh.mesh_right - mesh.mesh_left).astype(f32).view(np.uint32)
+        assert np.array_equal(wbits, w)
+        cut = np.r_[True, (mesh.matid[1:] != mesh.matid[:-1]) | (w[1:] != w[:-1])]   # a segment starts here
+        starts = np.flatnonzero(cut)
+        ends = np.r_[starts[1:], N]
+        assert nseg.value == len(starts)
+        for a, b in zip(starts, ends):
+            want = max(a - 1, 0) | ((min(b, N - 1) + 1) << 16)
+            assert (stops[a:b] == want).all(), (case, a, b)
+        runs = 1 + int((mesh.matid[1:] != mesh.matid[:-1]).sum())
+        assert runs <= nseg.value <= runs + 12   # a run splits only where the position crosses a power of two
+        if case == "c" and mpfr is None:
+            assert (runs, nseg.value) == (69, 76)
+    assert L.nraps_walk_segments(None, None, None, 4, None, None, None) == 1

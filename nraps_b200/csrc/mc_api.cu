@@ -540,6 +540,10 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     P.rng_inc = c->master.inc;
     P.hist_begin = begin; P.hist_end = begin + (uint64_t)nb * count;
     P.rows = nb * c->G; P.hist_shard = count; P.hist_total = c->histories;
+    if (surface_fused) {
+        const SurfLayout SL = make_surface_layout(c->M, c->G, c->N, c->surf_mode, P.rows);
+        P.diff_hi_off = SL.diff_hi - SL.diff_lo; P.direct_hi_off = SL.direct_hi - SL.direct_lo;
+    }
     P.work = c->d_work; P.tally = c->d_tally;
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;

@@ -112,6 +112,8 @@ struct TransportParams {
     uint32_t skip_walk;      // surface kernel: stride over the surely-crossed cells of a segment in closed form (fine meshes)
     float length;            // right edge of the slab (bounds the rounding of x + ds)
     float stride_min;        // closed-form strides only while |ds| > stride_min * w (fewer cells than that: the exact loop)
+    uint32_t diff_hi_off, direct_hi_off; // surface kernel: byte distance from the low to the high words of a shared-memory bin array
+                                         // (host-computed from SurfLayout: the kernel reads them in the rare carry path only)
     uint32_t M, G, N, NF, NB, big;
     uint32_t rows;       // tally rows of this launch = batch * G: generations gen .. gen+batch-1 share the launch
     uint64_t hist_shard; // histories of one generation in this launch (hist_end - hist_begin = batch * hist_shard)

@@ -171,8 +171,8 @@ __global__ void __maxnreg__((RegCap<TRACE, MODE>::k)) transport_kernel(const Tra
 
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
     Tally<MODE> T;
-    T.diff_base = smem_base + L.diff_lo; T.diff_hi_off = L.diff_hi - L.diff_lo;
-    T.direct_base = smem_base + L.direct_lo; T.direct_hi_off = L.direct_hi - L.direct_lo;
+    T.diff_base = smem_base + L.diff_lo; T.diff_hi_off = P.diff_hi_off;
+    T.direct_base = smem_base + L.direct_lo; T.direct_hi_off = P.direct_hi_off;
     T.N = P.N; T.g_direct = P.tally; T.g_diff = P.diff;
     uint32_t edges_base = BIG ? 0u : smem_base + L.edges; // edge reference: shared byte address, or the edge index
     uint32_t segw_base = smem_base + L.segw, matid_base = smem_base + L.matid;
@@ -348,25 +348,27 @@ __global__ void __maxnreg__((RegCap<TRACE, MODE>::k)) transport_kernel(const Tra
                                 e_addr += (uint32_t)stride;
                                 return e_addr != e_stop;
                             };
+                            // |ds| >= lim: the reference's test cannot fail in the cell ahead (the roundings of x + ds and
+                            // of the difference are bounded by 2^-22 (L + |ds|)).  |ds| only shrinks along a walk, so one
+                            // bound computed from the |ds| at its start serves the whole walk.
+                            const float lim = __fmaf_rn(fadd(P.length, fabsf(ds)), 4.76837158203125e-07f, w); // w + 2^-21 (L + |ds|)
                             if (kSkip && P.skip_walk) {
                                 // Fine meshes: a flight crosses tens of cells of one segment.  While |ds| is surely large
-                                // enough for the collision test to pass (|ds| >= w + the rounding of x + ds), the only
-                                // thing a crossing changes is ds <- fl(ds -+ w), and inside one binade of |ds| that is an
-                                // exact integer recurrence on the mantissa (skip_cells above): those cells are taken in
-                                // one stride, in registers.  One real subtraction carries |ds| over what the recurrence
-                                // does not cover (the change of binade, an odd mantissa under a rounding tie), then the
-                                // next stride; the position is read once at the end and the exact loop finishes the walk.
+                                // enough for the collision test to pass, the only thing a crossing changes is
+                                // ds <- fl(ds -+ w), and inside one binade of |ds| that is an exact integer recurrence on
+                                // the mantissa (skip_cells above): those cells are taken in one stride, in registers.  One
+                                // real subtraction carries |ds| over what the recurrence does not cover (the change of
+                                // binade, an odd mantissa under a rounding tie), then the next stride.
                                 const uint32_t mw = (sw.y & 0x7fffffu) | 0x800000u;
                                 const int ewb = (int)(sw.y >> 23);
                                 float a = fabsf(ds);
-                                const float lim = fadd(w, fmul(fadd(P.length, a), 4.76837158203125e-07f)); // w + 2^-21 (L + |ds|)
                                 const float w4 = fmul(w, P.stride_min);
                                 const uint32_t total = (uint32_t)((int)(e_stop - e_addr) * dir) / (uint32_t)kStep; // cells to the stop
                                 uint32_t done = 0u;
 #pragma unroll 1
                                 for (int round = 0; round < 8; ++round) {
                                     const uint32_t rem = total - done;
-                                    if (rem < 4u || !(a > w4)) break; // a handful of cells left: the exact loop is cheaper
+                                    if (rem < 4u || !(a > w4)) break; // a handful of cells left: the loops below are cheaper
                                     float an;
                                     done += skip_cells(a, mw, ewb, lim, rem, an);
                                     a = an;
@@ -377,9 +379,22 @@ __global__ void __maxnreg__((RegCap<TRACE, MODE>::k)) transport_kernel(const Tra
                                 if (done) {
                                     ds = copysignf(a, ds);
                                     e_addr += (uint32_t)(stride * (int)done);
-                                    xc = ld_edge(e_addr - (uint32_t)stride);
                                 }
                             }
+#ifndef NRAPS_NO_SURE_LOOP
+                            // Surely crossed cells, one by one: nothing but ds <- fl(ds -+ w) and the edge address, five
+                            // instructions per crossing against the ten of the exact step; the position is read once,
+                            // afterwards.  What is left for the exact loop is the cell the flight ends in.
+                            if (e_addr != e_stop && fabsf(ds) >= lim) {
+#pragma unroll 1
+                                do {
+                                    ds = fadd(ds, tn);
+                                    e_addr += (uint32_t)stride;
+                                } while ((e_addr != e_stop) & (fabsf(ds) >= lim));
+                                asm volatile("" : "+r"(e_addr)); // or the compiler carries e_addr - stride through the loop
+                            }
+#endif
+                            xc = ld_edge(e_addr - (uint32_t)stride); // the edge crossed last
                             if (e_addr != e_stop) {
                                 // not unrolled: ten instructions per crossing either way (measured 7.90e8 / 4.62e8
                                 // histories/s on configs 3 / 4 against 7.91e8 / 4.57e8 unrolled by four)

@@ -728,7 +728,14 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     // tally rows, as long as the block still fits twice on an SM.
     uint32_t batch = 1;
     if (allow_batch && !big && o->source_mode == NRAPS_SOURCE_UNIFORM_FUEL && o->kernel_variant == NRAPS_KERNEL_FUSED) {
-        uint64_t want = std::min<uint64_t>(std::min<uint64_t>((1ull << 23) / p->histories, p->generations), 64);
+        uint64_t want = (1ull << 23) / p->histories;
+        // Larger generations fill the GPU, but every launch of the persistent kernel ends in a tail -- the last histories
+        // to start finish alone, ~0.65 ms on config 3 whatever the size of the launch (profiles/r3_size_scan.txt) -- so
+        // up to 2^25 histories a launch still carries three generations and the tail is paid once for the three.
+        uint64_t tail_batch = 3;
+        if (const char *e = std::getenv("NRAPS_TAIL_BATCH")) tail_batch = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
+        if (want < tail_batch && p->histories * tail_batch <= (1ull << 25)) want = tail_batch;
+        want = std::min<uint64_t>(std::min<uint64_t>(want, p->generations), 64);
         const uint32_t budget = 100u * 1024u;
         if (surface_fused) {
             // the split image doubles the bins per generation: keep it if the whole batch still fits, else the unified one

@@ -124,6 +124,21 @@ def test_batched_generations_bit_exact(case, tracking, H, gens):
             assert np.array_equal(tally, got.tally_fixed[gen])
 
 
+def test_large_generations_share_a_launch_bit_exact(monkeypatch):
+    """Up to 2^25 histories nraps_mc_run lets one launch carry three uniform-source generations, so that the tail of
+    the persistent kernel is paid once for the three (NRAPS_TAIL_BATCH overrides the count).  3e6 histories per
+    generation used to go two per launch: every generation's tally, k and the folded results must equal the oracle's,
+    and the run with one generation per launch."""
+    got, want = _both("c", generations=4, histories=3_000_000, skip=1)
+    _assert_identical(got, want)
+    monkeypatch.setenv("NRAPS_TAIL_BATCH", "1")
+    v, xs, dx, mesh, fuel = load_case("c")
+    one = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=4, histories=3_000_000, skip=1, want_tally=True)
+    assert np.array_equal(one.tally_fixed, got.tally_fixed)
+    assert np.array_equal(one.k.view(np.uint32), got.k.view(np.uint32))
+    assert np.array_equal(one.flux.view(np.uint32), got.flux.view(np.uint32))
+
+
 @pytest.mark.parametrize("case,H,gens,skip", [("a", 100_000, 6, 4), ("b", 150_000, 3, 1), ("c", 150_000, 3, 1)])
 def test_results_bit_exact(case, H, gens, skip):
     got, want = _both(case, generations=gens, histories=H, skip=skip)

@@ -157,6 +157,37 @@ def test_plot_solution_files(tmp_path):
     assert len(rows) == 2 * G + 1 and all(len(row.split(",")) == N for row in rows)  # src/plot_solution.rs:43-52
 
 
+def test_reference_plot_reader_reads_our_csv(tmp_path):
+    """the CSV files must be the ones upstream's plot.py reads (plot.py:5-58).  The fixture holds what the
+    READING part of the reference's own plot.py -- executed unmodified on files written by nraps_plot_solution, in the
+    build container (tools/make_plot_reader_golden.py) -- bound to its variables: the live 2-group block
+    (plot.py:27-37) and, for G = 4, the 4-group block upstream keeps commented out right below it (plot.py:39-56).
+    Here: the writer still produces those very files, and every array plot.py read is the field we meant it to get."""
+    import json
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_plot_reader_golden", os.path.join(ROOT, "tools", "make_plot_reader_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fixture = json.load(open(os.path.join(ROOT, "tests", "golden", "plot_reader.json")))
+    assert [c["name"] for c in fixture["cases"]] == [c["name"] for c in gen.CASES]
+    for c in fixture["cases"]:
+        G, N, gens = c["G"], c["N"], c["gens"]
+        r = gen.results_for(G, N, gens, c["seed"])
+        d = tmp_path / c["name"]
+        d.mkdir()
+        nb.plot_solution(r, G, gens, N, c["length"], str(d))
+        for name, text in c["files"].items():
+            assert (d / name).read_text() == text, (c["name"], name)
+        read = c["read"]
+        assert read["length"] == c["length"] and read["meshed"] == N and read["generations"] == gens
+        same = lambda got, want: np.array_equal(np.asarray(got, np.float64).astype(f32), want)  # noqa: E731 -- shortest round-trip text
+        assert same(read["k"], r.k) and same(read["k_fund"], r.k_fund) and same(read["fission"], r.fission_source)
+        for g in range(G):
+            assert same(read[f"flux{g}"], r.flux[g]) and same(read[f"average{g}"], r.assembly_average[g]), (c["name"], g)
+        assert f"flux{G}" not in read and f"average{G}" not in read
+
+
 def test_average_assembly_and_k_fund_match_oracle():
     rng = np.random.default_rng(2)
     fp = C.POINTER(C.c_float)

@@ -3,8 +3,8 @@
 // of the issue slots of the surface kernel and 16 % of the Woodcock kernel, profiles/r1d, r1g).
 //
 // Replaces spawn_neutron + energy (src/mc_code.rs:7-53, 228-230); draw order cell, position, mu, chi (:46-51), or
-// site index, mu, chi in fission_bank mode.  Each thread takes a run of consecutive histories so that only the
-// first needs the full PCG32 jump; the next ones are one affine map (stride draws) further.  Output: one 32-byte
+// site index, mu, chi in fission_bank mode.  Each thread takes kRun histories 32 apart so that only the first
+// needs the full PCG32 jump; the next ones are one affine map (32 * stride draws) further.  Output: one 32-byte
 // record per history {x, mu, cell | g << 16, first tally row of its generation, rng state, -}, read back by the lane that adopts the history.
 #include "mc_lane.cuh"
 
@@ -12,7 +12,7 @@ namespace nraps {
 
 namespace {
 
-constexpr int kRun = 8; // consecutive histories per thread
+constexpr int kRun = 8; // histories per thread
 
 template <int TG, bool BANK>
 __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, uint4 *out)
@@ -34,15 +34,18 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
     const float *chi = P.xs + 2 * MG;
     const uint64_t n = (uint64_t)(P.rows / P.G) * P.hist_shard;
     const unsigned long long src_count = (BANK && P.n_peers) ? s_first[P.n_peers] : 0ull;
-    const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRun;
+    // A warp takes 32 * kRun consecutive histories and lane l the ones at l, l + 32, l + 64, ...: the 32-byte records of
+    // one store instruction are consecutive in memory (a thread that owned kRun consecutive histories wrote 256 bytes
+    // apart from its neighbour: 32 sectors per store).  The thread's next history is 32 further: one affine map, jump[5].
+    const uint64_t tid_global = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t first = (tid_global >> 5) * (32u * kRun) + (tid_global & 31u);
     if (first >= n) return;
     // record i belongs to generation i / hist_shard of the launch and history hist_begin + i % hist_shard of it;
     // its stream starts (generation * hist_total + history) * stride draws into the master stream
     uint32_t gen_local = (uint32_t)(first / P.hist_shard);
     uint64_t in_gen = first % P.hist_shard;
     uint64_t base = jump_ahead(P.rng_state, (uint64_t)gen_local * P.hist_total + P.hist_begin + in_gen, s_jump);
-    const ulonglong2 J1 = s_jump[0];
-    const uint64_t last = first + kRun < n ? first + kRun : n;
+    const ulonglong2 J32 = s_jump[5];
     if (BANK && src_count) {
         // Bank source (never batched: one generation per launch).  No gathered copy of the bank exists: a site index is
         // resolved to (rank, offset) and the 8-byte site is loaded from the rank that banked it -- over NVLink for 7 of
@@ -53,19 +56,19 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
 #pragma unroll
         for (int j = 0; j < kRun; ++j) {
             uint64_t rng = b;
-            b = J1.x * b + J1.y;
+            b = J32.x * b + J32.y;
             const uint32_t u = pcg32_next(rng, P.rng_inc);
             const unsigned long long idx = ((unsigned long long)u * src_count) >> 32;
             uint32_t r = 0;
             while (r + 1 < P.n_peers && idx >= s_first[r + 1]) ++r;
-            site[j] = first + j < last ? __ldg(P.peer_bank[r] + kBankHeader + (idx - s_first[r])) : 0ull;
+            site[j] = first + 32u * j < n ? __ldg(P.peer_bank[r] + kBankHeader + (idx - s_first[r])) : 0ull;
         }
 #pragma unroll
         for (int j = 0; j < kRun; ++j) {
-            const uint64_t i = first + j;
-            if (i >= last) break;
+            const uint64_t i = first + 32u * j;
+            if (i >= n) break;
             uint64_t rng = base;
-            base = J1.x * base + J1.y;
+            base = J32.x * base + J32.y;
             (void)pcg32_next(rng, P.rng_inc); // the site draw, already used above
             const int cell = (int)(site[j] >> 32);
             const float x = __uint_as_float((uint32_t)site[j]);
@@ -76,15 +79,9 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
         }
         return;
     }
-    for (uint64_t i = first; i < last; ++i) {
-        if (in_gen == P.hist_shard) { // the run crosses into the next generation of the batch
-            in_gen = 0;
-            ++gen_local;
-            base = jump_ahead(P.rng_state, (uint64_t)gen_local * P.hist_total + P.hist_begin, s_jump);
-        }
-        ++in_gen;
+#pragma unroll 1
+    for (uint64_t i = first; i < n; ) {
         uint64_t rng = base;
-        base = J1.x * base + J1.y; // stream of the next history
         const uint32_t u = pcg32_next(rng, P.rng_inc);
         const int cell = __ldg(P.fuel + __umulhi(u, P.NF));
         const float xi_pos = pcg32_unit(rng, P.rng_inc);
@@ -93,6 +90,16 @@ __global__ void __launch_bounds__(256) source_kernel(const TransportParams P, ui
         const int g = search_cdf_global<TG>(chi + __ldg(P.matid + cell) * G, G, pcg32_unit(rng, P.rng_inc));
         out[2 * i] = make_uint4(__float_as_uint(x), __float_as_uint(mu), (uint32_t)cell | ((uint32_t)g << 16), gen_local * P.G);
         out[2 * i + 1] = make_uint4((uint32_t)rng, (uint32_t)(rng >> 32), 0u, 0u);
+        i += 32u;
+        if (i >= first + 32u * kRun) break;
+        in_gen += 32u;
+        if (in_gen >= P.hist_shard) { // the run crosses into a later generation of the batch
+            gen_local = (uint32_t)(i / P.hist_shard);
+            in_gen = i % P.hist_shard;
+            base = jump_ahead(P.rng_state, (uint64_t)gen_local * P.hist_total + P.hist_begin + in_gen, s_jump);
+        } else {
+            base = J32.x * base + J32.y; // stream of the history 32 further
+        }
     }
 }
 

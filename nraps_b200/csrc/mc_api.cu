@@ -1292,11 +1292,12 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
     cudaEventElapsedTime(&ms, e0, e1);
     r->seconds_device = 1e-3 * (double)ms;
     const auto w1 = std::chrono::steady_clock::now();
+    const uint32_t batch_used = c->batch; // generations per launch (the context is gone after bail)
     rc = bail(NRAPS_OK);
     if (timing)
         std::fprintf(stderr, "{\"nraps_mc_run_ms\": {\"cuda_context\": %.1f, \"create_tables_buffers\": %.1f, \"enqueue_generations\": %.1f, "
                              "\"wait_and_fetch\": %.1f, \"destroy\": %.1f, \"device_generations\": %.1f, \"batch\": %u}}\n",
-                     ms_context, ms_create, ms_enqueue, ms_fetch, since(w1), (double)ms, 0u);
+                     ms_context, ms_create, ms_enqueue, ms_fetch, since(w1), (double)ms, batch_used);
     return rc;
 }
 

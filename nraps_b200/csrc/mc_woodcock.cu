@@ -18,8 +18,15 @@ namespace nraps {
 
 namespace {
 
+// Register budget per instantiation (see RegCap in mc_transport.cu): blocks of 1024 threads must be launchable (64);
+// the production instantiations are asked for NRAPS_WREG registers so that two blocks of 640 threads share an SM.
+#ifndef NRAPS_WREG
+#define NRAPS_WREG 48
+#endif
+template <bool TRACE, bool BIG> struct WoodcockRegCap { static constexpr int k = (!TRACE && !BIG) ? NRAPS_WREG : 64; };
+
 template <int TG, bool TRACE, bool BANK, bool BIG>
-__global__ void __launch_bounds__(1024, 1) woodcock_kernel(const TransportParams P)
+__global__ void __maxnreg__((WoodcockRegCap<TRACE, BIG>::k)) woodcock_kernel(const TransportParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = TG ? TG : (int)P.G;

@@ -529,7 +529,10 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
 
     TransportParams P{};
     P.segw = c->d_segw; P.diff = c->d_diff; P.surf_mode = c->surf_mode; P.skip_walk = c->skip_walk; P.length = c->length;
-    P.stride_min = c->opt.walk_cap > 0 ? (float)c->opt.walk_cap : 6.0f; // swept on config 4: 2 -> 4.0e8, 4 -> 4.3e8, 6 -> 4.5e8, 12 -> 4.4e8, 24 -> 4.0e8
+    // closed-form strides while |ds| exceeds the first power of two >= stride_min cell widths; swept on config 4 with that
+    // rounding: 3 -> 4.73e8, 4 -> 4.69e8, 6 -> 4.88e8, 8 / 10 / 12 -> 4.77e8 (without it 6 -> 4.76e8, 12 -> 4.89e8: luck of
+    // where 6 or 12 widths of this mesh fall inside a binade)
+    P.stride_min = c->opt.walk_cap > 0 ? (float)c->opt.walk_cap : 6.0f;
     P.edges = c->d_edges; P.runb = c->d_runb; P.matid = c->d_matid; P.fuel = c->d_fuel; P.xs = c->d_xs; P.jump = c->d_jump;
     P.M = c->M; P.G = c->G; P.N = c->N; P.NF = c->NF; P.NB = c->NB; P.bucket = c->d_bucket; P.inv_h = c->inv_h; P.big = c->big;
     P.boundl = c->boundl; P.boundr = c->boundr; P.dx_fuel = c->dx_fuel;

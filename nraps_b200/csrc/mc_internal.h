@@ -111,7 +111,7 @@ struct TransportParams {
     uint32_t surf_mode;      // SURF_SPLIT / SURF_UNIFIED / SURF_GLOBAL
     uint32_t skip_walk;      // surface kernel: stride over the surely-crossed cells of a segment in closed form (fine meshes)
     float length;            // right edge of the slab (bounds the rounding of x + ds)
-    float stride_min;        // closed-form strides only while |ds| > stride_min * w (fewer cells than that: the exact loop)
+    float stride_min;        // closed-form strides only while |ds| > the first power of two >= stride_min * w (then cell by cell)
     uint32_t diff_hi_off, direct_hi_off; // surface kernel: byte distance from the low to the high words of a shared-memory bin array
                                          // (host-computed from SurfLayout: the kernel reads them in the rare carry path only)
     uint32_t M, G, N, NF, NB, big;

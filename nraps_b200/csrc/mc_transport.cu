@@ -362,7 +362,9 @@ __global__ void __maxnreg__((RegCap<TRACE, MODE>::k)) transport_kernel(const Tra
                                 const uint32_t mw = (sw.y & 0x7fffffu) | 0x800000u;
                                 const int ewb = (int)(sw.y >> 23);
                                 float a = fabsf(ds);
-                                const float w4 = fmul(w, P.stride_min);
+                                // strides stop at the first power of two >= stride_min * w: the last stride then ends with
+                                // its binade instead of a few cells into the next one (a stride costs a dozen crossings)
+                                const float w4 = __uint_as_float((__float_as_uint(fmul(w, P.stride_min)) + 0x7fffffu) & 0xff800000u);
                                 const uint32_t total = (uint32_t)((int)(e_stop - e_addr) * dir) / (uint32_t)kStep; // cells to the stop
                                 uint32_t done = 0u;
 #pragma unroll 1

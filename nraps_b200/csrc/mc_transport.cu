@@ -445,9 +445,14 @@ __global__ void __maxnreg__((RegCap<TRACE, MODE>::k)) transport_kernel(const Tra
                     const float wgt = fmul(fmul(nusigf, s_inv_sigtr[xs]), inv_k);
                     const uint32_t n = (uint32_t)__float2int_rz(fadd(wgt, pcg32_unit(rng, inc)));
                     const unsigned long long site = ((unsigned long long)(uint32_t)cell << 32) | __float_as_uint(end);
-                    for (uint32_t j = 0; j < n; ++j) {
-                        if (h_bank < P.bank_cap) P.slots[(size_t)y * P.bank_cap + h_bank] = site;
-                        ++h_bank;
+                    if (n) { // a history's sites fill its slot row in order; what does not fit is counted, not kept
+                        const uint32_t have = h_bank < P.bank_cap ? h_bank : P.bank_cap;
+                        uint32_t fit = P.bank_cap - have;
+                        fit = n < fit ? n : fit;
+                        unsigned long long *dst = P.slots + ((size_t)y * P.bank_cap + have);
+#pragma unroll 1
+                        for (; fit; --fit) *dst++ = site;
+                        h_bank += n;
                     }
                 }
             }

@@ -57,25 +57,30 @@ static Res walk_seq(const float *e, int c, int dir, float ds, float w, int stop)
     r.cell = c; r.ds = ds; r.x = xc; return r;
 }
 
-static long g_skipped = 0, g_steps = 0, g_rounds = 0;
+static long g_skipped = 0, g_steps = 0, g_rounds = 0, g_sure = 0;
+// the walk as mc_transport.cu does it: closed-form strides while |ds| exceeds the first power of two >= 6 widths, then
+// the surely-crossed cells one by one without the test (ds <- fl(ds -+ w) only), then the reference's own step
 static Res walk_cf(const float *e, int c, int dir, float ds, float w, int stop, float L)
 {
     Res r; int fwd = dir > 0; float xc = e[c + (fwd ? 0 : 1)]; const float tn = fwd ? -w : w;
     const uint32_t iw = f2u(w); const uint32_t mw = (iw & 0x7fffffu) | 0x800000u; const int ewb = (int)(iw >> 23);
     r.collided = 0; r.end = 0;
-    const float lim = w + (L + fabsf(ds)) * 4.76837158e-07f; // 2^-21
+    const float lim = fmaf(L + fabsf(ds), 4.76837158203125e-07f, w); // w + 2^-21 (L + |ds|)
+    const float w4 = u2f((f2u(w * 6.0f) + 0x7fffffu) & 0xff800000u); // first power of two >= 6 w
     const uint32_t total = (uint32_t)((stop - c) * dir);
     uint32_t done = 0; float a = fabsf(ds);
     for (int round = 0; round < 8; ++round) {
         const uint32_t rem = total - done;
-        if (rem < 4 || !(a > 4.0f * w)) break;
+        if (rem < 4 || !(a > w4)) break;
         ++g_rounds;
         float an; const uint32_t j = jump(a, mw, ewb, lim, rem, &an);
         a = an; done += j;
         if (done == total || !(a >= lim)) break;
         a = a - w; done += 1;            // one exact decrement: binade transition / parity fix; the cell is surely crossed
     }
-    if (done) { ds = ds < 0 ? -a : a; c += (int)done * dir; xc = e[c + (fwd ? 0 : 1)]; g_skipped += done; }
+    if (done) { ds = ds < 0 ? -a : a; c += (int)done * dir; g_skipped += done; }
+    while (c != stop && fabsf(ds) >= lim) { ds = ds + tn; c += dir; ++g_sure; }   // the sure loop: no test, no position
+    xc = e[c + (fwd ? 0 : 1)];                                                    // the edge crossed last
     while (c != stop) {
         r.end = xc + ds; float d = r.end - xc; ++g_steps;
         if (!(fabsf(d) > w)) { r.collided = 1; break; }
@@ -112,6 +117,11 @@ int main(int argc, char **argv)
             while (hi < N && segid[hi] == segid[c] && f2u(e[hi + 1] - e[hi]) == f2u(w)) ++hi;
             int stop = dir > 0 ? hi : lo - 1;
             double mag = lrand48() % 3 == 0 ? drand48() * 40.0 : (lrand48() % 2 ? drand48() * 3.0 : drand48() * (hi - lo) * w * 1.2);
+            if (lrand48() % 4 == 0) { // adversarial: |ds| lands within +-10 % of the sure-crossing margin, or within an ulp or two of a whole number of widths, after k cells
+                const double k = (double)(lrand48() % (hi - lo + 2));
+                mag = lrand48() % 2 ? k * w + w * 0.5 + (L + k * w) * 4.76837158203125e-07 * (0.9 + 0.2 * drand48())
+                                    : k * w + w * 0.5 + (drand48() - 0.5) * 4e-6;
+            }
             float ds = (float)(dir * (w * 0.5 + mag));
             Res a = walk_seq(e, c, dir, ds, w, stop), b = walk_cf(e, c, dir, ds, w, stop, L);
             if (a.cell != b.cell || f2u(a.ds) != f2u(b.ds) || a.collided != b.collided || f2u(a.x) != f2u(b.x) || (a.collided && f2u(a.end) != f2u(b.end))) {
@@ -119,7 +129,7 @@ int main(int argc, char **argv)
                 ++bad;
             }
         }
-        printf("mesh mpfr=%d N=%d L=%.4f: bad so far %ld, skipped %ld exact steps %ld rounds %ld\n", mpfr, N, L, bad, g_skipped, g_steps, g_rounds);
+        printf("mesh mpfr=%d N=%d L=%.4f: bad so far %ld, skipped %ld sure steps %ld exact steps %ld rounds %ld\n", mpfr, N, L, bad, g_skipped, g_sure, g_steps, g_rounds);
     }
     return bad != 0;
 }

@@ -32,8 +32,11 @@
 // only), so tally = direct + prefix_sum(diff) (tally_prefix_kernel) equals the
 // cell-by-cell sums of the oracle bit for bit, for any scheduling.  Only the
 // partial cells at the two ends of a flight are still scored one by one.
-// On fine meshes the surely-crossed cells of a segment are not even walked:
-// skip_cells() takes them in closed-form strides (see there).
+// While |ds| is so large that the reference's test cannot fail (|ds| >= w + 2^-21 (L + |ds|)) a crossing changes
+// nothing but ds <- fl(ds -+ w) and the edge address: those cells go through a loop of five instructions, the
+// position is read once afterwards, and the ten-instruction step is left with the cell the flight ends in.
+// On fine meshes most of the surely-crossed cells of a segment are not even walked: skip_cells() takes them in
+// closed-form strides (see there).
 #include "mc_lane.cuh"
 
 namespace nraps {
@@ -398,8 +401,8 @@ __global__ void __maxnreg__((RegCap<TRACE, MODE>::k)) transport_kernel(const Tra
 #endif
                             xc = ld_edge(e_addr - (uint32_t)stride); // the edge crossed last
                             if (e_addr != e_stop) {
-                                // not unrolled: ten instructions per crossing either way (measured 7.90e8 / 4.62e8
-                                // histories/s on configs 3 / 4 against 7.91e8 / 4.57e8 unrolled by four)
+                                // the reference's own step, for the cell the flight ends in (one iteration in 99 % of the
+                                // trips).  Not unrolled: measured the same unrolled by four when it still did all the cells.
 #pragma unroll 1
                                 while (step()) {}
                             }

@@ -84,7 +84,8 @@ typedef struct nraps_options {
                                     * walks predicted to cross >= this many cells form the "long" list (0 = split by run length) */
     int32_t walk_cap;              /* tuning knob of the surface kernel's walk.  Round 1: crossings before a warp regroups (gone:
                                     * with range-update tallies a lane walks to the end of its segment).  Round 2, fine meshes:
-                                    * > 0 = closed-form strides only while |ds| > walk_cap cell widths (0 = auto, 6);
+                                    * > 0 = closed-form strides only while |ds| > the first power of two >= walk_cap cell
+                                    * widths (0 = auto, 6);
                                     * -2 = never stride (cell-by-cell loop only).  No value changes a result bit. */
     int32_t slots_per_thread;      /* block_event variant: neutrons banked per thread of a block; 0 = 3 (was reserved1) */
     uint64_t max_flights;          /* per-history safety cap; 0 = 1<<24               */

@@ -326,8 +326,14 @@ def run_ours(a):
         clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
         ms_total = t_begin.elapsed_time(t_end)
         ms_kernel = sum(e0.elapsed_time(e1) for e0, e1 in kernel_ev) / k_steps
+        if not bank and red.pipelined:
+            # uniform source: the launches of consecutive generations are pipelined on two streams (OverlappedReducer), so
+            # the events of one launch span the end of the launch before it; the kernel time of a generation is the
+            # rate at which launches complete over the timed region
+            ms_kernel = ms_total / k_steps
         ms_coll = sum(e0.elapsed_time(e1) for e0, e1 in coll_ev) / k_steps if coll_ev else 0.0
         out = dict(H=H, count=count, res=ctx.fetch(main.cuda_stream), info=ctx.launch_info(), clocks=clocks, bank=bank,
+                   pipelined=(not bank) and red.pipelined,
                    scaling=scaling, desc=desc)
         if phases:
             p1 = ctx.phase_ms()
@@ -437,7 +443,7 @@ def run_ours(a):
             "data": "synthetic",
             "config": workload_config(a.workload, world, a.tracking),
             "details": {"histories_per_gpu": count, "generations_timed": K, "kernel_variant": a.variant,
-                        "parallelism": f"history-sharded x{world}; int64 tally all-reduce per generation on a side stream, overlapped with the next generation",
+                        "parallelism": f"history-sharded x{world}; int64 tally all-reduce + finalize per generation on a side stream, overlapped with the next generation" + ("; launches of consecutive generations alternate between two streams" if head["pipelined"] else ""),
                         "launch": info, "l2": "256 MiB device memset between steps inside the timed region (kernel inputs are ~12 KB of tables)"},
             "clocks": head["clocks"],
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
@@ -451,8 +457,11 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": facts.get("bytes"), "peak_source": peak_src,
                          "kernel": kname + "<4,false,%s>" % ("true" if head["bank"] else "false"), "kernel_ms": ms_kernel,
-                         "kernel_ms_note": "births + transport + tally prefix sum of one generation (CUDA events on the launching stream); "
-                                           "the transport kernel is > 98 % of it (profiles/ launch list)",
+                         "kernel_ms_note": ("births + transport + tally prefix sum of one generation (CUDA events on the launching stream); "
+                                            "the transport kernel is > 98 % of it (profiles/ launch list)") if not head["pipelined"] else
+                                           ("timed region / K: consecutive generations are launched on two streams so that the next launch fills "
+                                            "the tail of the one before (uniform source: independent generations), per-launch events would overlap; "
+                                            "births, L2 flush and tally prefix sum are inside, the transport kernel is > 98 % of it (profiles/ launch list)"),
                          "bytes_per_history": b_hist, "collisions_per_history": coll_per_hist,
                          "actual_limiter": {"what": "instruction issue (ncu, profiles/)", **{k: v for k, v in facts.items() if k not in ("bytes", "source", "round1")}},
                          "note": "algorithmic bytes = 24 + 48*collisions/history (SURVEY 8d bank model); the fused kernel keeps "

@@ -159,6 +159,12 @@ int nraps_mc_finalize_generation(nraps_mc_ctx *ctx, uint64_t gen, void *stream);
  * follow (cell histogram of the generation's bank).  n_words is what a multi-GPU host all-reduces. */
 int nraps_mc_tally_buffer(nraps_mc_ctx *ctx, void **device_ptr, uint64_t *n_words);
 int nraps_mc_set_tally_buffer(nraps_mc_ctx *ctx, void *device_ptr); /* caller-owned, same size */
+/* A transport launch owns a set of scratch buffers (birth records, chunk cursor, difference array) until its kernels are
+ * done; a context has two such sets.  nraps_mc_select_lane(ctx, 0 | 1) chooses the set the following nraps_mc_transport
+ * calls use (default 0), so that -- uniform source only: generations independent -- generation g+1 can be launched on a
+ * second stream, into a second tally buffer, while the tail of generation g still runs.  The caller orders the reuse of
+ * a lane and of a tally buffer (same stream, or events); finalize calls stay in generation order. */
+int nraps_mc_select_lane(nraps_mc_ctx *ctx, int32_t lane);
 int nraps_mc_read_tally(nraps_mc_ctx *ctx, uint64_t *host_words, void *stream);      /* synchronous */
 int nraps_mc_fetch(nraps_mc_ctx *ctx, nraps_results *r, void *stream);               /* synchronous */
 /* replay: run [hist_begin, hist_begin+hist_count) of `gen` and return one record per history (synchronous) */

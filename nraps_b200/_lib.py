@@ -83,7 +83,7 @@ class Mesh(C.Structure):
 # every symbol include/nraps_mc.h and include/nraps_host.h declare
 EXPORTS = [
     "nraps_mc_run", "nraps_mc_create", "nraps_mc_destroy", "nraps_mc_trim", "nraps_mc_reset", "nraps_mc_transport",
-    "nraps_mc_finalize_generation", "nraps_mc_tally_buffer", "nraps_mc_set_tally_buffer", "nraps_mc_read_tally",
+    "nraps_mc_finalize_generation", "nraps_mc_tally_buffer", "nraps_mc_set_tally_buffer", "nraps_mc_select_lane", "nraps_mc_read_tally",
     "nraps_mc_fetch", "nraps_mc_trace", "nraps_mc_launch_info", "nraps_mc_bank_compact", "nraps_mc_bank_local",
     "nraps_mc_bank_advance", "nraps_mc_bank_reserve", "nraps_mc_bank_export", "nraps_mc_bank_import", "nraps_mc_bank_peers",
     "nraps_mc_phase_ms", "nraps_dev_logf", "nraps_dev_div", "nraps_dev_pcg32",
@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
     L.nraps_mc_finalize_generation.argtypes = [vp, C.c_uint64, vp]
     L.nraps_mc_tally_buffer.argtypes = [vp, C.POINTER(vp), _u64p]
     L.nraps_mc_set_tally_buffer.argtypes = [vp, vp]
+    L.nraps_mc_select_lane.argtypes = [vp, C.c_int32]
     L.nraps_mc_read_tally.argtypes = [vp, _u64p, vp]
     L.nraps_mc_fetch.argtypes = [vp, C.POINTER(Results), vp]
     L.nraps_mc_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, vp]

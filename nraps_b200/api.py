@@ -300,6 +300,11 @@ class MonteCarloContext:
         n = self.histories - hist_begin if hist_count is None else hist_count
         check(lib().nraps_mc_transport(self._h, gen, hist_begin, n, C.c_void_p(stream)), "nraps_mc_transport")
 
+    def select_lane(self, lane: int):
+        """Scratch-buffer set (0 or 1) of the following transport calls: lets generation g+1 of the uniform source be
+        launched on a second stream while the tail of generation g still runs (nraps_mc_select_lane)."""
+        check(lib().nraps_mc_select_lane(self._h, int(lane)), "nraps_mc_select_lane")
+
     def finalize_generation(self, gen: int, stream=None):
         check(lib().nraps_mc_finalize_generation(self._h, gen, C.c_void_p(stream)), "nraps_mc_finalize_generation")
 

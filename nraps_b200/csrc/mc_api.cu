@@ -269,7 +269,17 @@ struct nraps_mc_ctx {
     float *d_edges = nullptr, *d_xs = nullptr, *d_dx = nullptr, *d_nut = nullptr, *d_sigf = nullptr;
     uint32_t *d_runb = nullptr;
     uint2 *d_segw = nullptr;                 // surface kernel: segment bounds + width bits per cell
-    unsigned long long *d_diff = nullptr;    // surface kernel: difference array of the full-cell scores [batch*G*N]
+    // Per-launch scratch that a transport launch owns until its kernels are done: the difference array of the surface
+    // kernel's full-cell scores [batch*G*N], the chunk cursor, the birth records of the shard.  Two sets ("lanes",
+    // nraps_mc_select_lane): with the uniform source generation g+1 may be launched on a second stream while the tail
+    // of generation g still runs -- its blocks move in as blocks of g retire.
+    struct LaneBuffers {
+        unsigned long long *d_diff = nullptr, *d_work = nullptr;
+        uint4 *d_source = nullptr; // born neutrons of the current shard (source_kernel -> transport kernels)
+        uint64_t source_cap = 0;
+    } lanes[2];
+    int lane = 0;
+    uint64_t diff_words = 0; // size of a d_diff
     uint8_t *d_matid = nullptr;
     uint16_t *d_fuel = nullptr, *d_bucket = nullptr;
     uint32_t NB = 0;
@@ -278,13 +288,11 @@ struct nraps_mc_ctx {
     uint32_t prepared = 0, big = 0;
     uint32_t batch = 1; // generations one launch may carry (small generations do not fill the GPU on their own)
     ulonglong2 *d_jump = nullptr;
-    unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_work = nullptr, *d_counters_total = nullptr;
+    unsigned long long *d_tally_own = nullptr, *d_tally = nullptr, *d_counters_total = nullptr;
     double *d_res_moments = nullptr;
     float *d_terms = nullptr, *d_res_flux = nullptr, *d_res_fission = nullptr, *d_k_hist = nullptr, *d_k_cur = nullptr;
     uint32_t *d_trace = nullptr;
     uint64_t trace_cap = 0;
-    uint4 *d_source = nullptr; // born neutrons of the current shard (source_kernel -> transport kernels)
-    uint64_t source_cap = 0;
 
     // fission_bank source mode
     bool bank_mode = false;
@@ -419,11 +427,12 @@ void free_ctx(nraps_mc_ctx *c)
 {
     if (!c) return;
     dev_free(c->d_edges); dev_free(c->d_xs); dev_free(c->d_dx); dev_free(c->d_nut); dev_free(c->d_sigf);
-    dev_free(c->d_segw); dev_free(c->d_diff);
+    dev_free(c->d_segw);
+    for (auto &ln : c->lanes) { dev_free(ln.d_diff); dev_free(ln.d_work); dev_free(ln.d_source); }
     dev_free(c->d_runb); dev_free(c->d_matid); dev_free(c->d_fuel); dev_free(c->d_jump); dev_free(c->d_bucket);
-    dev_free(c->d_tally_own); dev_free(c->d_work); dev_free(c->d_counters_total);
+    dev_free(c->d_tally_own); dev_free(c->d_counters_total);
     dev_free(c->d_res_moments); dev_free(c->d_terms); dev_free(c->d_res_flux); dev_free(c->d_res_fission); dev_free(c->d_k_hist); dev_free(c->d_k_cur);
-    dev_free(c->d_trace); dev_free(c->d_source);
+    dev_free(c->d_trace);
     dev_free(c->d_slots); dev_free(c->d_block_sums);
     free_bank_buffers(c);
     for (cudaEvent_t e : c->ph_ev)
@@ -513,6 +522,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     if (begin > c->histories || count > c->histories - begin) return NRAPS_ERR_SHAPE;
     if (nb < 1 || nb > c->batch || gen + nb > c->generations || (nb > 1 && (trace || c->d_tally != c->d_tally_own))) return NRAPS_ERR_STATE;
     c->last_shard = count;
+    auto &LN = c->lanes[c->lane]; // the scratch set of this launch (nraps_mc_select_lane)
     if (c->bank_mode) {
         int rc = ensure_bank(c, count, s);
         if (rc != NRAPS_OK) return rc;
@@ -522,13 +532,13 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     // bank mode: the cell histogram of the generation's bank rides behind the counters (one all-reduce for all of it)
     const uint64_t words = (uint64_t)nb * c->G * c->N + NRAPS_CT_WORDS + (c->bank_mode ? c->N : 0u);
     CU(cudaMemsetAsync(c->d_tally, 0, words * sizeof(unsigned long long), s));
-    CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(LN.d_work, 0, sizeof(unsigned long long), s));
     if (count == 0) return NRAPS_OK;
     const bool surface_fused = !c->woodcock && c->opt.kernel_variant == NRAPS_KERNEL_FUSED;
-    if (surface_fused) CU(cudaMemsetAsync(c->d_diff, 0, (uint64_t)nb * c->G * c->N * sizeof(unsigned long long), s));
+    if (surface_fused) CU(cudaMemsetAsync(LN.d_diff, 0, (uint64_t)nb * c->G * c->N * sizeof(unsigned long long), s));
 
     TransportParams P{};
-    P.segw = c->d_segw; P.diff = c->d_diff; P.surf_mode = c->surf_mode; P.skip_walk = c->skip_walk; P.length = c->length;
+    P.segw = c->d_segw; P.diff = LN.d_diff; P.surf_mode = c->surf_mode; P.skip_walk = c->skip_walk; P.length = c->length;
     // closed-form strides while |ds| exceeds the first power of two >= stride_min cell widths; swept on config 4 with that
     // rounding: 3 -> 4.73e8, 4 -> 4.69e8, 6 -> 4.88e8, 8 / 10 / 12 -> 4.77e8 (without it 6 -> 4.76e8, 12 -> 4.89e8: luck of
     // where 6 or 12 widths of this mesh fall inside a binade)
@@ -547,7 +557,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
         const SurfLayout SL = make_surface_layout(c->M, c->G, c->N, c->surf_mode, P.rows);
         P.diff_hi_off = SL.diff_hi - SL.diff_lo; P.direct_hi_off = SL.direct_hi - SL.direct_lo;
     }
-    P.work = c->d_work; P.tally = c->d_tally;
+    P.work = LN.d_work; P.tally = c->d_tally;
     P.trace = trace ? c->d_trace : nullptr;
     P.chunk = c->chunk; P.max_flights = c->max_flights;
     P.spawn_batch = c->opt.spawn_batch > 0 ? (uint32_t)std::min(c->opt.spawn_batch, 32) : (c->woodcock ? 2u : 1u);
@@ -569,17 +579,17 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     }
     if (c->opt.kernel_variant != NRAPS_KERNEL_EVENT) { // births first, every lane busy; the transport lanes adopt them
         const uint64_t births = std::min<uint64_t>((uint64_t)nb * count, sub);
-        if (births > c->source_cap) {
-            CU(dev_free(c->d_source));
-            c->d_source = nullptr; c->source_cap = 0;
-            CU(dev_malloc((void **)&c->d_source, births * 2 * sizeof(uint4)));
-            c->source_cap = births;
+        if (births > LN.source_cap) {
+            CU(dev_free(LN.d_source));
+            LN.d_source = nullptr; LN.source_cap = 0;
+            CU(dev_malloc((void **)&LN.d_source, births * 2 * sizeof(uint4)));
+            LN.source_cap = births;
         }
-        P.source = c->d_source;
+        P.source = LN.d_source;
     }
     auto births_of = [&](TransportParams &Q) -> int {
         phase_begin(c, NRAPS_PH_SOURCE, s);
-        CU(launch_source(Q, c->bank_mode, c->d_source, s));
+        CU(launch_source(Q, c->bank_mode, LN.d_source, s));
         phase_end(c, NRAPS_PH_SOURCE, s);
         return NRAPS_OK;
     };
@@ -630,7 +640,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
             Q.slots = P.slots ? P.slots + off * c->bank_cap : nullptr;
             Q.counts = P.counts ? P.counts + off : nullptr;
             Q.trace = P.trace ? P.trace + off * NRAPS_TR_WORDS : nullptr;
-            if (off) CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), s));
+            if (off) CU(cudaMemsetAsync(LN.d_work, 0, sizeof(unsigned long long), s));
         }
         { int rc = births_of(Q); if (rc != NRAPS_OK) return rc; }
         phase_begin(c, NRAPS_PH_TRANSPORT, s);
@@ -641,7 +651,7 @@ int run_transport(nraps_mc_ctx *c, uint64_t gen, uint64_t begin, uint64_t count,
     if (!c->woodcock) {
         // the cells a flight crossed completely were booked as range updates: fold their prefix sums into the tally
         phase_begin(c, NRAPS_PH_PREFIX, s);
-        CU(launch_tally_prefix(c->d_diff, c->d_tally, nb * c->G, c->N, s));
+        CU(launch_tally_prefix(LN.d_diff, c->d_tally, nb * c->G, c->N, s));
         phase_end(c, NRAPS_PH_PREFIX, s);
     }
     return NRAPS_OK;
@@ -895,11 +905,12 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return r == cudaSuccess; };
     ok(upload(&c->d_edges, edges)); ok(upload(&c->d_runb, runb)); ok(upload(&c->d_matid, matid)); ok(upload(&c->d_segw, segw));
-    ok(dev_malloc((void **)&c->d_diff, batch * GN * sizeof(unsigned long long)));
+    c->diff_words = batch * GN;
+    ok(dev_malloc((void **)&c->lanes[0].d_diff, c->diff_words * sizeof(unsigned long long)));
     ok(upload(&c->d_fuel, fuel)); ok(upload(&c->d_xs, xs)); ok(upload(&c->d_jump, jump)); ok(upload(&c->d_bucket, bucket));
     ok(upload(&c->d_dx, dx)); ok(upload(&c->d_nut, nut)); ok(upload(&c->d_sigf, sigf));
     ok(dev_malloc((void **)&c->d_tally_own, (batch * GN + NRAPS_CT_WORDS + N) * sizeof(unsigned long long)));
-    ok(dev_malloc((void **)&c->d_work, sizeof(unsigned long long)));
+    ok(dev_malloc((void **)&c->lanes[0].d_work, sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_counters_total, NRAPS_CT_WORDS * sizeof(unsigned long long)));
     ok(dev_malloc((void **)&c->d_terms, GN * sizeof(float)));
     ok(dev_malloc((void **)&c->d_res_flux, GN * sizeof(float)));
@@ -1012,6 +1023,18 @@ extern "C" int nraps_mc_set_tally_buffer(nraps_mc_ctx *c, void *device_ptr)
 {
     if (!c) return NRAPS_ERR_NULL;
     c->d_tally = device_ptr ? static_cast<unsigned long long *>(device_ptr) : c->d_tally_own;
+    return NRAPS_OK;
+}
+
+extern "C" int nraps_mc_select_lane(nraps_mc_ctx *c, int32_t lane)
+{
+    if (!c) return NRAPS_ERR_NULL;
+    if (lane < 0 || lane > 1) return NRAPS_ERR_OPTION;
+    CU(cudaSetDevice(c->device));
+    auto &ln = c->lanes[lane];
+    if (!ln.d_diff) CU(dev_malloc((void **)&ln.d_diff, std::max<uint64_t>(1, c->diff_words) * sizeof(unsigned long long)));
+    if (!ln.d_work) CU(dev_malloc((void **)&ln.d_work, sizeof(unsigned long long)));
+    c->lane = lane;
     return NRAPS_OK;
 }
 

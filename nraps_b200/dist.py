@@ -12,7 +12,8 @@ Two refinements (round 2):
 
 * uniform source: generations are independent (k cancels, src/mc_code.rs:346-351), so the all-reduce and the
   finalize of generation g run on a side stream while generation g+1 is already transporting into a second tally
-  buffer (``run_generations_overlapped``): the collective leaves the critical path.
+  buffer (``OverlappedReducer``): the collective leaves the critical path; the transports alternate between two
+  streams, so that the launch of g+1 fills the tail of g.
 * fission_bank source: nothing is gathered.  Every rank keeps the bank it compacted in a peer-mapped buffer, the
   source kernel of generation g+1 turns a site index into (rank, offset) from the ranks' site counts and loads the
   site over NVLink (``setup_bank_peers`` shares the buffers once: cuMemCreate allocations, exported file descriptors).  The per-generation all-reduce --
@@ -75,39 +76,57 @@ def run_generations(engine: GenerationEngine, tally, rank: int, world: int, *, a
 
 
 class OverlappedReducer:
-    """Uniform source on GPUs: all-reduce + finalize of generation g on a side stream while g+1 transports.
+    """Uniform source on GPUs: generations are independent, so their launches are pipelined.
 
-    Two tally tensors alternate.  Main stream: transport(g) into tally[g & 1].  Side stream: waits for that transport,
-    all-reduces the tensor, finalizes g.  Before transport(g+2) reuses tally[g & 1] the main stream waits for the
-    side stream's finalize of g.  Finalizes stay in generation order (one side stream), as k and the running flux
-    sums are sequential f32 accumulations."""
+    * all-reduce + finalize of generation g run on a side stream while g+1 transports (two tally tensors alternate);
+    * the transports themselves alternate between two streams and the context's two scratch lanes
+      (``select_lane``): the launch of g+1 is already queued on the device while the tail of g runs -- the last
+      neutrons of a persistent launch finish one by one, ~0.6 ms with most of the GPU idle -- and its blocks move in as
+      blocks of g retire (8.72e8 -> 8.90e8 histories/s on config 3).  ``pipeline=False`` keeps
+      every transport on the main stream.
 
-    def __init__(self, ctx, world: int, device: int, main_stream=None):
+    Order kept by events: transport(g) waits for the finalize of g-2 (same tally tensor, same lane and stream); the side
+    stream takes the generations in order (k and the running flux sums are sequential f32 accumulations)."""
+
+    def __init__(self, ctx, world: int, device: int, main_stream=None, pipeline: bool = True):
         import torch
+
+        import os
 
         self.torch, self.ctx, self.world = torch, ctx, world
         dev = f"cuda:{device}"
+        pipeline = pipeline and os.environ.get("NRAPS_PIPELINE", "1") != "0"  # 0: every transport on the main stream (A/B)
+        self.pipelined = pipeline
         self.tallies = [torch.zeros(ctx.n_words, dtype=torch.int64, device=dev) for _ in range(2)]
         self.main = main_stream if main_stream is not None else torch.cuda.current_stream()
+        self.streams = [self.main, torch.cuda.Stream(device=dev) if pipeline else self.main]
         self.side = torch.cuda.Stream(device=dev)
         self.done = [None, None]   # side-stream events: finalize of the generation that last used the tensor
+        self.last = [None, None]   # transport-stream events: end of the last launch on each stream
         self.launched = 0
+        start = torch.cuda.Event()
+        start.record(self.main)    # whatever the main stream was doing (tables, earlier runs) comes first on both
+        self.streams[1].wait_event(start)
 
     def step(self, gen: int, hist_begin: int, hist_count: int, before_transport=None, after_transport=None):
         torch = self.torch
         import torch.distributed as dist
 
-        t = self.tallies[gen & 1]
-        if self.done[gen & 1] is not None:
-            self.main.wait_event(self.done[gen & 1])
-        self.ctx.use_tally_tensor(t)
-        if before_transport is not None:
-            before_transport()
-        self.ctx.transport(gen, hist_begin, hist_count, self.main.cuda_stream)
-        if after_transport is not None:
-            after_transport()
-        ready = torch.cuda.Event()
-        ready.record(self.main)
+        lane = gen & 1
+        t, stream = self.tallies[lane], self.streams[lane]
+        with torch.cuda.stream(stream):   # the callbacks' torch work (L2 flush, timing events) goes where the launch goes
+            if self.done[lane] is not None:
+                stream.wait_event(self.done[lane])
+            self.ctx.select_lane(lane)
+            self.ctx.use_tally_tensor(t)
+            if before_transport is not None:
+                before_transport()
+            self.ctx.transport(gen, hist_begin, hist_count, stream.cuda_stream)
+            if after_transport is not None:
+                after_transport()
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        self.last[lane] = ready
         self.side.wait_event(ready)
         with torch.cuda.stream(self.side):
             if self.world > 1:
@@ -117,12 +136,12 @@ class OverlappedReducer:
             self.ctx.finalize_generation(gen, self.side.cuda_stream)
             ev = torch.cuda.Event()
             ev.record(self.side)
-        self.done[gen & 1] = ev
+        self.done[lane] = ev
         self.launched += 1
 
     def drain(self):
-        """Main stream waits for everything the side stream still owes."""
-        for ev in self.done:
+        """Main stream waits for everything the other streams still owe."""
+        for ev in self.done + self.last:
             if ev is not None:
                 self.main.wait_event(ev)
 

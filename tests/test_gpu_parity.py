@@ -124,6 +124,30 @@ def test_batched_generations_bit_exact(case, tracking, H, gens):
             assert np.array_equal(tally, got.tally_fixed[gen])
 
 
+def test_pipelined_generations_bit_exact():
+    """Uniform source: the launches of consecutive generations alternate between two streams and the context's two
+    scratch lanes (nraps_mc_select_lane), all-reduce + finalize on a side stream (OverlappedReducer).  k, flux and the
+    fission source must equal nraps_mc_run's, whatever overlaps on the device; small generations so that launches
+    really are in flight together, and a larger one."""
+    import torch
+
+    from nraps_b200.dist import OverlappedReducer
+
+    for case, H, gens in (("c", 2_000, 12), ("a", 300_000, 7)):
+        v, xs, dx, mesh, fuel = load_case(case)
+        want = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1)
+        for pipeline in (True, False):
+            with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1) as ctx:
+                red = OverlappedReducer(ctx, 1, 0, torch.cuda.current_stream(), pipeline=pipeline)
+                for gen in range(gens):
+                    red.step(gen, 0, H)
+                red.drain()
+                got = ctx.fetch(torch.cuda.current_stream().cuda_stream)
+            for name in ("k", "k_fund", "flux", "assembly_average", "fission_source"):
+                assert np.array_equal(bits(getattr(got, name)), bits(getattr(want, name))), (case, pipeline, name)
+            assert got.counters["collisions"] == want.counters["collisions"]
+
+
 def test_large_generations_share_a_launch_bit_exact(monkeypatch):
     """Up to 2^25 histories nraps_mc_run lets one launch carry three uniform-source generations, so that the tail of
     the persistent kernel is paid once for the three (NRAPS_TAIL_BATCH overrides the count).  3e6 histories per

@@ -743,9 +743,11 @@ int create_ctx(const nraps_problem *p, const nraps_options *o, nraps_mc_ctx **ou
     if (allow_batch && !big && o->source_mode == NRAPS_SOURCE_UNIFORM_FUEL && o->kernel_variant == NRAPS_KERNEL_FUSED) {
         uint64_t want = (1ull << 23) / p->histories;
         // Larger generations fill the GPU, but every launch of the persistent kernel ends in a tail -- the last histories
-        // to start finish alone, ~0.65 ms on config 3 whatever the size of the launch (profiles/r3_size_scan.txt) -- so
-        // up to 2^25 histories a launch still carries three generations and the tail is paid once for the three.
-        uint64_t tail_batch = 3;
+        // to start finish alone, ~0.6 ms on config 3 whatever the size of the launch (profiles/r3_size_scan.txt).  A launch
+        // can carry NRAPS_TAIL_BATCH generations up to 2^25 histories so that the tail is paid once for them (measured:
+        // three per launch save 2 % on config 3 but need a birth buffer three times the size); by default the launches
+        // of large generations are pipelined on two streams instead (nraps_mc_run).
+        uint64_t tail_batch = 1; // (3 was the default until the launches were pipelined instead, see nraps_mc_run: no 1 GB birth buffer)
         if (const char *e = std::getenv("NRAPS_TAIL_BATCH")) tail_batch = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
         if (want < tail_batch && p->histories * tail_batch <= (1ull << 25)) want = tail_batch;
         want = std::min<uint64_t>(std::min<uint64_t>(want, p->generations), 64);
@@ -1279,12 +1281,18 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
     const double ms_create = since(w0) - ms_context;
     if (!o->quiet) { std::printf("running MC code\n"); std::fflush(stdout); } // src/mc_code.rs:292
 
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaStream_t s = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, fin[2] = {nullptr, nullptr};
+    cudaStream_t s = nullptr, s2 = nullptr;
+    unsigned long long *tally2 = nullptr;
     auto bail = [&](int code) {
+        if (s2) cudaStreamSynchronize(s2);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
+        for (cudaEvent_t f : fin) if (f) cudaEventDestroy(f);
         if (s) cudaStreamDestroy(s);
+        if (s2) cudaStreamDestroy(s2);
+        c->d_tally = c->d_tally_own; // tally2 is not the context's to free
+        dev_free(tally2);
         nraps_mc_destroy(c);
         return code;
     };
@@ -1293,7 +1301,37 @@ extern "C" int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nrap
         return bail(cuda_fail(cudaGetLastError(), "stream/event create"));
     cudaEventRecord(e0, s);
     const uint64_t GN = (uint64_t)p->G * p->N;
-    for (uint64_t gen = 0; gen < p->generations;) {
+    // Uniform source, one generation per launch: the generations are independent, so their launches alternate between two
+    // streams and the context's two scratch lanes (into two tally buffers).  The launch of g+1 is queued on the device
+    // while the tail of g runs -- the last neutrons of a persistent launch finish one by one -- and its blocks move in as
+    // blocks of g retire.  Finalizes stay in generation order (an event chain): k and the running
+    // flux sums are sequential f32 accumulations.  NRAPS_PIPELINE=0: everything on one stream.
+    const char *pipe_env = std::getenv("NRAPS_PIPELINE");
+    const bool pipelined = c->batch == 1 && !c->bank_mode && !r->tally_fixed && !o->profile_phases && p->generations > 1 &&
+                           c->opt.kernel_variant == NRAPS_KERNEL_FUSED && !(pipe_env && pipe_env[0] == '0');
+    if (pipelined) {
+        if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&fin[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&fin[1], cudaEventDisableTiming) != cudaSuccess)
+            return bail(cuda_fail(cudaGetLastError(), "stream/event create"));
+        if (dev_malloc((void **)&tally2, (GN + NRAPS_CT_WORDS + p->N) * sizeof(unsigned long long)) != cudaSuccess)
+            return bail(cuda_fail(cudaGetLastError(), "second tally buffer"));
+        for (uint64_t gen = 0; gen < p->generations; ++gen) {
+            const int lane = (int)(gen & 1u);
+            cudaStream_t st = lane ? s2 : s;
+            if ((rc = nraps_mc_select_lane(c, lane)) != NRAPS_OK) return bail(rc);
+            c->d_tally = lane ? tally2 : c->d_tally_own;
+            if ((rc = run_transport(c, gen, 0, p->histories, false, st, 1)) != NRAPS_OK) return bail(rc);
+            if (gen && cudaStreamWaitEvent(st, fin[lane ^ 1], 0) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "finalize order"));
+            if ((rc = finalize_slice(c, gen, 0, 1, st)) != NRAPS_OK) return bail(rc);
+            if (cudaEventRecord(fin[lane], st) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "finalize order"));
+        }
+        // the last finalize is after everything before it on both streams (each follows its transport and the finalize before it)
+        if (cudaStreamWaitEvent(s, fin[(p->generations - 1) & 1u], 0) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "join"));
+        c->lane = 0;
+        c->d_tally = c->d_tally_own;
+    }
+    for (uint64_t gen = pipelined ? p->generations : 0; gen < p->generations;) {
         const uint32_t nb = (uint32_t)std::min<uint64_t>(c->batch, p->generations - gen);
         if ((rc = run_transport(c, gen, 0, p->histories, false, s, nb)) != NRAPS_OK) return bail(rc);
         if (r->tally_fixed) {

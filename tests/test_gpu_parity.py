@@ -135,7 +135,7 @@ def test_pipelined_generations_bit_exact():
 
     for case, H, gens in (("c", 2_000, 12), ("a", 300_000, 7)):
         v, xs, dx, mesh, fuel = load_case(case)
-        want = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1)
+        want = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1, want_tally=True)  # one stream
         for pipeline in (True, False):
             with nb.MonteCarloContext(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1) as ctx:
                 red = OverlappedReducer(ctx, 1, 0, torch.cuda.current_stream(), pipeline=pipeline)
@@ -148,19 +148,32 @@ def test_pipelined_generations_bit_exact():
             assert got.counters["collisions"] == want.counters["collisions"]
 
 
-def test_large_generations_share_a_launch_bit_exact(monkeypatch):
-    """Up to 2^25 histories nraps_mc_run lets one launch carry three uniform-source generations, so that the tail of
-    the persistent kernel is paid once for the three (NRAPS_TAIL_BATCH overrides the count).  3e6 histories per
-    generation used to go two per launch: every generation's tally, k and the folded results must equal the oracle's,
-    and the run with one generation per launch."""
-    got, want = _both("c", generations=4, histories=3_000_000, skip=1)
-    _assert_identical(got, want)
-    monkeypatch.setenv("NRAPS_TAIL_BATCH", "1")
+def test_large_generations_pipelined_or_batched_bit_exact(monkeypatch):
+    """The tail of a persistent launch (the last neutrons finish one by one) is hidden two ways in nraps_mc_run, uniform
+    source only: by default the launches of consecutive generations alternate between two streams and two scratch
+    lanes; NRAPS_TAIL_BATCH=3 lets one launch carry three generations instead (up to 2^25 histories).  Both, and the
+    plain one-stream run (NRAPS_PIPELINE=0), must give the oracle's k, flux and fission source bit for bit; the batched
+    run is also compared tally by tally (the pipelined run does not read tallies back: that path is sequential)."""
+    H, gens = 3_000_000, 5
     v, xs, dx, mesh, fuel = load_case("c")
-    one = nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=4, histories=3_000_000, skip=1, want_tally=True)
-    assert np.array_equal(one.tally_fixed, got.tally_fixed)
-    assert np.array_equal(one.k.view(np.uint32), got.k.view(np.uint32))
-    assert np.array_equal(one.flux.view(np.uint32), got.flux.view(np.uint32))
+    deck, m = oracle_inputs(v, xs, dx, mesh, fuel)
+    want = orc.monte_carlo(deck, m, generations=gens, histories=H, skip=1, threads=8, want_tally=True)
+
+    def same(got, tallies):
+        for name in ("k", "k_fund", "flux", "assembly_average", "fission_source"):
+            assert np.array_equal(bits(getattr(got, name)), bits(getattr(want, name))), name
+        assert got.counters["collisions"] == want.counters["collisions"]
+        if tallies:
+            assert np.array_equal(got.tally_fixed, want.tally_fixed)
+
+    same(nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1), False)          # pipelined
+    same(nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1, tracking_mode="surface",
+                        want_tally=True), True)                                                               # sequential (tally read-back)
+    monkeypatch.setenv("NRAPS_PIPELINE", "0")
+    same(nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1), False)
+    monkeypatch.delenv("NRAPS_PIPELINE")
+    monkeypatch.setenv("NRAPS_TAIL_BATCH", "3")
+    same(nb.monte_carlo(v, xs, dx, mesh, fuel, 1.0, generations=gens, histories=H, skip=1, want_tally=True), True)  # 3 + 2 per launch
 
 
 @pytest.mark.parametrize("case,H,gens,skip", [("a", 100_000, 6, 4), ("b", 150_000, 3, 1), ("c", 150_000, 3, 1)])

@@ -449,9 +449,9 @@ def run_ours(a):
             "e2e": {"value": H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "wall_s": e2e_s, "device_s": float(getattr(e2e_res, "seconds_device", 0.0)),
                     "note": "one monte_carlo() call: context create + table upload + K generations + result download; bytes are per run / K"
-                            + ("; the call carries up to three independent uniform-source generations per launch (one tail of the "
-                               "persistent kernel for the three: DESIGN.md section 5), `value` launches every generation on its own"
-                               if world == 1 and not head["bank"] else "")},
+                            + ("; like `value`, the call launches consecutive uniform-source generations on two alternating streams, so "
+                               "that the next launch fills the tail of the one before (DESIGN.md section 5)"
+                               if not head["bank"] else "")},
             # births + transport + tally prefix sum + finalize (+ bank: 3 compaction kernels, histogram, entropy)
             "gpu_launches": ((4 if a.tracking == "surface" else 3) + (5 if head["bank"] else 0)) * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -136,7 +136,11 @@ void nraps_options_default(nraps_options *o);
 /* Whole job on one GPU: the monte_carlo() replacement (src/mc_code.rs:276-380).  With the uniform source, generations
  * are independent, so one launch carries several small generations (up to ~2^23 histories, each generation scoring
  * into its own tally rows) and they are folded in order afterwards: results are bit-identical to one launch per
- * generation, which is what the generation-level API below always does. */
+ * generation, which is what the generation-level API below always does.  Generations large enough for a launch of their
+ * own are pipelined instead: consecutive launches alternate between two streams (see nraps_mc_select_lane), the
+ * finalizes stay in order -- same bits again.  Environment: NRAPS_PIPELINE=0 keeps every launch on one stream,
+ * NRAPS_TAIL_BATCH=n lets a launch carry n generations up to 2^25 histories, NRAPS_TIMING=1 prints the host-side
+ * split of the call on stderr. */
 int nraps_mc_run(const nraps_problem *p, const nraps_options *o, nraps_results *r);
 
 /*

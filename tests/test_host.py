@@ -438,6 +438,8 @@ def test_validation_codes_come_before_any_cuda_call_and_there_is_no_fallback():
     assert code(variables=v1) == 2                                            # G >= 2: nut[M*1] (src/mc_code.rs:356)
     if not os.path.exists("/dev/nvidiactl"):
         assert code() == 6                                                    # well-formed: NRAPS_ERR_CUDA, no CPU path
+    L = _lib.lib()
+    assert L.nraps_mc_select_lane(None, 0) == 1 and L.nraps_mc_transport(None, 0, 0, 1, None) == 1   # NRAPS_ERR_NULL: no context, no work
 
 
 def test_python_mirror_refuses_arrays_shorter_than_the_abi_reads():
